@@ -1,0 +1,124 @@
+"""ctypes binding of include/cdgvae.h.  Loading fails loudly: there is no CPU or PyTorch fallback."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_NODE, MAX_DEC, MAX_FLOW, MAX_LAYERS, MAX_SPANS, MAX_SEG = 8, 8, 2, 4, 64, 32
+SCM = {"linear": 0, "nonlinear": 1}
+GEMM_MODES = {"auto": 0, "simt": 1, "tc3x": 2, "tc1x": 3}
+TAB_KIND = {"loan": 0, "adult": 1, "covtype": 2, "tvae": 3}
+
+
+class Linear(C.Structure):
+    _fields_ = [("w", C.c_int64), ("b", C.c_int64), ("in_", C.c_int32), ("out", C.c_int32)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("n_seg", C.c_int32), ("seg_off", C.c_int64 * MAX_SEG), ("seg_len", C.c_int64 * MAX_SEG),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("grad_scale", C.c_float), ("step", C.c_int32),
+                ("clamp_off", C.c_int64), ("clamp_len", C.c_int64), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float)]
+
+
+class PendulumConfig(C.Structure):
+    _fields_ = [("node", C.c_int32), ("n_dec", C.c_int32), ("factor", C.c_int32 * MAX_DEC),
+                ("col_lo", C.c_int32 * MAX_DEC), ("col_hi", C.c_int32 * MAX_DEC), ("scm", C.c_int32),
+                ("flow_num", C.c_int32), ("input_dim", C.c_int32), ("hidden", C.c_int32), ("gemm_mode", C.c_int32),
+                ("n_params", C.c_int64), ("enc", Linear * 3), ("dec", (Linear * 3) * MAX_DEC),
+                ("flow_off", C.c_int64 * MAX_NODE), ("I_B_inv", C.c_float * (MAX_NODE * MAX_NODE)),
+                ("beta", C.c_float), ("lambda_", C.c_float)]
+
+
+class PendulumIO(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("ld_y", C.c_int32),
+                ("noise", C.c_void_p), ("batch", C.c_int64), ("x_l", C.c_void_p), ("y_l", C.c_void_p),
+                ("ld_y_l", C.c_int32), ("batch_l", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p)]
+
+
+class PendulumFwdIO(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("x", C.c_void_p), ("noise", C.c_void_p), ("latent_in", C.c_void_p), ("batch", C.c_int64),
+                ("deterministic", C.c_int32), ("mean", C.c_void_p), ("logvar", C.c_void_p), ("epsilon", C.c_void_p),
+                ("orig_latent", C.c_void_p), ("latent", C.c_void_p), ("align_latent", C.c_void_p),
+                ("xhat_separated", C.c_void_p), ("xhat", C.c_void_p)]
+
+
+class TabularConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("node", C.c_int32), ("n_dec", C.c_int32), ("factor", C.c_int32 * MAX_DEC),
+                ("out_dim", C.c_int32 * MAX_DEC), ("scm", C.c_int32), ("flow_num", C.c_int32),
+                ("input_dim", C.c_int32), ("act", C.c_int32), ("n_enc_layers", C.c_int32),
+                ("n_dec_layers", C.c_int32), ("enc", Linear * MAX_LAYERS), ("dec", (Linear * MAX_LAYERS) * MAX_DEC),
+                ("flow_off", C.c_int64 * MAX_NODE), ("sigma_off", C.c_int64), ("flatten_topology", C.c_int32 * 16),
+                ("n_span", C.c_int32), ("span_start", C.c_int32 * MAX_SPANS), ("span_dim", C.c_int32 * MAX_SPANS),
+                ("span_kind", C.c_int32 * MAX_SPANS), ("n_params", C.c_int64),
+                ("I_B_inv", C.c_float * (MAX_NODE * MAX_NODE)), ("beta", C.c_float), ("lambda_", C.c_float)]
+
+
+class TabularIO(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("noise", C.c_void_p),
+                ("batch", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p), ("latents", C.c_void_p)]
+
+
+# every symbol include/cdgvae.h declares
+EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_adam_step", "cdg_pendulum_create",
+           "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_forward_backward",
+           "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
+           "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm"]
+
+_lib = None
+
+
+def lib():
+    """Load libcdgvae_sm100.so (building it first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on the box: a prebuilt library must be present
+            if not os.path.exists(path):
+                raise RuntimeError(f"libcdgvae_sm100.so is missing and cannot be built: {e}") from e
+    if not os.path.exists(path):
+        raise RuntimeError("libcdgvae_sm100.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
+    L.cdg_last_error.restype = C.c_char_p
+    L.cdg_pendulum_workspace_bytes.restype = C.c_int64
+    L.cdg_pendulum_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.cdg_pendulum_create.argtypes = [C.POINTER(PendulumConfig), C.POINTER(C.c_void_p)]
+    L.cdg_pendulum_destroy.argtypes = [C.c_void_p]
+    L.cdg_pendulum_destroy.restype = None
+    L.cdg_pendulum_forward_backward.argtypes = [C.c_void_p, C.POINTER(PendulumIO), C.c_void_p]
+    L.cdg_pendulum_forward.argtypes = [C.c_void_p, C.POINTER(PendulumFwdIO), C.c_void_p]
+    L.cdg_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamArgs), C.c_void_p]
+    L.cdg_tabular_workspace_bytes.restype = C.c_int64
+    L.cdg_tabular_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.cdg_tabular_create.argtypes = [C.POINTER(TabularConfig), C.POINTER(C.c_void_p)]
+    L.cdg_tabular_destroy.argtypes = [C.c_void_p]
+    L.cdg_tabular_destroy.restype = None
+    L.cdg_tabular_forward_backward.argtypes = [C.c_void_p, C.POINTER(TabularIO), C.c_void_p]
+    L.cdg_tabular_forward.argtypes = [C.c_void_p, C.POINTER(TabularIO), C.c_int32, C.c_void_p]
+    L.cdg_gemm.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                           C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().cdg_last_error().decode()
+        if rc == 1:
+            raise ValueError(msg)
+        raise RuntimeError(f"libcdgvae_sm100 error {rc}: {msg}")
+
+
+def require_cuda(device):
+    import torch
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("cdgvae_b200 runs on sm_100a CUDA devices only (no CPU path); got device %r" % (device,))
+    return dev

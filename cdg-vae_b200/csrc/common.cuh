@@ -1,0 +1,113 @@
+// Shared device/host helpers for libcdgvae_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cdgvae.h"
+
+namespace cdg {
+
+void set_error(const char* fmt, ...);
+
+#define CDG_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            cdg::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,          \
+                           cudaGetErrorString(_e));                                       \
+            return CDG_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define CDG_CHECK_LAUNCH() CDG_CHECK_CUDA(cudaGetLastError())
+
+#define CDG_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            cdg::set_error(__VA_ARGS__);                                                  \
+            return CDG_ERR_INVALID;                                                       \
+        }                                                                                 \
+    } while (0)
+
+#define CDG_TRY(expr)                                                                     \
+    do {                                                                                  \
+        int _r = (expr);                                                                  \
+        if (_r != CDG_OK) return _r;                                                      \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+enum Epi : int {
+    EPI_NONE = 0,       // C = acc (or += when accumulate)
+    EPI_BIAS = 1,       // C = acc + bias[n]
+    EPI_BIAS_ACT = 2,   // C = act(acc + bias[n])
+    EPI_MUL_DACT = 3,   // C = acc * act'(aux[m,n])   (aux holds the post-activation value)
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    // ELU(alpha=1): modules/model.py:221 (nn.ELU);  ReLU: tabular/modules/model.py:373
+    if (act == CDG_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v > 0.f ? v : 0.f;
+}
+// derivative expressed through the post-activation value h
+__device__ __forceinline__ float act_bwd_from_out(float h, int act) {
+    if (act == CDG_ACT_ELU) return h > 0.f ? 1.f : h + 1.f;
+    return h > 0.f ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result valid on thread 0.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? smem[lane] : T(0);
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// ---- generic strided GEMM interface (implemented in gemm_simt.cu / gemm_tc.cu) ----
+struct GemmDesc {
+    const float* A; int64_t sa_m, sa_k;
+    const float* B; int64_t sb_n, sb_k;
+    float* C; int64_t ldc;
+    int64_t M, N, K;
+    int epi = EPI_NONE;
+    int act = CDG_ACT_ELU;
+    const float* bias = nullptr;     // [N]
+    const float* aux = nullptr;      // [M, ld_aux]
+    int64_t ld_aux = 0;
+    int accumulate = 0;              // C += result (EPI_NONE only)
+};
+
+int gemm_simt(const GemmDesc& g, cudaStream_t s);
+// tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the
+// dispatcher can route it to the SIMT kernel.
+int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int gemm_dispatch(int mode, const GemmDesc& g, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+
+int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,
+                    const float* aux, int64_t ld_aux, cudaStream_t s);
+int launch_colsum(const float* G, int64_t ld, int64_t M, int64_t N, float* out, cudaStream_t s);
+
+}  // namespace cdg

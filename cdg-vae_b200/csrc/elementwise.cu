@@ -1,0 +1,174 @@
+// Memory-bound fused kernels of the training step: masked-sum/tanh/MSE reconstruction head
+// with its backward, fused Adam over the flat arena, and the per-step log row.
+#include "latent.cuh"
+#include "elementwise.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+
+namespace cdg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- reconstruction head (modules/model.py:285-287 + modules/train.py:175) ---------------
+//   xhat = tanh(pre)   (pre already holds the masked sum: decoder k wrote only its live columns)
+//   recon += 0.5 * (xhat - x)^2 ;  pre <- d recon / d pre = (xhat - x) (1 - xhat^2) / batch
+template <int VEC>
+__global__ void __launch_bounds__(256) recon_kernel(float* __restrict__ pre, const float* __restrict__ x,
+                                                    float* __restrict__ xhat, int64_t total, float inv_batch,
+                                                    double* acc, int write_grad) {
+    __shared__ double red[32];
+    double local = 0.0;
+    const int64_t nvec = total / VEC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float p[VEC], xv[VEC], xh[VEC];
+        if (VEC == 4) {
+            const float4 a = reinterpret_cast<const float4*>(pre)[i];
+            p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
+            if (x) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+                xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
+            }
+        } else {
+            p[0] = pre[i];
+            if (x) xv[0] = x[i];
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            xh[j] = tanhf(p[j]);
+            if (x) {
+                const float df = xh[j] - xv[j];
+                s += 0.5f * df * df;
+                p[j] = df * (1.f - xh[j] * xh[j]) * inv_batch;
+            }
+        }
+        local += (double)s;
+        if (VEC == 4) {
+            if (write_grad) reinterpret_cast<float4*>(pre)[i] = make_float4(p[0], p[1], p[2], p[3]);
+            if (xhat) reinterpret_cast<float4*>(xhat)[i] = make_float4(xh[0], xh[1], xh[2], xh[3]);
+        } else {
+            if (write_grad) pre[i] = p[0];
+            if (xhat) xhat[i] = xh[0];
+        }
+    }
+    if (acc) {
+        const double s = block_sum<double>(local, red);
+        if (threadIdx.x == 0) atomicAdd(acc + ACC_RECON, s);
+    }
+}
+
+int launch_recon(float* pre, const float* x, float* xhat, int64_t batch, int64_t P, double* acc, int write_grad,
+                 cudaStream_t s) {
+    const int64_t total = batch * P;
+    if (total == 0) return CDG_OK;
+    const float inv_b = 1.f / (float)batch;
+    const bool vec = (total % 4 == 0) && (((uintptr_t)pre | (uintptr_t)x | (uintptr_t)xhat) % 16 == 0);
+    const int64_t n = vec ? total / 4 : total;
+    const int blocks = (int)imin64((n + 255) / 256, kNumSMs * 16);
+    if (vec) recon_kernel<4><<<blocks, 256, 0, s>>>(pre, x, xhat, total, inv_b, acc, write_grad);
+    else recon_kernel<1><<<blocks, 256, 0, s>>>(pre, x, xhat, total, inv_b, acc, write_grad);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+// ---- log row (modules/train.py:198-207) --------------------------------------------------
+__global__ void finalize_logs_kernel(double* acc, float* logs, int d, float recon_div, float kl_div, float align_div,
+                                     float beta, float lambda_) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float recon = (float)(acc[ACC_RECON] / (double)recon_div);
+        const float kl = (float)(acc[ACC_KL] / (double)kl_div);
+        const float al = (float)(acc[ACC_ALIGN] / (double)align_div);
+        float loss = recon + beta * kl;
+        loss += lambda_ * al;
+        logs[0] = loss; logs[1] = recon; logs[2] = kl; logs[3] = al;
+        for (int i = 0; i < d; ++i) logs[4 + i] = (float)(acc[ACC_VAR + i] / (double)kl_div);
+        for (int i = 0; i < ACC_LEN; ++i) acc[i] = 0.0;
+    }
+}
+
+int launch_finalize_logs(double* acc, float* logs, int d, float recon_div, float kl_div, float align_div, float beta,
+                         float lambda_, cudaStream_t s) {
+    finalize_logs_kernel<<<1, 32, 0, s>>>(acc, logs, d, recon_div, kl_div, align_div, beta, lambda_);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+// ---- Adam (torch/optim/adam.py::_single_tensor_adam, amsgrad=False) ----------------------
+struct AdamK {
+    int64_t off[CDG_MAX_SEG], len[CDG_MAX_SEG];
+    float one_minus_b1, b2, one_minus_b2, eps, wd, gscale, step_size, bc2_sqrt;
+    int64_t clamp_off, clamp_len;
+    float clamp_lo, clamp_hi;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, AdamK k) {
+    const int64_t off = k.off[blockIdx.y], len = k.len[blockIdx.y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = off + i;
+        float pj = p[j];
+        float gj = g[j] * k.gscale;
+        if (k.wd != 0.f) gj = gj + k.wd * pj;                         // coupled L2 (main_tvae.py:196-200)
+        float mj = m[j], vj = v[j];
+        mj = mj + k.one_minus_b1 * (gj - mj);                          // exp_avg.lerp_(grad, 1 - beta1)
+        vj = vj * k.b2 + k.one_minus_b2 * gj * gj;                     // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        const float denom = sqrtf(vj) / k.bc2_sqrt + k.eps;        // (sqrt(v) / sqrt(bc2)).add_(eps)
+        pj = pj - k.step_size * (mj / denom);                          // addcdiv_(m, denom, -lr / bc1)
+        if (j >= k.clamp_off && j < k.clamp_off + k.clamp_len)         // sigma.data.clamp_ (train.py:314)
+            pj = fminf(fmaxf(pj, k.clamp_lo), k.clamp_hi);
+        p[j] = pj; m[j] = mj; v[j] = vj;
+    }
+}
+
+}  // namespace cdg
+
+extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                             const cdg_adam_args* a, void* stream) {
+    using namespace cdg;
+    CDG_REQUIRE(params && grads && exp_avg && exp_avg_sq && a, "cdg_adam_step: null argument");
+    CDG_REQUIRE(a->n_seg >= 0 && a->n_seg <= CDG_MAX_SEG, "cdg_adam_step: n_seg out of range");
+    CDG_REQUIRE(a->step >= 1, "cdg_adam_step: step must be >= 1");
+    if (a->n_seg == 0) return CDG_OK;
+    AdamK k;
+    int64_t maxlen = 0;
+    for (int i = 0; i < a->n_seg; ++i) {
+        k.off[i] = a->seg_off[i];
+        k.len[i] = a->seg_len[i];
+        CDG_REQUIRE(k.off[i] >= 0 && k.len[i] >= 0, "cdg_adam_step: bad segment");
+        if (k.len[i] > maxlen) maxlen = k.len[i];
+    }
+    const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
+    const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
+    k.one_minus_b1 = (float)(1.0 - a->beta1);
+    k.b2 = (float)a->beta2;
+    k.one_minus_b2 = (float)(1.0 - a->beta2);
+    k.eps = (float)a->eps;
+    k.wd = (float)a->weight_decay;
+    k.gscale = a->grad_scale;
+    k.step_size = (float)(a->lr / bc1);
+    k.bc2_sqrt = (float)sqrt(bc2);
+    k.clamp_off = a->clamp_off; k.clamp_len = a->clamp_len; k.clamp_lo = a->clamp_lo; k.clamp_hi = a->clamp_hi;
+    if (maxlen == 0) return CDG_OK;
+    const int bx = (int)imin64((maxlen + 255) / 256, kNumSMs * 8);
+    adam_kernel<<<dim3(bx, a->n_seg), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, k);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+extern "C" const char* cdg_last_error(void) { return cdg::get_error(); }
+extern "C" int cdg_version(void) { return 100; }
+extern "C" int cdg_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    return prop.major == 10 ? 1 : 0;
+}

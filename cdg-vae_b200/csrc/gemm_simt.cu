@@ -1,0 +1,197 @@
+// FP32 CUDA-core GEMM with arbitrary operand strides.
+//   C[m,n] = sum_k A[m*sa_m + k*sa_k] * B[n*sb_n + k*sb_k]
+// It serves (i) every contraction whose shape cannot feed a tcgen05 tile (N = 2d = 8 encoder
+// head, K in {1,2} decoder inputs: modules/model.py:224, :245), (ii) split-K reductions at the
+// reference batch size, and (iii) the on-device cross-check of the tensor-core kernel.
+#include "common.cuh"
+
+namespace cdg {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+
+struct SimtArgs {
+    GemmDesc g;
+    int k_chunk;      // K range handled by one blockIdx.z
+    int atomic;       // split-K: red.add into pre-zeroed / accumulated C
+};
+
+template <bool A_MCONTIG, bool B_NCONTIG>
+__global__ void __launch_bounds__(NT, 2) gemm_simt_kernel(SimtArgs a) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const GemmDesc& g = a.g;
+    const int t = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    const int64_t kbeg = (int64_t)blockIdx.z * a.k_chunk;
+    const int64_t kend = min(g.K, kbeg + (int64_t)a.k_chunk);
+    const int tx = t & 15, ty = t >> 4;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        // ---- stage A tile [BM x BK] -> As[k][m] ----
+        if (A_MCONTIG) {
+            const int m = t & (BM - 1);
+#pragma unroll
+            for (int kk = t / BM; kk < BK; kk += NT / BM) {
+                const int64_t gm = m0 + m, gk = k0 + kk;
+                As[kk][m] = (gm < g.M && gk < kend) ? g.A[gm * g.sa_m + gk * g.sa_k] : 0.f;
+            }
+        } else {
+            const int kk = t & (BK - 1);
+#pragma unroll
+            for (int m = t / BK; m < BM; m += NT / BK) {
+                const int64_t gm = m0 + m, gk = k0 + kk;
+                As[kk][m] = (gm < g.M && gk < kend) ? g.A[gm * g.sa_m + gk * g.sa_k] : 0.f;
+            }
+        }
+        if (B_NCONTIG) {
+            const int n = t & (BN - 1);
+#pragma unroll
+            for (int kk = t / BN; kk < BK; kk += NT / BN) {
+                const int64_t gn = n0 + n, gk = k0 + kk;
+                Bs[kk][n] = (gn < g.N && gk < kend) ? g.B[gn * g.sb_n + gk * g.sb_k] : 0.f;
+            }
+        } else {
+            const int kk = t & (BK - 1);
+#pragma unroll
+            for (int n = t / BK; n < BN; n += NT / BK) {
+                const int64_t gn = n0 + n, gk = k0 + kk;
+                Bs[kk][n] = (gn < g.N && gk < kend) ? g.B[gn * g.sb_n + gk * g.sb_k] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            float* c = g.C + m * g.ldc + n;
+            if (a.atomic) { atomicAdd(c, v); continue; }
+            if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) v += g.bias[n];
+            if (g.epi == EPI_BIAS_ACT) v = act_fwd(v, g.act);
+            if (g.epi == EPI_MUL_DACT) v *= act_bwd_from_out(g.aux[m * g.ld_aux + n], g.act);
+            if (g.accumulate) v += *c;
+            *c = v;
+        }
+    }
+}
+
+__global__ void bias_act_kernel(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,
+                                const float* aux, int64_t ld_aux) {
+    const int64_t total = M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N, n = i - m * N;
+        float v = C[m * ldc + n];
+        if (epi == EPI_BIAS || epi == EPI_BIAS_ACT) v += bias[n];
+        if (epi == EPI_BIAS_ACT) v = act_fwd(v, act);
+        if (epi == EPI_MUL_DACT) v *= act_bwd_from_out(aux[m * ld_aux + n], act);
+        C[m * ldc + n] = v;
+    }
+}
+
+int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,
+                    const float* aux, int64_t ld_aux, cudaStream_t s) {
+    if (M * N == 0 || epi == EPI_NONE) return CDG_OK;
+    const int64_t total = M * N;
+    const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 8);
+    bias_act_kernel<<<blocks, 256, 0, s>>>(C, ldc, M, N, bias, epi, act, aux, ld_aux);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+// out[n] += sum_m G[m*ld + n]   (bias gradients: the batch sum autograd performs for nn.Linear)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ G, int64_t ld, int64_t M, int64_t N,
+                                                     float* __restrict__ out, int rows_per_block) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+    const int64_t mbeg = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t mend = min(M, mbeg + rows_per_block);
+    float s = 0.f;
+    if (n < N)
+        for (int64_t m = mbeg + r; m < mend; m += 8) s += G[m * ld + n];
+    red[r][lane] = s;
+    __syncthreads();
+    if (r == 0 && n < N) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += red[i][lane];
+        atomicAdd(out + n, s);
+    }
+}
+
+int launch_colsum(const float* G, int64_t ld, int64_t M, int64_t N, float* out, cudaStream_t s) {
+    if (M == 0 || N == 0) return CDG_OK;
+    const int cb = (int)((N + 31) / 32);
+    int rsplit = (int)imin64((M + 255) / 256, imax64(1, (kNumSMs * 4) / cb));
+    const int rows = (int)((M + rsplit - 1) / rsplit);
+    rsplit = (int)((M + rows - 1) / rows);
+    colsum_kernel<<<dim3(cb, rsplit), 256, 0, s>>>(G, ld, M, N, out, rows);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+int gemm_simt(const GemmDesc& g, cudaStream_t s) {
+    if (g.M == 0 || g.N == 0) return CDG_OK;
+    CDG_REQUIRE(g.K >= 0 && g.M > 0 && g.N > 0, "gemm_simt: bad shape");
+    const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+    CDG_REQUIRE(tm <= 65535, "gemm_simt: M too large for grid.y");
+    // split-K when the tile grid cannot fill the chip and K is long
+    int splits = 1;
+    const int64_t tiles = tm * tn;
+    if (tiles < kNumSMs && g.K >= 512) {
+        splits = (int)imin64((2 * kNumSMs + tiles - 1) / tiles, g.K / 128);
+        splits = (int)imax64(1, imin64(splits, 256));
+    }
+    int k_chunk = (int)(((g.K + splits - 1) / splits + BK - 1) / BK * BK);
+    if (k_chunk <= 0) k_chunk = BK;
+    splits = (int)((g.K + k_chunk - 1) / k_chunk);
+    if (splits < 1) splits = 1;
+    SimtArgs a;
+    a.g = g;
+    a.k_chunk = k_chunk;
+    a.atomic = splits > 1;
+    if (a.atomic && !g.accumulate) {
+        if (g.ldc == g.N) {
+            CDG_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * g.M * g.N, s));
+        } else {
+            CDG_CHECK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, s));
+        }
+    }
+    dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+    const bool am = (g.sa_m == 1 && g.sa_k != 1), bn = (g.sb_n == 1 && g.sb_k != 1);
+    if (am && bn) gemm_simt_kernel<true, true><<<grid, NT, 0, s>>>(a);
+    else if (am) gemm_simt_kernel<true, false><<<grid, NT, 0, s>>>(a);
+    else if (bn) gemm_simt_kernel<false, true><<<grid, NT, 0, s>>>(a);
+    else gemm_simt_kernel<false, false><<<grid, NT, 0, s>>>(a);
+    CDG_CHECK_LAUNCH();
+    if (a.atomic && g.epi != EPI_NONE)
+        CDG_TRY(launch_bias_act(g.C, g.ldc, g.M, g.N, g.bias, g.epi, g.act, g.aux, g.ld_aux, s));
+    return CDG_OK;
+}
+
+}  // namespace cdg

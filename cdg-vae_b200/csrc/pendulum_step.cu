@@ -1,0 +1,326 @@
+// Host orchestration of the pendulum CDG-VAE step: the launch sequence that replaces
+// CDGVAE.forward (modules/model.py:290-304), the loss assembly and loss.backward() of
+// train_CDGVAE / train_CDGVAE_semi (modules/train.py:168-202, :235-278).
+//
+// Observable-equivalent shortcuts, each covered by a parity test:
+//   * the encoder runs once per batch; the deterministic pass reuses `mean` (model.py:292 vs :300);
+//   * decoder k's last Linear is evaluated only on the columns its {0,1} mask keeps
+//     (model.py:284-286); masked-out weights get exactly zero gradient in the reference too;
+//   * in the semi-supervised step the unlabeled deterministic pass is skipped (train.py:241 vs :261).
+#include "latent.cuh"
+#include "elementwise.cuh"
+
+#include <new>
+
+struct cdg_pendulum_plan {
+    cdg_pendulum_config c;
+    int lat_off[CDG_MAX_DEC];   // first latent column of decoder k
+};
+
+namespace cdg {
+
+static inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }
+
+struct PendWs {
+    int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, total;
+    int64_t gemm_ws_floats;
+};
+
+static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL) {
+    PendWs w;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += pad64(n); return r; };
+    const int64_t H = c.hidden, d = c.node, P = c.input_dim;
+    const int64_t Bal = BL > 0 ? BL : B;
+    w.acc = take(2 * ACC_LEN + 2);
+    w.h1 = take(B * H); w.h2 = take(B * H); w.ml = take(B * 2 * d);
+    w.eps = take(B * d); w.u = take(B * d); w.z = take(B * d);
+    w.zal = take(Bal * d); w.g_align = take(Bal * 2 * d);
+    for (int k = 0; k < c.n_dec; ++k) { w.a1[k] = take(B * H); w.a2[k] = take(B * H); }
+    w.pre = take(B * P);
+    w.ga2 = take(B * H); w.ga1 = take(B * H); w.g_z = take(B * d); w.g_ml = take(B * 2 * d);
+    w.g_h2 = take(B * H); w.g_h1 = take(B * H);
+    w.h1l = take(BL * H); w.h2l = take(BL * H); w.mll = take(BL * 2 * d);
+    w.g_h2l = take(BL * H); w.g_h1l = take(BL * H);
+    w.gemm_ws_floats = 1 << 16;
+    w.gemm_ws = take(w.gemm_ws_floats);
+    w.total = o;
+    return w;
+}
+
+struct Ctx {
+    const cdg_pendulum_plan* p;
+    const float* P;   // params
+    float* G;         // grads (may be null in forward-only)
+    float* W;         // workspace base
+    PendWs w;
+    cudaStream_t s;
+    int mode;
+};
+
+// Y[M,N] = act(X[M,K] W[N,K]^T + b)   (nn.Linear forward)
+static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
+                      float* Y, int64_t ldy, int64_t M, bool act) {
+    GemmDesc g;
+    g.A = X; g.sa_m = ldx; g.sa_k = 1;
+    g.B = c.P + L.w + row_lo * L.in; g.sb_n = L.in; g.sb_k = 1;
+    g.C = Y; g.ldc = ldy; g.M = M; g.N = n_rows; g.K = L.in;
+    g.epi = act ? EPI_BIAS_ACT : EPI_BIAS; g.act = CDG_ACT_ELU; g.bias = c.P + L.b + row_lo;
+    return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+}
+// dW[rows,K] += dY[M,rows]^T X[M,K];  db[rows] += colsum(dY)
+static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float* X, int64_t ldx, const cdg_linear& L,
+                        int64_t row_lo, int64_t n_rows, int64_t M) {
+    GemmDesc g;
+    g.A = dY; g.sa_m = 1; g.sa_k = ldy;
+    g.B = X; g.sb_n = 1; g.sb_k = ldx;
+    g.C = c.G + L.w + row_lo * L.in; g.ldc = L.in; g.M = n_rows; g.N = L.in; g.K = M;
+    g.epi = EPI_NONE; g.accumulate = 1;
+    CDG_TRY(gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s));
+    return launch_colsum(dY, ldy, M, n_rows, c.G + L.b + row_lo, c.s);
+}
+// dX[M,K] = (dY[M,rows] W[rows,K]) * act'(Hout)      (Hout == nullptr: no activation in front)
+static int linear_dgrad(const Ctx& c, const float* dY, int64_t ldy, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
+                        float* dX, int64_t lddx, const float* Hout, int64_t ldh, int64_t M) {
+    GemmDesc g;
+    g.A = dY; g.sa_m = ldy; g.sa_k = 1;
+    g.B = c.P + L.w + row_lo * L.in; g.sb_n = 1; g.sb_k = L.in;
+    g.C = dX; g.ldc = lddx; g.M = M; g.N = L.in; g.K = n_rows;
+    if (Hout) { g.epi = EPI_MUL_DACT; g.act = CDG_ACT_ELU; g.aux = Hout; g.ld_aux = ldh; }
+    return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+}
+
+static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.d = c.node; a.scm = c.scm; a.flow_num = c.flow_num;
+    for (int i = 0; i < c.node; ++i) a.flow_off[i] = c.flow_off[i];
+    for (int i = 0; i < c.node * c.node; ++i) a.A[i] = c.I_B_inv[i];
+    a.beta = c.beta; a.lambda_ = c.lambda_;
+}
+
+static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float* h2, float* ml) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node;
+    CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true));
+    CDG_TRY(linear_fwd(c, h1, H, cf.enc[1], 0, H, h2, H, B, true));
+    CDG_TRY(linear_fwd(c, h2, H, cf.enc[2], 0, 2 * d, ml, 2 * d, B, false));
+    return CDG_OK;
+}
+
+static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1, const float* h2, const float* g_ml,
+                       float* g_h2, float* g_h1) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node;
+    CDG_TRY(linear_wgrad(c, g_ml, 2 * d, h2, H, cf.enc[2], 0, 2 * d, B));
+    CDG_TRY(linear_dgrad(c, g_ml, 2 * d, cf.enc[2], 0, 2 * d, g_h2, H, h2, H, B));
+    CDG_TRY(linear_wgrad(c, g_h2, H, h1, H, cf.enc[1], 0, H, B));
+    CDG_TRY(linear_dgrad(c, g_h2, H, cf.enc[1], 0, H, g_h1, H, h1, H, B));
+    CDG_TRY(linear_wgrad(c, g_h1, H, x, cf.input_dim, cf.enc[0], 0, H, B));
+    return CDG_OK;
+}
+
+// decoders: z[B,d] -> pre[B,P] (live columns only)
+static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node, P = cf.input_dim;
+    for (int k = 0; k < cf.n_dec; ++k) {
+        float* a1 = c.W + c.w.a1[k];
+        float* a2 = c.W + c.w.a2[k];
+        CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
+        CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
+        const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
+        if (n > 0) CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], lo, n, pre + lo, P, B, false));
+    }
+    return CDG_OK;
+}
+
+static bool covers_all(const cdg_pendulum_config& c) {
+    // live ranges are validated disjoint at create time; full cover <=> widths sum to P
+    int64_t s = 0;
+    for (int k = 0; k < c.n_dec; ++k) s += c.col_hi[k] - c.col_lo[k];
+    return s == c.input_dim;
+}
+
+}  // namespace cdg
+
+using namespace cdg;
+
+extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_plan** out) {
+    CDG_REQUIRE(cfg && out, "cdg_pendulum_create: null argument");
+    const cdg_pendulum_config& c = *cfg;
+    CDG_REQUIRE(c.node >= 1 && c.node <= CDG_MAX_NODE, "node=%d out of range [1,%d]", c.node, CDG_MAX_NODE);
+    CDG_REQUIRE(c.n_dec >= 1 && c.n_dec <= CDG_MAX_DEC, "n_dec=%d out of range", c.n_dec);
+    CDG_REQUIRE(c.scm == CDG_SCM_LINEAR || c.scm == CDG_SCM_PLANAR, "Not supported SCM!");
+    CDG_REQUIRE(c.flow_num >= 1 && c.flow_num <= CDG_MAX_FLOW, "flow_num=%d out of range [1,%d]", c.flow_num, CDG_MAX_FLOW);
+    int s = 0;
+    for (int k = 0; k < c.n_dec; ++k) {
+        CDG_REQUIRE(c.factor[k] >= 1, "factor[%d] must be >= 1", k);
+        s += c.factor[k];
+        CDG_REQUIRE(0 <= c.col_lo[k] && c.col_lo[k] <= c.col_hi[k] && c.col_hi[k] <= c.input_dim, "mask range %d invalid", k);
+        for (int j = 0; j < k; ++j)
+            CDG_REQUIRE(c.col_hi[j] <= c.col_lo[k] || c.col_hi[k] <= c.col_lo[j], "mask ranges %d and %d overlap", j, k);
+        CDG_REQUIRE(c.dec[k][0].in == c.factor[k] && c.dec[k][2].out == c.input_dim, "decoder %d shape mismatch", k);
+    }
+    CDG_REQUIRE(s == c.node, "sum(factor) != node");               // modules/model.py:214
+    CDG_REQUIRE(c.enc[0].in == c.input_dim && c.enc[2].out == 2 * c.node, "encoder shape mismatch");
+    cdg_pendulum_plan* p = new (std::nothrow) cdg_pendulum_plan;
+    CDG_REQUIRE(p, "out of host memory");
+    p->c = c;
+    int off = 0;
+    for (int k = 0; k < c.n_dec; ++k) { p->lat_off[k] = off; off += c.factor[k]; }
+    *out = p;
+    return CDG_OK;
+}
+
+extern "C" void cdg_pendulum_destroy(cdg_pendulum_plan* p) { delete p; }
+
+extern "C" int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l) {
+    if (!p || batch < 0 || batch_l < 0) return -1;
+    return pend_layout(p->c, batch, batch_l).total * 4;
+}
+
+extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pendulum_io* io, void* stream) {
+    CDG_REQUIRE(p && io, "cdg_pendulum_forward_backward: null argument");
+    CDG_REQUIRE(io->params && io->grads && io->workspace && io->x && io->noise && io->logs, "null buffer");
+    const cdg_pendulum_config& cf = p->c;
+    const int64_t B = io->batch, BL = io->x_l ? io->batch_l : 0;
+    const bool semi = io->x_l != nullptr;
+    CDG_REQUIRE(B > 0, "empty batch");
+    CDG_REQUIRE(semi ? (io->y_l && BL > 0 && io->ld_y_l >= cf.node) : (io->y && io->ld_y >= cf.node), "labels missing");
+    Ctx c;
+    c.p = p; c.P = io->params; c.G = io->grads; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
+    c.mode = cf.gemm_mode;
+    c.w = pend_layout(cf, B, BL);
+    if (c.w.total * 4 > io->workspace_bytes) {
+        set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
+        return CDG_ERR_WORKSPACE;
+    }
+    const int64_t H = cf.hidden, d = cf.node, Pd = cf.input_dim;
+    float* W = c.W;
+    double* acc = (double*)(W + c.w.acc);
+    cudaStream_t s = c.s;
+
+    // optimizer.zero_grad() (train.py:168) + loss accumulators
+    CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * cf.n_params, s));
+    CDG_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_LEN, s));
+    if (!covers_all(cf)) CDG_CHECK_CUDA(cudaMemsetAsync(W + c.w.pre, 0, sizeof(float) * B * Pd, s));
+
+    // ---- forward ----
+    CDG_TRY(encoder_fwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.ml));
+    LatentArgs la;
+    fill_latent(cf, la);
+    la.batch = B; la.params = io->params; la.ml = W + c.w.ml; la.noise = io->noise;
+    la.eps_out = W + c.w.eps; la.u_out = W + c.w.u; la.z_out = W + c.w.z; la.acc = acc;
+    CDG_TRY(launch_latent_fwd(la, s));
+
+    LatentArgs al;
+    fill_latent(cf, al);
+    al.params = io->params; al.grads = io->grads; al.acc = acc;
+    al.z_out = W + c.w.zal; al.g_out = W + c.w.g_align;
+    if (semi) {
+        CDG_TRY(encoder_fwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.mll));
+        al.batch = BL; al.ml = W + c.w.mll; al.y = io->y_l; al.ld_y = io->ld_y_l;
+    } else {
+        al.batch = B; al.ml = W + c.w.ml; al.y = io->y; al.ld_y = io->ld_y;
+    }
+    CDG_TRY(launch_align(al, s));
+
+    CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
+    CDG_TRY(launch_recon(W + c.w.pre, io->x, io->xhat, B, Pd, acc, 1, s));
+
+    // ---- backward ----
+    float* g_pre = W + c.w.pre;
+    float* ga2 = W + c.w.ga2;
+    float* ga1 = W + c.w.ga1;
+    float* g_z = W + c.w.g_z;
+    for (int k = 0; k < cf.n_dec; ++k) {
+        const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
+        const float* a1 = W + c.w.a1[k];
+        const float* a2 = W + c.w.a2[k];
+        const float* zk = W + c.w.z + p->lat_off[k];
+        if (n > 0) {
+            CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B));
+            CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B));
+        } else {
+            CDG_CHECK_CUDA(cudaMemsetAsync(ga2, 0, sizeof(float) * B * H, s));
+        }
+        CDG_TRY(linear_wgrad(c, ga2, H, a1, H, cf.dec[k][1], 0, H, B));
+        CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B));
+        CDG_TRY(linear_wgrad(c, ga1, H, zk, d, cf.dec[k][0], 0, H, B));
+        CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, g_z + p->lat_off[k], d, nullptr, 0, B));
+    }
+    LatentArgs lb;
+    fill_latent(cf, lb);
+    lb.batch = B; lb.params = io->params; lb.grads = io->grads; lb.ml = W + c.w.ml; lb.noise = io->noise;
+    lb.u_in = W + c.w.u; lb.g_z = g_z; lb.g_align = semi ? nullptr : W + c.w.g_align; lb.g_out = W + c.w.g_ml;
+    CDG_TRY(launch_latent_bwd(lb, s));
+    CDG_TRY(encoder_bwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.g_ml, W + c.w.g_h2, W + c.w.g_h1));
+    if (semi)
+        CDG_TRY(encoder_bwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.g_align, W + c.w.g_h2l, W + c.w.g_h1l));
+
+    CDG_TRY(launch_finalize_logs(acc, io->logs, (int)d, (float)B, (float)B, (float)(semi ? BL : B), cf.beta, cf.lambda_, s));
+    return CDG_OK;
+}
+
+extern "C" int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd_io* io, void* stream) {
+    CDG_REQUIRE(p && io, "cdg_pendulum_forward: null argument");
+    CDG_REQUIRE(io->params && io->workspace && (io->x || io->latent_in), "null buffer");
+    const cdg_pendulum_config& cf = p->c;
+    const int64_t B = io->batch;
+    CDG_REQUIRE(B > 0, "empty batch");
+    Ctx c;
+    c.p = p; c.P = io->params; c.G = nullptr; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
+    c.mode = cf.gemm_mode;
+    c.w = pend_layout(cf, B, 0);
+    if (c.w.total * 4 > io->workspace_bytes) {
+        set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
+        return CDG_ERR_WORKSPACE;
+    }
+    const int64_t H = cf.hidden, d = cf.node, Pd = cf.input_dim;
+    float* W = c.W;
+    cudaStream_t s = c.s;
+    const float* z = io->latent_in;
+    if (io->x) {
+        CDG_REQUIRE(io->deterministic || io->noise, "noise missing");
+        CDG_TRY(encoder_fwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.ml));
+        LatentArgs la;
+        fill_latent(cf, la);
+        la.batch = B; la.params = io->params; la.ml = W + c.w.ml; la.noise = io->noise; la.deterministic = io->deterministic;
+        la.eps_out = io->epsilon ? io->epsilon : W + c.w.eps;
+        la.u_out = io->orig_latent ? io->orig_latent : W + c.w.u;
+        la.z_out = io->latent ? io->latent : W + c.w.z;
+        CDG_TRY(launch_latent_fwd(la, s));
+        if (!z) z = la.z_out;
+        if (io->align_latent) {
+            LatentArgs al;
+            fill_latent(cf, al);
+            al.batch = B; al.params = io->params; al.ml = W + c.w.ml; al.z_out = io->align_latent;
+            CDG_TRY(launch_align(al, s));
+        }
+        if (io->mean)
+            CDG_CHECK_CUDA(cudaMemcpy2DAsync(io->mean, 4 * d, W + c.w.ml, 8 * d, 4 * d, B, cudaMemcpyDeviceToDevice, s));
+        if (io->logvar)
+            CDG_CHECK_CUDA(cudaMemcpy2DAsync(io->logvar, 4 * d, W + c.w.ml + d, 8 * d, 4 * d, B, cudaMemcpyDeviceToDevice, s));
+    }
+    if (io->xhat || io->xhat_separated) {
+        float* pre = io->xhat ? io->xhat : W + c.w.pre;
+        if (!covers_all(cf)) CDG_CHECK_CUDA(cudaMemsetAsync(pre, 0, sizeof(float) * B * Pd, s));
+        CDG_TRY(decoders_fwd(c, z, B, pre));
+        CDG_TRY(launch_recon(pre, nullptr, pre, B, Pd, nullptr, 0, s));       // xhat = tanh(masked sum), in place
+        if (io->xhat_separated)
+            for (int k = 0; k < cf.n_dec; ++k)
+                CDG_TRY(linear_fwd(c, W + c.w.a2[k], H, cf.dec[k][2], 0, Pd, io->xhat_separated + (int64_t)k * B * Pd, Pd, B, false));
+    }
+    return CDG_OK;
+}
+
+extern "C" int cdg_gemm(int mode, const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_n, int64_t sb_k,
+                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+    CDG_REQUIRE(A && B && C, "cdg_gemm: null pointer");
+    GemmDesc g;
+    g.A = A; g.sa_m = sa_m; g.sa_k = sa_k; g.B = B; g.sb_n = sb_n; g.sb_k = sb_k;
+    g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.accumulate = accumulate;
+    return gemm_dispatch(mode, g, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,212 @@
+"""Host-side plumbing shared by the drop-in model classes: the flat fp32 parameter arena the
+nn.Parameters are views of, the binding of a caller-constructed torch.optim.Adam to the arena
+(so that `optimizer.state` holds what the reference would hold), the device log buffer and the
+data-parallel gradient exchange.  All arithmetic happens in libcdgvae_sm100.so.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import dist as _dist
+
+ALIGN = 32  # floats (128 B): keeps every weight 16-B aligned for float4 / TMA access
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t, device):
+    """Bring a batch tensor to the device as contiguous fp32 (the reference does `.cuda()`, train.py:163-165)."""
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32, non_blocking=True)
+    return t.contiguous()
+
+
+class ArenaModule(nn.Module):
+    """nn.Module whose parameters live in one flat arena (params / grads / exp_avg / exp_avg_sq)."""
+
+    _arena = None
+
+    # -- arena ---------------------------------------------------------------------------------
+    def _group_of(self, name):
+        # parameters of one flow node are packed contiguously (the kernels index them as a block)
+        if name.startswith("flows."):
+            return ".".join(name.split(".")[:2])
+        return name
+
+    def _build_arena(self):
+        named = list(self.named_parameters())
+        if not named:
+            return
+        device = named[0][1].device
+        off, offsets, prev = 0, {}, None
+        for name, p in named:
+            g = self._group_of(name)
+            if g != prev:
+                off = (off + ALIGN - 1) // ALIGN * ALIGN
+            offsets[name] = off
+            off += p.numel()
+            prev = g
+        total = (off + ALIGN - 1) // ALIGN * ALIGN
+        arena = torch.zeros(total, dtype=torch.float32, device=device)
+        grads = torch.zeros_like(arena)
+        with torch.no_grad():
+            for name, p in named:
+                o, n = offsets[name], p.numel()
+                arena[o:o + n].copy_(p.data.reshape(-1).to(torch.float32))
+                p.data = arena[o:o + n].view(p.shape)
+                p.grad = None
+        self._arena, self._grads = arena, grads
+        self._exp_avg = self._exp_avg_sq = None
+        self._offsets, self._n_params = offsets, total
+        self._bound_opt = None
+        self._destroy_plan()
+        self._workspace = None
+        self._logs = None
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        self._build_arena()
+        return self
+
+    def _destroy_plan(self):
+        pass
+
+    @property
+    def arena_device(self):
+        return self._arena.device
+
+    def _lin(self, prefix):
+        w, b = prefix + ".weight", prefix + ".bias"
+        shape = dict(self.named_parameters())[w].shape
+        return _lib.Linear(self._offsets[w], self._offsets[b], shape[1], shape[0])
+
+    def _flow_offsets(self, node):
+        first = "p" if self.config["scm"] == "linear" else "w.0"
+        return [self._offsets[f"flows.{i}.{first}"] for i in range(node)]
+
+    def _grad_views(self, live_names=None):
+        """Expose gradients the way autograd would: p.grad is a view of the gradient arena."""
+        for name, p in self.named_parameters():
+            if live_names is not None and name not in live_names:
+                p.grad = None
+                continue
+            o, n = self._offsets[name], p.numel()
+            p.grad = self._grads[o:o + n].view(p.shape)
+
+    # -- workspace / logs ----------------------------------------------------------------------
+    def _get_workspace(self, nbytes):
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes:
+            self._workspace = ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.arena_device)
+        return ws
+
+    def _log_rows(self, n_rows, width):
+        lg = self._logs
+        if lg is None or lg.shape[0] < n_rows or lg.shape[1] != width:
+            new = torch.zeros(max(n_rows, 256 if lg is None else 2 * lg.shape[0]), width, device=self.arena_device)
+            if lg is not None and lg.shape[1] == width:
+                new[: lg.shape[0]].copy_(lg)
+            self._logs = lg = new
+        return lg
+
+    # -- optimizer -----------------------------------------------------------------------------
+    def live_param_names(self):
+        """Parameters that receive a gradient in the reference (all, except covtype's unused decoder)."""
+        return [n for n, _ in self.named_parameters()]
+
+    def adam_segments(self):
+        """(offset, length) ranges of the arena the optimizer touches."""
+        segs = []
+        shapes = {n: p.numel() for n, p in self.named_parameters()}
+        for n in self.live_param_names():
+            segs.append((self._offsets[n], shapes[n]))
+        return self._merge(segs)
+
+    @staticmethod
+    def _merge(segs):
+        out = []
+        for o, ln in sorted(s for s in segs if s[1] > 0):
+            if out and 0 <= o - (out[-1][0] + out[-1][1]) < ALIGN:     # only alignment padding between
+                out[-1] = (out[-1][0], o + ln - out[-1][0])
+            else:
+                out.append((o, ln))
+        return out
+
+    def bind_optimizer(self, opt):
+        """Make `opt.state[p]['exp_avg'|'exp_avg_sq']` views of the arena-shaped moment buffers and
+        remember the hyper-parameters' source.  torch.optim.Adam only (the reference's optimizer)."""
+        if self._bound_opt is opt:
+            return
+        if not isinstance(opt, torch.optim.Adam) or isinstance(opt, torch.optim.AdamW):
+            raise TypeError("the reference trains with torch.optim.Adam; got %s" % type(opt).__name__)
+        mine = {id(p): n for n, p in self.named_parameters()}
+        groups = [g for g in opt.param_groups if any(id(p) in mine for p in g["params"])]
+        if not groups:
+            raise ValueError("optimizer does not hold this model's parameters")
+        for g in groups[1:]:
+            for key in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):
+                if g.get(key) != groups[0].get(key):
+                    raise ValueError("parameter groups with different hyper-parameters are not supported")
+        if groups[0].get("amsgrad") or groups[0].get("maximize"):
+            raise ValueError("amsgrad / maximize are not used by the reference and are not supported")
+        self._opt_group = groups[0]
+        if self._exp_avg is None:
+            self._exp_avg = torch.zeros_like(self._arena)
+            self._exp_avg_sq = torch.zeros_like(self._arena)
+        step = 0
+        self._step_tensors = []
+        live = set(self.live_param_names())
+        for name, p in self.named_parameters():
+            if name not in live:
+                continue
+            st = opt.state[p]
+            o, n = self._offsets[name], p.numel()
+            for key, buf in (("exp_avg", self._exp_avg), ("exp_avg_sq", self._exp_avg_sq)):
+                view = buf[o:o + n].view(p.shape)
+                if key in st and st[key].data_ptr() != view.data_ptr():
+                    view.copy_(st[key])
+                st[key] = view
+            if "step" not in st:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            step = max(step, int(st["step"].item()))
+            self._step_tensors.append(st["step"])
+        self._step_count = step
+        self._bound_opt = opt
+
+    def adam_step(self, grad_scale=1.0, clamp=None):
+        g = self._opt_group
+        a = _lib.AdamArgs()
+        segs = self.adam_segments()
+        if len(segs) > _lib.MAX_SEG:
+            raise RuntimeError("too many Adam segments")
+        a.n_seg = len(segs)
+        for i, (o, n) in enumerate(segs):
+            a.seg_off[i], a.seg_len[i] = o, n
+        lr = g["lr"]
+        a.lr = float(lr.item() if torch.is_tensor(lr) else lr)
+        a.beta1, a.beta2 = float(g["betas"][0]), float(g["betas"][1])
+        a.eps, a.weight_decay = float(g["eps"]), float(g["weight_decay"])
+        a.grad_scale = float(grad_scale)
+        self._step_count += 1
+        a.step = self._step_count
+        if clamp is not None:
+            a.clamp_off, a.clamp_len, a.clamp_lo, a.clamp_hi = clamp
+        else:
+            a.clamp_off, a.clamp_len = -1, 0
+        stream = torch.cuda.current_stream(self.arena_device).cuda_stream
+        _lib.check(_lib.lib().cdg_adam_step(_ptr(self._arena), _ptr(self._grads), _ptr(self._exp_avg),
+                                            _ptr(self._exp_avg_sq), C.byref(a), C.c_void_p(stream)))
+        torch._foreach_add_(self._step_tensors, 1.0)
+
+    # -- data parallel -------------------------------------------------------------------------
+    def exchange_gradients(self):
+        """Sum the gradient arena over the data-parallel ranks.  Returns the factor the
+        optimizer must scale gradients by (1/world)."""
+        return _dist.allreduce_arena(self._grads, self.reduce_ranges())
+
+    def reduce_ranges(self):
+        return self.adam_segments()

@@ -1,0 +1,306 @@
+"""Drop-in for the reference's modules/model.py (pendulum images): same class names, constructor
+signatures, method arities, attribute names and state_dict keys; the arithmetic runs in
+libcdgvae_sm100.so on an sm_100a device.
+
+    CDGVAE(B, mask, config, device)               modules/model.py:208-304
+    InvertiblePriorLinear(device)                  modules/model.py:8-29
+    PlanarFlows(input_dim, flow_num, inverse_loop, device)   modules/model.py:31-100
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import ArenaModule, _f32c, _ptr
+
+
+class InvertiblePriorLinear(nn.Module):
+    """Per-node affine flow o = p[0] * eps + p[1] (modules/model.py:8-29).  Holds the parameter;
+    inside CDGVAE the evaluation is fused into the latent kernels."""
+
+    def __init__(self, device="cpu"):
+        super().__init__()
+        self.p = nn.Parameter(torch.rand([2], device=device) * 0.1)        # model.py:18
+
+    def forward(self, eps, log_determinant=False):
+        o = self.p[0] * eps + self.p[1]
+        logdet = 0
+        if log_determinant:
+            logdet += torch.log(self.p[0].abs()).repeat(eps.size(0), 1)
+        return o, logdet
+
+    def inverse(self, o):
+        return (o - self.p[1]) / self.p[0]
+
+
+class PlanarFlows(nn.Module):
+    """ELU planar flow with the invertibility re-parameterisation of u (modules/model.py:31-100)."""
+
+    def __init__(self, input_dim, flow_num, inverse_loop, device="cpu"):
+        super().__init__()
+        self.input_dim, self.flow_num, self.inverse_loop, self.device = input_dim, flow_num, inverse_loop, device
+        self.alpha = torch.tensor(1, dtype=torch.float32).to(device)
+        self.w = nn.ParameterList([nn.Parameter(torch.randn(input_dim, 1, device=device) * 0.1) for _ in range(flow_num)])
+        self.b = nn.ParameterList([nn.Parameter(torch.randn(1, 1, device=device) * 0.1) for _ in range(flow_num)])
+        self.u = nn.ParameterList([nn.Parameter(torch.randn(input_dim, 1, device=device) * 0.1) for _ in range(flow_num)])
+
+    def build_u(self, u_, w_):
+        wu = w_.t() @ u_
+        return u_ + ((-1 + torch.log(1 + torch.exp(wu))) - wu) * (w_ / torch.norm(w_, p=2) ** 2)
+
+    def inverse(self, inputs):
+        h = inputs
+        for j in reversed(range(self.flow_num)):
+            z = h
+            u_ = self.build_u(self.u[j], self.w[j])
+            for _ in range(self.inverse_loop):
+                z = h - u_.t() * nn.functional.elu(z @ self.w[j] + self.b[j])
+            h = z
+        return h
+
+    def forward(self, inputs, log_determinant=False):
+        h, logdet = inputs, 0
+        for j in range(self.flow_num):
+            u_ = self.build_u(self.u[j], self.w[j])
+            if log_determinant:
+                x = h @ self.w[j] + self.b[j]
+                gradient = torch.where(x > 0, torch.ones_like(x), torch.exp(x))
+                logdet += torch.log((1 + (gradient * self.w[j].squeeze()) @ u_).abs())
+            h = h + u_.t() * nn.functional.elu(h @ self.w[j] + self.b[j])
+        return h, logdet
+
+
+def mask_ranges(mask, n_cols):
+    """Each decoder mask must be the {0,1} indicator of one contiguous range of flattened (H,W,3)
+    columns (the row bands of main.py:167-179), pairwise disjoint.  Returns [(lo, hi)]."""
+    out = []
+    for k, m in enumerate(mask):
+        flat = torch.as_tensor(m).reshape(-1).to("cpu")
+        if flat.numel() != n_cols:
+            raise ValueError(f"mask {k} has {flat.numel()} entries, expected {n_cols}")
+        nz = torch.nonzero(flat).reshape(-1)
+        if nz.numel() == 0:
+            out.append((0, 0))
+            continue
+        lo, hi = int(nz[0]), int(nz[-1]) + 1
+        if hi - lo != nz.numel() or not bool((flat[lo:hi] == 1).all()):
+            raise ValueError(f"mask {k} is not the 0/1 indicator of a contiguous column range; "
+                             "only band masks (main.py:167-179) are supported")
+        out.append((lo, hi))
+    return out
+
+
+class CDGVAE(ArenaModule):
+    HIDDEN = 300
+
+    def __init__(self, B, mask, config, device):
+        super().__init__()
+        self.config = config
+        self.mask = mask
+        assert sum(config["factor"]) == config["node"]              # model.py:214
+        assert len(config["factor"]) == len(mask)                   # model.py:215
+        self.device = device
+        P, H = 3 * config["image_size"] * config["image_size"], self.HIDDEN
+        self._ranges = mask_ranges(mask, P)
+
+        # parameter creation order = reference order (encoder, flows, decoders) for same-seed init
+        self.encoder = nn.Sequential(nn.Linear(P, H), nn.ELU(), nn.Linear(H, H), nn.ELU(),
+                                     nn.Linear(H, config["node"] * 2)).to(device)
+        self.B = B.to(device)
+        self.I = torch.eye(config["node"]).to(device)
+        self._A_host = torch.inverse(torch.eye(config["node"]) - B.detach().to("cpu", torch.float32))
+        self.I_B_inv = self._A_host.to(device)                       # model.py:228-230
+        if config["scm"] == "linear":
+            self.flows = nn.ModuleList([InvertiblePriorLinear(device=device) for _ in range(config["node"])])
+        elif config["scm"] == "nonlinear":
+            self.flows = nn.ModuleList([PlanarFlows(1, config["flow_num"], config["inverse_loop"], device)
+                                        for _ in range(config["node"])])
+        else:
+            raise ValueError("Not supported SCM!")                   # model.py:240
+        self.decoder = nn.ModuleList([
+            nn.Sequential(nn.Linear(k, H), nn.ELU(), nn.Linear(H, H), nn.ELU(), nn.Linear(H, P)).to(device)
+            for k in config["factor"]])
+        self.gemm_mode = config.get("gemm_mode", "auto") if isinstance(config, dict) else "auto"
+        self.noise_fn = None      # tests/bench inject noise; default draws like model.py:276
+        self._plan = None
+        self._build_arena()
+
+    # -- C-ABI plan ------------------------------------------------------------------------------
+    def _destroy_plan(self):
+        if getattr(self, "_plan", None):
+            _lib.lib().cdg_pendulum_destroy(self._plan)
+        self._plan = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def _get_plan(self):
+        cfg = self.config
+        key = (float(cfg.get("beta", 0.0)), float(cfg.get("lambda", 0.0)), self.gemm_mode)
+        if self._plan is not None and self._plan_key == key:
+            return self._plan
+        self._destroy_plan()
+        _lib.require_cuda(self.arena_device)
+        c = _lib.PendulumConfig()
+        d, K = cfg["node"], len(cfg["factor"])
+        if cfg["scm"] == "nonlinear" and cfg["flow_num"] > _lib.MAX_FLOW:
+            raise ValueError(f"flow_num > {_lib.MAX_FLOW} is not supported")
+        c.node, c.n_dec = d, K
+        for k in range(K):
+            c.factor[k] = cfg["factor"][k]
+            c.col_lo[k], c.col_hi[k] = self._ranges[k]
+            for j, idx in enumerate((0, 2, 4)):
+                c.dec[k][j] = self._lin(f"decoder.{k}.{idx}")
+        c.scm, c.flow_num = _lib.SCM[cfg["scm"]], int(cfg.get("flow_num", 1))
+        c.input_dim, c.hidden = 3 * cfg["image_size"] ** 2, self.HIDDEN
+        c.gemm_mode = _lib.GEMM_MODES[self.gemm_mode]
+        c.n_params = self._n_params
+        for j, idx in enumerate((0, 2, 4)):
+            c.enc[j] = self._lin(f"encoder.{idx}")
+        for i, o in enumerate(self._flow_offsets(d)):
+            c.flow_off[i] = o
+        A = self._A_host.reshape(-1).tolist()
+        for i, v in enumerate(A):
+            c.I_B_inv[i] = v
+        c.beta, c.lambda_ = key[0], key[1]
+        plan = C.c_void_p()
+        _lib.check(_lib.lib().cdg_pendulum_create(C.byref(c), C.byref(plan)))
+        self._plan, self._plan_key = plan, key
+        return plan
+
+    def adam_segments(self):
+        """Skip the decoder output rows the masks zero out: their gradient is exactly 0 in the reference,
+        so Adam leaves them bit-unchanged."""
+        segs, H = [], self.HIDDEN
+        shapes = {n: p.numel() for n, p in self.named_parameters()}
+        for n in self.live_param_names():
+            o = self._offsets[n]
+            parts = n.split(".")
+            if parts[0] == "decoder" and parts[2] == "4":
+                lo, hi = self._ranges[int(parts[1])]
+                w = H if parts[3] == "weight" else 1
+                segs.append((o + lo * w, (hi - lo) * w))
+            else:
+                segs.append((o, shapes[n]))
+        return self._merge(segs)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.arena_device).cuda_stream)
+
+    def _noise(self, batch):
+        if self.noise_fn is not None:
+            return self.noise_fn(batch, self.config["node"])
+        return torch.randn(batch, self.config["node"])              # CPU draw, as model.py:276
+
+    # -- training entry (used by modules/train.py) -------------------------------------------------
+    def forward_backward(self, x, y, noise, logs_row, x_l=None, y_l=None, xhat=None):
+        dev = self.arena_device
+        plan = self._get_plan()
+        x = _f32c(x, dev).reshape(x.shape[0], -1)
+        noise = _f32c(noise, dev)
+        io = _lib.PendulumIO()
+        io.params, io.grads = _ptr(self._arena), _ptr(self._grads)
+        Bn = x.shape[0]
+        keep = [x, noise]
+        if x_l is not None:
+            x_l = _f32c(x_l, dev).reshape(x_l.shape[0], -1)
+            y_l = _f32c(y_l, dev)
+            io.x_l, io.y_l, io.ld_y_l, io.batch_l = _ptr(x_l), _ptr(y_l), y_l.shape[1], x_l.shape[0]
+            keep += [x_l, y_l]
+        else:
+            y = _f32c(y, dev)
+            io.y, io.ld_y = _ptr(y), y.shape[1]
+            keep.append(y)
+        nbytes = _lib.lib().cdg_pendulum_workspace_bytes(plan, Bn, 0 if x_l is None else x_l.shape[0])
+        ws = self._get_workspace(nbytes)
+        io.workspace, io.workspace_bytes = _ptr(ws), ws.numel()
+        io.x, io.noise, io.batch = _ptr(x), _ptr(noise), Bn
+        io.logs = _ptr(logs_row)
+        io.xhat = _ptr(xhat)
+        _lib.check(_lib.lib().cdg_pendulum_forward_backward(plan, C.byref(io), self._stream()))
+        return keep
+
+    # -- inference API (modules/model.py:252-304) ---------------------------------------------------
+    def _run_forward(self, x=None, noise=None, latent_in=None, deterministic=False, want=()):
+        dev = self.arena_device
+        plan = self._get_plan()
+        d = self.config["node"]
+        P = 3 * self.config["image_size"] ** 2
+        K = len(self.config["factor"])
+        src = x if x is not None else latent_in
+        Bn = src.shape[0]
+        io = _lib.PendulumFwdIO()
+        io.params = _ptr(self._arena)
+        keep = []
+        if x is not None:
+            x = _f32c(x, dev).reshape(Bn, -1)
+            io.x = _ptr(x)
+            keep.append(x)
+            if not deterministic:
+                noise = _f32c(noise if noise is not None else self._noise(Bn), dev)
+                io.noise = _ptr(noise)
+                keep.append(noise)
+        else:
+            latent_in = _f32c(latent_in, dev)
+            io.latent_in = _ptr(latent_in)
+            keep.append(latent_in)
+        out = {}
+        for name in want:
+            shape = {"xhat": (Bn, P), "xhat_separated": (K, Bn, P)}.get(name, (Bn, d))
+            out[name] = torch.empty(shape, device=dev)
+            setattr(io, name, _ptr(out[name]))
+        nbytes = _lib.lib().cdg_pendulum_workspace_bytes(plan, Bn, 0)
+        ws = self._get_workspace(nbytes)
+        io.workspace, io.workspace_bytes, io.batch, io.deterministic = _ptr(ws), ws.numel(), Bn, int(deterministic)
+        _lib.check(_lib.lib().cdg_pendulum_forward(plan, C.byref(io), self._stream()))
+        return out
+
+    @staticmethod
+    def _cols(t):
+        return list(torch.split(t, 1, dim=1))
+
+    def _logdet(self, log_determinant, batch):
+        if not log_determinant:
+            return [0] * self.config["node"]
+        if self.config["scm"] != "linear":
+            raise NotImplementedError("log_determinant=True is only provided for the linear SCM")
+        return [torch.log(f.p[0].abs()).repeat(batch, 1) for f in self.flows]
+
+    def inverse(self, input):
+        return list(map(lambda x, layer: layer.inverse(x), input, self.flows))      # model.py:252-254
+
+    def get_posterior(self, input):
+        o = self._run_forward(x=input, deterministic=True, want=("mean", "logvar"))
+        return o["mean"], o["logvar"]
+
+    def transform(self, input, log_determinant=False):
+        """u = input @ I_B_inv, then the per-node flows (model.py:261-268).  Off the hot path: evaluated
+        with the parameter views (autograd-capable) rather than a dedicated kernel."""
+        latent = torch.matmul(input, self.I_B_inv)
+        orig_latent = latent.clone()
+        outs = [layer(c, log_determinant=log_determinant) for c, layer in zip(torch.split(latent, 1, dim=1), self.flows)]
+        return orig_latent, [o[0] for o in outs], [o[1] for o in outs]
+
+    def encode(self, input, deterministic=False, log_determinant=False):
+        o = self._run_forward(x=input, deterministic=deterministic,
+                              want=("mean", "logvar", "epsilon", "orig_latent", "latent"))
+        return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
+                self._logdet(log_determinant, input.shape[0]))
+
+    def decode(self, input):
+        s = self.config["image_size"]
+        o = self._run_forward(latent_in=torch.cat(list(input), dim=1), want=("xhat", "xhat_separated"))
+        return list(o["xhat_separated"].unbind(0)), o["xhat"].view(-1, s, s, 3)
+
+    def forward(self, input, deterministic=False, log_determinant=False):
+        s = self.config["image_size"]
+        o = self._run_forward(x=input, deterministic=deterministic,
+                              want=("mean", "logvar", "epsilon", "orig_latent", "latent", "align_latent",
+                                    "xhat_separated", "xhat"))
+        return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
+                self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]),
+                list(o["xhat_separated"].unbind(0)), o["xhat"].view(-1, s, s, 3))

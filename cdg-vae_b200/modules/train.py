@@ -1,0 +1,107 @@
+"""Drop-in for the reference's modules/train.py: same function names, signatures and returns.
+
+    train_CDGVAE(dataloader, model, config, optimizer, device) -> (logs, xhat)        train.py:150-209
+    train_CDGVAE_semi(datasetL, datasetU, model, config, optimizer, device) -> (logs, xhat)   :211-282
+
+Per batch the reference does H2D, zero_grad, forward, three losses, backward, Adam and 4+d `.item()`
+syncs; here a batch is two C-ABI calls (forward_backward, adam_step), the log row stays on the
+device and is read back once per call of these functions.
+"""
+import torch
+from torch.utils.data import DataLoader
+
+from .. import dist as _dist
+
+
+def _log_keys(config):
+    return ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i + 1}" for i in range(config["node"])]
+
+
+def _lookahead(it):
+    """Yield (item, is_last) so that xhat is materialised for the last batch only (train.py:209)."""
+    it = iter(it)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, False
+        cur = nxt
+    yield cur, True
+
+
+def _finish(model, config, n_steps):
+    """One device->host copy per call instead of 4+d `.item()` per step (train.py:206-207)."""
+    keys = _log_keys(config)
+    logs = {k: [] for k in keys}
+    if n_steps:
+        rows = model._logs[:n_steps]
+        if _dist.world() > 1:
+            rows = _dist.allreduce_mean_(rows.clone())
+        host = rows.cpu()
+        for j, k in enumerate(keys):
+            logs[k] = host[:, j].tolist()
+    model._grad_views()
+    return logs
+
+
+def _step(model, config, optimizer, row, x, y, noise, x_l=None, y_l=None, xhat=None):
+    model._plan_key_check = (config.get("beta"), config.get("lambda"))
+    keep = model.forward_backward(x, y, noise, row, x_l=x_l, y_l=y_l, xhat=xhat)
+    scale = model.exchange_gradients()
+    model.adam_step(grad_scale=scale)
+    return keep
+
+
+def _sync_config(model, config):
+    # the train loops read beta / lambda from the `config` they are given (train.py:198-199)
+    for k in ("beta", "lambda"):
+        if k in config:
+            model.config[k] = config[k]
+
+
+def train_CDGVAE(dataloader, model, config, optimizer, device):
+    _sync_config(model, config)
+    model.bind_optimizer(optimizer)
+    width = 4 + config["node"]
+    s = config["image_size"] if "image_size" in config else model.config["image_size"]
+    xhat, n = None, 0
+    for (x_batch, y_batch), last in _lookahead(dataloader):
+        rows = model._log_rows(n + 1, width)
+        noise = model._noise(x_batch.shape[0])
+        if last:
+            xhat = torch.empty(x_batch.shape[0], 3 * s * s, device=model.arena_device)
+        _step(model, config, optimizer, rows[n], x_batch, y_batch, noise, xhat=xhat if last else None)
+        n += 1
+    logs = _finish(model, config, n)
+    return logs, (None if xhat is None else xhat.view(-1, s, s, 3))
+
+
+def train_CDGVAE_semi(datasetL, datasetU, model, config, optimizer, device):
+    _sync_config(model, config)
+    model.bind_optimizer(optimizer)
+    width = 4 + config["node"]
+    s = config["image_size"] if "image_size" in config else model.config["image_size"]
+    # the reference builds both loaders on every call (train.py:222-223)
+    dataloaderU = DataLoader(datasetU, batch_size=config["batch_size"], shuffle=True)
+    dataloaderL = DataLoader(datasetL, batch_size=config["batch_sizeL"], shuffle=True)
+    iterL = None
+    xhat, n = None, 0
+    for x_batchU, last in _lookahead(dataloaderU):
+        # labeled iterator restarts when exhausted (train.py:226-230)
+        try:
+            if iterL is None:
+                raise StopIteration
+            x_batchL, y_batchL = next(iterL)
+        except StopIteration:
+            iterL = iter(dataloaderL)
+            x_batchL, y_batchL = next(iterL)
+        rows = model._log_rows(n + 1, width)
+        noise = model._noise(x_batchU.shape[0])
+        if last:
+            xhat = torch.empty(x_batchU.shape[0], 3 * s * s, device=model.arena_device)
+        _step(model, config, optimizer, rows[n], x_batchU, None, noise, x_l=x_batchL, y_l=y_batchL,
+              xhat=xhat if last else None)
+        n += 1
+    logs = _finish(model, config, n)
+    return logs, (None if xhat is None else xhat.view(-1, s, s, 3))

@@ -1,0 +1,119 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+the drop-in model reproduces the reference's same-seed initialisation / state_dict layout, mask and
+segment bookkeeping is exact, and loading the product without CUDA fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import cdgvae_b200
+from cdgvae_b200 import _lib
+from cdgvae_b200.modules.model import CDGVAE, mask_ranges
+from oracle import cdgvae_oracle as orc
+from helpers import case_setup, exact_check
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "cdgvae.h")).read()
+    declared = set(re.findall(r"\b(cdg_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.cdg_version() >= 100
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors vs the C compiler's view of include/cdgvae.h."""
+    import subprocess, tempfile
+    src = '#include "cdgvae.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(cdg_linear),sizeof(cdg_adam_args),sizeof(cdg_pendulum_config),sizeof(cdg_pendulum_io),' \
+          'sizeof(cdg_pendulum_fwd_io),sizeof(cdg_tabular_config),sizeof(cdg_tabular_io));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    mine = [ctypes.sizeof(t) for t in (_lib.Linear, _lib.AdamArgs, _lib.PendulumConfig, _lib.PendulumIO,
+                                       _lib.PendulumFwdIO, _lib.TabularConfig, _lib.TabularIO)]
+    assert sizes == mine
+
+
+def _pendulum_model(c, device="cpu"):
+    spec, Bm, batches, cfg = case_setup(c)
+    torch.manual_seed(cfg["seed"])
+    model = CDGVAE(Bm, spec.mask, cfg, device)
+    return model, spec, Bm, batches, cfg
+
+
+@pytest.mark.parametrize("name", ["pendulum_small_linear", "pendulum_small_nonlinear", "pendulum_full_linear"])
+def test_pendulum_same_seed_init_and_state_dict(golden, name):
+    c = golden(name)
+    model, spec, Bm, batches, cfg = _pendulum_model(c)
+    sd = model.state_dict()
+    assert list(sd) == list(c["init"])                       # key names AND order
+    for k, v in sd.items():
+        exact_check(v, c["init"][k], k)                       # bit-exact same-seed init
+    assert model.I_B_inv.tolist() == c["I_B_inv"]
+    # parameters are views of one arena
+    base = model._arena.data_ptr()
+    for n, p in model.named_parameters():
+        assert p.data_ptr() == base + 4 * model._offsets[n]
+        assert model._offsets[n] % 4 == 0 or n.startswith("flows.")
+    # load_state_dict writes through to the arena
+    sd2 = {k: torch.full_like(v, 0.5) for k, v in sd.items()}
+    model.load_state_dict(sd2)
+    assert float(model._arena[model._offsets["encoder.2.bias"]]) == 0.5
+
+
+def test_mask_ranges_bit_exact():
+    m = orc.pendulum_masks(64, (20, 51))
+    assert mask_ranges(m, 12288) == [(0, 3840), (3840, 9792), (9792, 12288)]
+    bad = torch.zeros(64, 64, 3)
+    bad[::2] = 1
+    with pytest.raises(ValueError):
+        mask_ranges([bad], 12288)
+
+
+def test_adam_segments_skip_dead_decoder_rows(golden):
+    model, *_ = _pendulum_model(golden("pendulum_full_linear"))
+    segs = model.adam_segments()
+    live = sum(n for _, n in segs)
+    total = sum(p.numel() for p in model.parameters())
+    assert total == 15_148_480
+    dead = 2 * 12288 * 300 + 2 * 12288                         # two thirds of the decoder output rows
+    assert total - dead <= live <= total - dead + 32 * 28            # + alignment padding between merged params
+    assert len(segs) <= _lib.MAX_SEG
+
+
+def test_asserts_and_errors_match_reference():
+    cfg = dict(node=4, scm="cubic", flow_num=1, inverse_loop=100, factor=[1, 1, 2], image_size=8)
+    with pytest.raises(ValueError, match="Not supported SCM!"):
+        CDGVAE(orc.pendulum_B(4), orc.pendulum_masks(8, (3, 6)), cfg, "cpu")
+    cfg["scm"] = "linear"
+    cfg["factor"] = [1, 1, 1]
+    with pytest.raises(AssertionError):
+        CDGVAE(orc.pendulum_B(4), orc.pendulum_masks(8, (3, 6)), cfg, "cpu")
+
+
+def test_no_cpu_fallback(golden):
+    """Without a CUDA device the product path must refuse to compute."""
+    model, spec, Bm, batches, cfg = _pendulum_model(golden("pendulum_small_linear"))
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(batches[0]["x"])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "cdg-vae_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("restatement", ""), os.path.join(dp, f)

@@ -1,0 +1,160 @@
+"""GPU parity of the pendulum CDG-VAE step (through the C ABI via the drop-in Python API) against
+(i) the committed reference goldens and (ii) the oracle run on the same inputs.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative for fp32 losses, gradients and updated
+parameters; bit-exact for masks / index bookkeeping (checked in test_host_cpu.py).  "Relative" is
+per tensor: ||a-b||_2 / ||b||_2 (and max-abs error relative to the tensor's max-abs for samples)."""
+import pytest
+import torch
+
+from oracle import cdgvae_oracle as orc
+from helpers import case_setup, summary_check
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(c, gemm_mode="auto"):
+    from cdgvae_b200.modules.model import CDGVAE
+    spec, Bm, batches, cfg = case_setup(c)
+    cfg["gemm_mode"] = gemm_mode
+    torch.manual_seed(cfg["seed"])
+    model = CDGVAE(Bm, spec.mask, cfg, "cpu").to("cuda")
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    return model, opt, spec, Bm, batches, cfg
+
+
+PEND = ["pendulum_small_linear", "pendulum_small_nonlinear", "pendulum_small_semi", "pendulum_full_linear",
+        "pendulum_full_semi"]
+
+
+@pytest.mark.parametrize("gemm_mode", ["simt", "auto"])
+@pytest.mark.parametrize("name", PEND)
+def test_train_step_matches_reference_and_oracle(golden, name, gemm_mode):
+    from cdgvae_b200.modules import train as T
+    c = golden(name)
+    model, opt, spec, Bm, batches, cfg = build(c, gemm_mode)
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    oadam = orc.new_adam_state(oparams)
+    s_img = cfg["image_size"]
+    for s, (b, e) in enumerate(zip(batches, c["steps"]), 1):
+        model.noise_fn = lambda n, d, b=b: b["noise"]
+        if c["semi"]:
+            class L(list):
+                pass
+            T.DataLoader = lambda ds, batch_size, shuffle: ds           # batches are pre-made
+            logs, xhat = T.train_CDGVAE_semi([(b["x_l"], b["y_l"])], [b["x"]], model, cfg, opt, "cuda")
+        else:
+            logs, xhat = T.train_CDGVAE([(b["x"], b["y"])], model, cfg, opt, "cuda")
+        ologs, ograds, oout = orc.train_step(oparams, oadam, spec, A, b["x"], b.get("y"), b["noise"],
+                                             b.get("x_l"), b.get("y_l"))
+        # losses: against the reference golden and the oracle
+        for k, v in e["logs"].items():
+            assert len(logs[k]) == 1
+            assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (name, s, k, logs[k][0], v)
+            assert abs(logs[k][0] - ologs[k]) <= RTOL * abs(ologs[k]) + 1e-7, (name, s, k)
+        assert xhat.shape == (b["x"].shape[0], s_img, s_img, 3)
+        assert rel(xhat, oout["xhat"]) < RTOL
+        # gradients (p.grad is exposed like autograd would)
+        for n, p in model.named_parameters():
+            assert p.grad is not None
+            og = ograds[n]
+            assert rel(p.grad, og) < RTOL, (name, s, "grad", n, rel(p.grad, og))
+            if "grads" in e:
+                summary_check(p.grad, e["grads"][n], RTOL, "golden grad " + n, atol_scale=1e-6)
+        # updated parameters + Adam state
+        sd = model.state_dict()
+        for n in sd:
+            tol = RTOL if s == 1 else 3 * RTOL          # Adam's g/sqrt(v) amplifies rounding after step 1
+            assert rel(sd[n], oparams[n]) < tol, (name, s, "param", n, rel(sd[n], oparams[n]))
+            if "params" in e:
+                summary_check(sd[n], e["params"][n], tol, f"golden param {n} step {s}", atol_scale=1e-6)
+        for n, p in model.named_parameters():
+            st = opt.state[p]
+            assert float(st["step"]) == s
+            assert rel(st["exp_avg"], oadam[n]["exp_avg"]) < RTOL
+            assert rel(st["exp_avg_sq"], oadam[n]["exp_avg_sq"]) < 2 * RTOL
+
+
+def test_dead_decoder_columns_stay_bit_identical(golden):
+    """masked-out decoder weights get exactly zero gradient and never move."""
+    from cdgvae_b200.modules import train as T
+    c = golden("pendulum_small_linear")
+    model, opt, spec, Bm, batches, cfg = build(c)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    b = batches[0]
+    model.noise_fn = lambda n, d: b["noise"]
+    T.train_CDGVAE([(b["x"], b["y"])], model, cfg, opt, "cuda")
+    for k, (lo, hi) in enumerate(model._ranges):
+        w, g = model.decoder[k][4].weight, model.decoder[k][4].weight.grad
+        dead = torch.ones(w.shape[0], dtype=torch.bool, device=w.device)
+        dead[lo:hi] = False
+        assert torch.equal(w[dead], before[f"decoder.{k}.4.weight"][dead])
+        assert float(g[dead].abs().max()) == 0.0
+        assert not torch.equal(w[~dead], before[f"decoder.{k}.4.weight"][~dead])
+
+
+@pytest.mark.parametrize("name", ["pendulum_small_linear", "pendulum_small_nonlinear"])
+def test_forward_api_matches_oracle(golden, name):
+    c = golden(name)
+    model, opt, spec, Bm, batches, cfg = build(c)
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    b = batches[0]
+    model.noise_fn = lambda n, d: b["noise"]
+    out = model(b["x"].cuda())
+    assert len(out) == 9                                         # model.py:304
+    mean, logvar, eps, orig, latent, logdet, align, sep, xhat = out
+    o = orc.forward(oparams, spec, A, b["x"], b["noise"])
+    f = c["steps"][0]["forward"]
+    for got, key in ((mean, "mean"), (logvar, "logvar"), (eps, "epsilon"), (orig, "orig_latent"), (xhat, "xhat")):
+        assert rel(got, o[key]) < RTOL, key
+        summary_check(got, f[key], RTOL, key, atol_scale=1e-6)
+    assert isinstance(latent, list) and len(latent) == cfg["node"] and latent[0].shape == (b["x"].shape[0], 1)
+    assert rel(torch.cat(latent, 1), torch.cat(o["latent"], 1)) < RTOL
+    assert rel(torch.cat(align, 1), torch.cat(o["align_latent"], 1)) < RTOL
+    assert logdet == [0] * cfg["node"]
+    assert len(sep) == len(cfg["factor"])
+    for k in range(len(sep)):
+        assert rel(sep[k], o["xhat_separated"][k]) < RTOL
+    # encode / decode / get_posterior arities (model.py:256-288)
+    m2, lv2 = model.get_posterior(b["x"].cuda())
+    assert rel(m2, o["mean"]) < RTOL and rel(lv2, o["logvar"]) < RTOL
+    enc = model.encode(b["x"].cuda(), deterministic=True)
+    assert len(enc) == 6 and rel(enc[2], o["mean"]) < RTOL          # deterministic: epsilon = mean
+    sep2, xhat2 = model.decode(latent)
+    assert rel(xhat2, o["xhat"]) < RTOL
+    # inverse o transform round trip (model.py:252-254)
+    inv = model.inverse(latent)
+    assert rel(torch.cat(inv, 1), orig) < (1e-4 if cfg["scm"] == "linear" else 1e-3)
+
+
+def test_ragged_last_batch_and_multi_batch_logs(golden):
+    """A loader whose last batch is smaller (DataLoader without drop_last) and several steps per call."""
+    from cdgvae_b200.modules import train as T
+    c = golden("pendulum_small_linear")
+    model, opt, spec, Bm, batches, cfg = build(c)
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    oadam = orc.new_adam_state(oparams)
+    sizes = [16, 16, 5, 1]
+    data, noises = [], []
+    for i, n in enumerate(sizes):
+        x, y, nz = orc.synth_pendulum(n, cfg["image_size"], 4, 77 + i, 99 + i)
+        data.append((x, y))
+        noises.append(nz)
+    q = list(noises)
+    model.noise_fn = lambda n, d: q.pop(0)
+    logs, xhat = T.train_CDGVAE(data, model, cfg, opt, "cuda")
+    assert xhat.shape[0] == 1
+    for i, ((x, y), nz) in enumerate(zip(data, noises)):
+        ol, _, _ = orc.train_step(oparams, oadam, spec, A, x, y, nz)
+        for k in ol:
+            assert abs(logs[k][i] - ol[k]) <= 3 * RTOL * abs(ol[k]) + 1e-7, (i, k, logs[k][i], ol[k])
+    assert list(logs) == ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i+1}" for i in range(4)]
