@@ -8,6 +8,7 @@ MAX_NODE, MAX_DEC, MAX_FLOW, MAX_LAYERS, MAX_SPANS, MAX_SEG = 8, 8, 2, 4, 64, 32
 SCM = {"linear": 0, "nonlinear": 1}
 GEMM_MODES = {"auto": 0, "simt": 1, "tc3x": 2, "tc1x": 3}
 TAB_KIND = {"loan": 0, "adult": 1, "covtype": 2, "tvae": 3}
+PROF_CATS = ["enc0_fwd", "dec2_fwd", "dec2_dgrad", "dec2_wgrad", "enc0_wgrad", "gemm_other", "latent", "recon", "misc"]
 
 
 class Linear(C.Structure):
@@ -63,7 +64,8 @@ class TabularIO(C.Structure):
 
 
 # every symbol include/cdgvae.h declares
-EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_adam_step", "cdg_pendulum_create",
+EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_pendulum_profile_enable",
+           "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm"]
@@ -87,6 +89,9 @@ def lib():
         raise RuntimeError("libcdgvae_sm100.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(path)
     L.cdg_last_error.restype = C.c_char_p
+    L.cdg_launch_count.restype = C.c_longlong
+    L.cdg_pendulum_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.cdg_pendulum_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cdg_pendulum_workspace_bytes.restype = C.c_int64
     L.cdg_pendulum_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.cdg_pendulum_create.argtypes = [C.POINTER(PendulumConfig), C.POINTER(C.c_void_p)]

@@ -21,7 +21,12 @@ void set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define CDG_CHECK_LAUNCH() CDG_CHECK_CUDA(cudaGetLastError())
+extern long long g_launches;   // kernels launched by this library (host-side count)
+#define CDG_CHECK_LAUNCH()                                                                \
+    do {                                                                                  \
+        ++cdg::g_launches;                                                                \
+        CDG_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
 
 #define CDG_REQUIRE(cond, ...)                                                            \
     do {                                                                                  \
@@ -85,6 +90,24 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
     }
     return v;
 }
+
+// ---- optional per-category device timing (cudaEvents on the caller's stream) ----
+enum ProfCat { PROF_ENC0_FWD = 0, PROF_DEC2_FWD, PROF_DEC2_DGRAD, PROF_DEC2_WGRAD, PROF_ENC0_WGRAD, PROF_GEMM_OTHER,
+               PROF_LATENT, PROF_RECON, PROF_MISC, PROF_NCAT };
+struct Profiler {
+    bool enabled = false;
+    static constexpr int kMax = 4096;
+    cudaEvent_t ev[kMax];
+    int cat[kMax];
+    int n = 0, created = 0;
+    // mark the start of a region of category c; the region ends at the next mark
+    void mark(int c, cudaStream_t s) {
+        if (!enabled || n >= kMax) return;
+        if (n >= created) { if (cudaEventCreate(&ev[n]) != cudaSuccess) return; created = n + 1; }
+        cudaEventRecord(ev[n], s);
+        cat[n++] = c;
+    }
+};
 
 // ---- generic strided GEMM interface (implemented in gemm_simt.cu / gemm_tc.cu) ----
 struct GemmDesc {

@@ -8,6 +8,7 @@
 
 namespace cdg {
 
+long long g_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -165,6 +166,7 @@ extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, 
 
 extern "C" const char* cdg_last_error(void) { return cdg::get_error(); }
 extern "C" int cdg_version(void) { return 100; }
+extern "C" long long cdg_launch_count(void) { return cdg::g_launches; }
 extern "C" int cdg_device_ok(void) {
     int dev = 0;
     cudaDeviceProp prop;

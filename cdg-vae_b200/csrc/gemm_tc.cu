@@ -1,6 +1,521 @@
-// tcgen05 / TMEM / TMA GEMM (placeholder until the kernel lands: everything is reported as
-// unsupported so that the dispatcher uses the SIMT kernel).
+// tcgen05 / TMEM / TMA GEMM for sm_100a with FP32-faithful arithmetic (3xTF32).
+//
+//   C[m,n] = sum_k A(m,k) * B(n,k)        A(m,k) = A[m*sa_m + k*sa_k],  B(n,k) = B[n*sb_n + k*sb_k]
+//
+// The reference's Linear layers are true-FP32 cuBLAS/MKL GEMMs (allow_tf32 = False) and parity is
+// judged at 1e-4 on gradients, so single-pass TF32 (10-bit mantissa) is not enough.  Each fp32
+// operand is split on the fly into hi = tf32(a) and lo = a - hi, and every K-step issues
+//   D += A_lo*B_hi;  D += A_hi*B_lo;  D += A_hi*B_hi        (tcgen05.mma.kind::tf32, fp32 accumulate in TMEM)
+// which recovers ~21 mantissa bits per product.
+//
+// CTA = 128 x BN output tile, one per SM (shared memory bound), 10 warps:
+//   warp 0      TMA producer: cp.async.bulk.tensor of the raw fp32 tiles (2-stage ring, mbarrier tx-count)
+//   warp 1      allocates TMEM, issues tcgen05.mma (one lane), commits to the ring's "empty" barriers
+//   warps 2-9   converter: split raw tiles into hi/lo K-major SWIZZLE_128B tiles in shared memory
+//               (operands whose contraction index is not the contiguous one -- dgrad weights, both wgrad
+//               operands -- arrive as [k][mn] boxes and are transposed here), then, after the last
+//               K-block, the epilogue: tcgen05.ld the accumulator, bias / ELU / ELU' / accumulate, store.
+// Partial tiles rely on TMA zero fill.  Split-K over gridDim.z adds into C with red.global.add.f32.
 #include "common.cuh"
+
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace cdg {
-int gemm_tc(const GemmDesc&, int, void*, int64_t, cudaStream_t) { return CDG_ERR_UNSUPPORTED; }
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int NUM_CONV_WARPS = 8;
+constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS);
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int STAGES = 2;
+
+struct Params {
+    float* C; int64_t sc_m, sc_n;
+    int64_t M, N;
+    int epi, act, accumulate, atomic;
+    const float* bias; int bias_on_m;
+    const float* aux; int64_t aux_sm, aux_sn;
+    int kb_total, kb_per_split;        // K-blocks (of BK) in total / per blockIdx.z
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// byte offset of element (row r, k) inside a K-major SWIZZLE_128B tile (16-byte chunk index XOR row%8)
+__device__ __forceinline__ uint32_t sw128_chunk(uint32_t r, uint32_t chunk) { return r * 128u + ((chunk ^ (r & 7u)) << 4); }
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // hi + lo for both operands
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int B_ROWS_PER_BOX = BN <= 256 ? BN : BN / 2;  // K-major TMA box rows (<= 256)
+    static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4);   // MN-major chunk width (<= 128)
+    static constexpr int N0 = BN <= 256 ? BN : 160;                 // first MMA's N
+    static constexpr int N1 = BN - N0;                              // second MMA's N (0 = none)
+    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+    static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
+    static_assert(SMEM <= 232448, "tile does not fit shared memory");
+};
+
+// ---- converter --------------------------------------------------------------------------------
+// K-major source: the raw tile already sits in the `hi` buffer in its final (swizzled) place.  Any
+// element-wise rewrite keeps the layout, so the tile is processed as a flat float4 array.
+template <int PASSES>
+__device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int bytes, int ct) {
+    if (PASSES == 1) return;
+    float4* h = reinterpret_cast<float4*>(hi);
+    float4* l = reinterpret_cast<float4*>(lo);
+    const int n = bytes / 16;
+    for (int i = ct; i < n; i += 32 * NUM_CONV_WARPS) {
+        const float4 r = h[i];
+        float4 a, b;
+        a.x = tf32_rna(r.x); a.y = tf32_rna(r.y); a.z = tf32_rna(r.z); a.w = tf32_rna(r.w);
+        b.x = r.x - a.x; b.y = r.y - a.y; b.z = r.z - a.z; b.w = r.w - a.w;
+        h[i] = a;
+        l[i] = b;
+    }
+}
+
+// MN-major source: raw boxes [BK k-rows][CW mn] landed in the `lo` buffer (chunk c at byte c*CW*128).
+// Each thread owns one mn column of a chunk: read its BK values (conflict-free), wait until every
+// converter thread has read the chunk (its bytes are about to be overwritten), then write the K-major
+// rows of hi and lo.
+template <int PASSES, int ROWS, int CW>
+__device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct) {
+    constexpr int NT = 32 * NUM_CONV_WARPS;
+    constexpr int IT = (ROWS + NT - 1) / NT;
+    float v[IT][BK];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int j = ct + it * NT;                       // mn index inside the tile
+        if (j < ROWS) {
+            const int c = j / CW, col = j - c * CW;
+            const float* raw = reinterpret_cast<const float*>(lo + (size_t)c * CW * 128);
+#pragma unroll
+            for (int k = 0; k < BK; ++k) v[it][k] = raw[k * CW + col];
+        }
+    }
+    // every raw byte has been read before any of them is overwritten by the lo rows
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int j = ct + it * NT;
+        if (j < ROWS) {
+#pragma unroll
+            for (int ch = 0; ch < BK / 4; ++ch) {
+                const float x0 = v[it][4 * ch], x1 = v[it][4 * ch + 1], x2 = v[it][4 * ch + 2], x3 = v[it][4 * ch + 3];
+                const uint32_t off = sw128_chunk((uint32_t)j, ch);
+                if (PASSES == 1) {
+                    *reinterpret_cast<float4*>(hi + off) = make_float4(x0, x1, x2, x3);
+                } else {
+                    float4 a;
+                    a.x = tf32_rna(x0); a.y = tf32_rna(x1); a.z = tf32_rna(x2); a.w = tf32_rna(x3);
+                    *reinterpret_cast<float4*>(hi + off) = a;
+                    *reinterpret_cast<float4*>(lo + off) = make_float4(x0 - a.x, x1 - a.y, x2 - a.z, x3 - a.w);
+                }
+            }
+        }
+    }
+}
+
+template <int BN, int PASSES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    using C_ = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
+    // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, [3S] accumulator ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int kb_beg = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
+    const int nkb = kb_end - kb_beg;
+
+    auto stage_ptr = [&](int s) { return smem + (size_t)s * C_::STAGE_BYTES; };
+    auto a_hi = [&](int s) { return stage_ptr(s); };
+    auto a_lo = [&](int s) { return stage_ptr(s) + A_BYTES; };
+    auto b_hi = [&](int s) { return stage_ptr(s) + 2 * A_BYTES; };
+    auto b_lo = [&](int s) { return stage_ptr(s) + 2 * A_BYTES + C_::B_BYTES; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[STAGES + s]), 32 * NUM_CONV_WARPS);
+            mbar_init(smem_u32(&bars[2 * STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[3 * STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C_::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0 && nkb > 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[2 * STAGES + s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bars[s]);
+                mbar_expect_tx(full, A_BYTES + C_::B_BYTES);
+                const int k0 = (kb_beg + i) * BK;
+                if (!A_MN) {
+                    tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
+                } else {
+                    tma_load_2d(smem_u32(a_lo(s)), &tmA, full, m_blk * BM, k0);
+                }
+                if (!B_MN) {
+#pragma unroll
+                    for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
+                        tma_load_2d(smem_u32(b_hi(s) + r * 128), &tmB, full, k0, n_blk * BN + r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < BN; r += C_::B_CW)
+                        tma_load_2d(smem_u32(b_lo(s) + r * 128), &tmB, full, n_blk * BN + r, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0 && nkb > 0) {
+            constexpr uint32_t idesc0 = make_idesc(BM, C_::N0);
+            constexpr uint32_t idesc1 = make_idesc(BM, C_::N1 > 0 ? C_::N1 : 16);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[STAGES + s]), ph);
+                tc_fence_after();
+                const uint64_t dah = make_kmajor_desc(smem_u32(a_hi(s))), dal = make_kmajor_desc(smem_u32(a_lo(s)));
+                const uint64_t dbh = make_kmajor_desc(smem_u32(b_hi(s))), dbl = make_kmajor_desc(smem_u32(b_lo(s)));
+#pragma unroll
+                for (int pass = 0; pass < PASSES; ++pass) {
+                    // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
+                    const uint64_t da = (PASSES == 3 && pass == 0) ? dal : dah;
+                    const uint64_t db = (PASSES == 3 && pass == 1) ? dbl : dbh;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                        umma_tf32(tmem_base, da + koff, db + koff, idesc0, acc);
+                        if (C_::N1 > 0)
+                            umma_tf32(tmem_base + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 128) >> 4), idesc1, acc);
+                    }
+                }
+                umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
+            }
+            umma_commit(smem_u32(&bars[3 * STAGES]));               // accumulator complete
+        }
+    } else {
+        // ================= converter, then epilogue =================
+        const int ct = threadIdx.x - 64;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(smem_u32(&bars[s]), ph);
+            if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct);
+            else convert_mnmajor<PASSES, BM, 128>(a_hi(s), a_lo(s), ct);
+            if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct);
+            else convert_mnmajor<PASSES, BN, C_::B_CW>(b_hi(s), b_lo(s), ct);
+            fence_async_smem();                                      // generic-proxy writes -> async proxy (UMMA)
+            mbar_arrive(smem_u32(&bars[STAGES + s]));
+        }
+        if (nkb > 0) {
+            mbar_wait(smem_u32(&bars[3 * STAGES]), 0);
+            tc_fence_after();
+            const int cw = warp - 2;
+            const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+            const int half = cw >> 2;                                // column half handled by this warp
+            constexpr int HALF = BN / 2;
+            const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 8) {
+                float v[8];
+                tmem_ld8(trow + (uint32_t)c0, v);
+                if (m < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t n = (int64_t)n_blk * BN + c0 + j;
+                        if (n < p.N) {
+                            float* cptr = p.C + m * p.sc_m + n * p.sc_n;
+                            float val = v[j];
+                            if (p.atomic) {
+                                atomicAdd(cptr, val);
+                            } else {
+                                if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) val += p.bias[p.bias_on_m ? m : n];
+                                if (p.epi == EPI_BIAS_ACT) val = act_fwd(val, p.act);
+                                if (p.epi == EPI_MUL_DACT) val *= act_bwd_from_out(p.aux[m * p.aux_sm + n * p.aux_sn], p.act);
+                                if (p.accumulate) val += *cptr;
+                                *cptr = val;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; int64_t rows, k, row_stride, k_stride; int box0, box1, mn;
+    bool operator<(const MapKey& o) const {
+        return std::tie(ptr, rows, k, row_stride, k_stride, box0, box1, mn) <
+               std::tie(o.ptr, o.rows, o.k, o.row_stride, o.k_stride, o.box0, o.box1, o.mn);
+    }
+};
+static std::map<MapKey, CUtensorMap> g_maps;
+static std::mutex g_maps_mu;
+
+// Operand X(r,k) = X[r*s_r + k*s_k], r < rows, k < K.  K-major (s_k == 1): dims {K, rows}, box {32, box_rows},
+// SWIZZLE_128B.  MN-major (s_r == 1): dims {rows, K}, box {cw, 32}, no swizzle.
+static int make_map(const float* X, int64_t rows, int64_t K, int64_t s_r, int64_t s_k, bool mn_major, int box_rows,
+                    CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
+    MapKey key{X, rows, K, s_r, s_k, mn_major ? box_rows : BK, mn_major ? BK : box_rows, mn_major ? 1 : 0};
+    {
+        std::lock_guard<std::mutex> g(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return CDG_OK; }
+    }
+    cuuint64_t dims[2], strides[1];
+    cuuint32_t box[2], estr[2] = {1, 1};
+    CUtensorMapSwizzle sw;
+    if (!mn_major) {
+        dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; strides[0] = (cuuint64_t)s_r * 4;
+        box[0] = BK; box[1] = (cuuint32_t)box_rows; sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    } else {
+        dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; strides[0] = (cuuint64_t)s_k * 4;
+        box[0] = (cuuint32_t)box_rows; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CDG_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *out;
+    return CDG_OK;
+}
+
+// an operand is usable when it is K-major or MN-major with TMA-legal strides and alignment
+static bool operand_ok(const float* X, int64_t s_r, int64_t s_k, int64_t rows, int64_t K, bool* mn_major) {
+    if (((uintptr_t)X & 15) != 0) return false;
+    if (s_k == 1 && (s_r % 4 == 0) && s_r >= K) { *mn_major = false; return true; }
+    if (s_r == 1 && (s_k % 4 == 0) && s_k >= rows) { *mn_major = true; return true; }
+    return false;
+}
+
+template <int BN, int PASSES, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t s) {
+    auto kern = gemm_tc_kernel<BN, PASSES, A_MN, B_MN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        attr_done = true;
+    }
+    kern<<<grid, THREADS, Cfg<BN>::SMEM, s>>>(ta, tb, p);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+template <int BN, int PASSES>
+static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid,
+                         cudaStream_t s) {
+    if (!a_mn && !b_mn) return launch<BN, PASSES, false, false>(ta, tb, p, grid, s);
+    if (!a_mn && b_mn) return launch<BN, PASSES, false, true>(ta, tb, p, grid, s);
+    if (a_mn && !b_mn) return launch<BN, PASSES, true, false>(ta, tb, p, grid, s);
+    return launch<BN, PASSES, true, true>(ta, tb, p, grid, s);
+}
+
+}  // namespace tc
+
+int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
+    using namespace tc;
+    GemmDesc g = g0;
+    int64_t sc_m = g.ldc, sc_n = 1, aux_sm = g.ld_aux, aux_sn = 1;
+    int bias_on_m = 0;
+    // Tensor-core tiles need real extents: tiny N (encoder head 2d = 8) / tiny K (decoder inputs 1-2) stay on SIMT.
+    if (g.K < 16 || (g.M < 32 && g.N < 32) || g.M * g.N < 4096) return CDG_ERR_UNSUPPORTED;
+    // put the long output dimension on M (128-row tiles) when the other fits one N tile
+    if (g.N > 304 && g.M <= 304) {
+        std::swap(g.A, g.B); std::swap(g.sa_m, g.sb_n); std::swap(g.sa_k, g.sb_k); std::swap(g.M, g.N);
+        std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
+        bias_on_m = 1;
+    }
+    if (g.N < 16) return CDG_ERR_UNSUPPORTED;
+    bool a_mn, b_mn;
+    if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn) || !operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn))
+        return CDG_ERR_UNSUPPORTED;
+
+    int BN;
+    if (g.N <= 128) BN = 128;
+    else if (g.N <= 256) BN = 256;
+    else if (g.N <= 304) BN = 304;
+    else BN = 256;
+    const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+    if (tm > 65535 || tn > 65535) return CDG_ERR_UNSUPPORTED;
+    const int kb_total = (int)((g.K + BK - 1) / BK);
+    // split-K, for two reasons:
+    //  (1) accuracy: the tensor core accumulates in fp32 with truncation, whose error grows linearly with the
+    //      number of accumulations (measured on B200: ~3.5e-9 * K relative).  Capping one TMEM accumulation at
+    //      KB_CAP K-blocks (K = 2048) keeps a partial sum at ~7e-6; partials are combined with fp32
+    //      round-to-nearest adds (red.global.add.f32).
+    //  (2) occupancy: fill the chip when the tile grid is small.
+    constexpr int KB_CAP = 64;
+    int splits = (kb_total + KB_CAP - 1) / KB_CAP;
+    const int64_t tiles = tm * tn;
+    if (tiles * splits < kNumSMs && kb_total >= 8) {
+        int want = (int)imin64((kNumSMs + tiles - 1) / tiles, kb_total / 4);
+        splits = (int)imax64(splits, imin64(want, 64));
+    }
+    if (splits < 1) splits = 1;
+    int kb_per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kb_per - 1) / kb_per;
+    if (splits > 65535) return CDG_ERR_UNSUPPORTED;
+
+    Params p;
+    p.C = g.C; p.sc_m = sc_m; p.sc_n = sc_n; p.M = g.M; p.N = g.N;
+    p.epi = g.epi; p.act = g.act; p.accumulate = g.accumulate; p.atomic = splits > 1;
+    p.bias = g.bias; p.bias_on_m = bias_on_m; p.aux = g.aux; p.aux_sm = aux_sm; p.aux_sn = aux_sn;
+    p.kb_total = kb_total; p.kb_per_split = kb_per;
+
+    if (p.atomic && !g.accumulate) {
+        // zero C (in the caller's orientation) before the partial sums are added
+        if (g0.ldc == g0.N) CDG_CHECK_CUDA(cudaMemsetAsync(g0.C, 0, sizeof(float) * g0.M * g0.N, s));
+        else CDG_CHECK_CUDA(cudaMemset2DAsync(g0.C, sizeof(float) * g0.ldc, 0, sizeof(float) * g0.N, g0.M, s));
+    }
+
+    CUtensorMap ta, tb;
+    const int b_box = b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4)) : (BN <= 256 ? BN : BN / 2);
+    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, a_mn, 128, &ta));
+    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, b_mn, b_box, &tb));
+    dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+    int r;
+    if (passes == 1) {
+        if (BN == 128) r = launch_layout<128, 1>(a_mn, b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 1>(a_mn, b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 1>(a_mn, b_mn, ta, tb, p, grid, s);
+    } else {
+        if (BN == 128) r = launch_layout<128, 3>(a_mn, b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 3>(a_mn, b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 3>(a_mn, b_mn, ta, tb, p, grid, s);
+    }
+    CDG_TRY(r);
+    if (p.atomic && g.epi != EPI_NONE)
+        CDG_TRY(launch_bias_act(g0.C, g0.ldc, g0.M, g0.N, g0.bias, g0.epi, g0.act, g0.aux, g0.ld_aux, s));
+    return CDG_OK;
+}
+
 }  // namespace cdg

@@ -15,6 +15,7 @@
 struct cdg_pendulum_plan {
     cdg_pendulum_config c;
     int lat_off[CDG_MAX_DEC];   // first latent column of decoder k
+    cdg::Profiler prof;
 };
 
 namespace cdg {
@@ -57,11 +58,14 @@ struct Ctx {
     PendWs w;
     cudaStream_t s;
     int mode;
+    Profiler* prof = nullptr;
+    void mark(int cat) const { if (prof) prof->mark(cat, s); }
 };
 
 // Y[M,N] = act(X[M,K] W[N,K]^T + b)   (nn.Linear forward)
 static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
-                      float* Y, int64_t ldy, int64_t M, bool act) {
+                      float* Y, int64_t ldy, int64_t M, bool act, int cat = PROF_GEMM_OTHER) {
+    c.mark(cat);
     GemmDesc g;
     g.A = X; g.sa_m = ldx; g.sa_k = 1;
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = L.in; g.sb_k = 1;
@@ -71,18 +75,21 @@ static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linea
 }
 // dW[rows,K] += dY[M,rows]^T X[M,K];  db[rows] += colsum(dY)
 static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float* X, int64_t ldx, const cdg_linear& L,
-                        int64_t row_lo, int64_t n_rows, int64_t M) {
+                        int64_t row_lo, int64_t n_rows, int64_t M, int cat = PROF_GEMM_OTHER) {
+    c.mark(cat);
     GemmDesc g;
     g.A = dY; g.sa_m = 1; g.sa_k = ldy;
     g.B = X; g.sb_n = 1; g.sb_k = ldx;
     g.C = c.G + L.w + row_lo * L.in; g.ldc = L.in; g.M = n_rows; g.N = L.in; g.K = M;
     g.epi = EPI_NONE; g.accumulate = 1;
     CDG_TRY(gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s));
+    c.mark(PROF_MISC);
     return launch_colsum(dY, ldy, M, n_rows, c.G + L.b + row_lo, c.s);
 }
 // dX[M,K] = (dY[M,rows] W[rows,K]) * act'(Hout)      (Hout == nullptr: no activation in front)
 static int linear_dgrad(const Ctx& c, const float* dY, int64_t ldy, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
-                        float* dX, int64_t lddx, const float* Hout, int64_t ldh, int64_t M) {
+                        float* dX, int64_t lddx, const float* Hout, int64_t ldh, int64_t M, int cat = PROF_GEMM_OTHER) {
+    c.mark(cat);
     GemmDesc g;
     g.A = dY; g.sa_m = ldy; g.sa_k = 1;
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = 1; g.sb_k = L.in;
@@ -102,7 +109,7 @@ static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
 static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float* h2, float* ml) {
     const cdg_pendulum_config& cf = c.p->c;
     const int64_t H = cf.hidden, d = cf.node;
-    CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true));
+    CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true, PROF_ENC0_FWD));
     CDG_TRY(linear_fwd(c, h1, H, cf.enc[1], 0, H, h2, H, B, true));
     CDG_TRY(linear_fwd(c, h2, H, cf.enc[2], 0, 2 * d, ml, 2 * d, B, false));
     return CDG_OK;
@@ -116,7 +123,7 @@ static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1,
     CDG_TRY(linear_dgrad(c, g_ml, 2 * d, cf.enc[2], 0, 2 * d, g_h2, H, h2, H, B));
     CDG_TRY(linear_wgrad(c, g_h2, H, h1, H, cf.enc[1], 0, H, B));
     CDG_TRY(linear_dgrad(c, g_h2, H, cf.enc[1], 0, H, g_h1, H, h1, H, B));
-    CDG_TRY(linear_wgrad(c, g_h1, H, x, cf.input_dim, cf.enc[0], 0, H, B));
+    CDG_TRY(linear_wgrad(c, g_h1, H, x, cf.input_dim, cf.enc[0], 0, H, B, PROF_ENC0_WGRAD));
     return CDG_OK;
 }
 
@@ -130,7 +137,7 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre) {
         CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
         const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
-        if (n > 0) CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], lo, n, pre + lo, P, B, false));
+        if (n > 0) CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], lo, n, pre + lo, P, B, false, PROF_DEC2_FWD));
     }
     return CDG_OK;
 }
@@ -173,7 +180,32 @@ extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_
     return CDG_OK;
 }
 
-extern "C" void cdg_pendulum_destroy(cdg_pendulum_plan* p) { delete p; }
+extern "C" void cdg_pendulum_destroy(cdg_pendulum_plan* p) {
+    if (!p) return;
+    for (int i = 0; i < p->prof.created; ++i) cudaEventDestroy(p->prof.ev[i]);
+    delete p;
+}
+
+extern "C" int cdg_pendulum_profile_enable(cdg_pendulum_plan* p, int enable) {
+    CDG_REQUIRE(p, "null plan");
+    p->prof.enabled = enable != 0;
+    p->prof.n = 0;
+    return CDG_OK;
+}
+
+extern "C" int cdg_pendulum_profile_read(cdg_pendulum_plan* p, double* out_ms) {
+    CDG_REQUIRE(p && out_ms, "null argument");
+    Profiler& pr = p->prof;
+    for (int i = 0; i + 1 < pr.n; ++i) {
+        if (pr.cat[i] < 0) continue;                 // end-of-step marker: gap until the next step is not ours
+        float ms = 0.f;
+        CDG_CHECK_CUDA(cudaEventSynchronize(pr.ev[i + 1]));
+        CDG_CHECK_CUDA(cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]));
+        out_ms[pr.cat[i]] += ms;
+    }
+    pr.n = 0;
+    return CDG_OK;
+}
 
 extern "C" int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l) {
     if (!p || batch < 0 || batch_l < 0) return -1;
@@ -191,6 +223,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     Ctx c;
     c.p = p; c.P = io->params; c.G = io->grads; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
     c.mode = cf.gemm_mode;
+    c.prof = p->prof.enabled ? &p->prof : nullptr;
     c.w = pend_layout(cf, B, BL);
     if (c.w.total * 4 > io->workspace_bytes) {
         set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
@@ -200,6 +233,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     float* W = c.W;
     double* acc = (double*)(W + c.w.acc);
     cudaStream_t s = c.s;
+    c.mark(PROF_MISC);
 
     // optimizer.zero_grad() (train.py:168) + loss accumulators
     CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * cf.n_params, s));
@@ -212,6 +246,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     fill_latent(cf, la);
     la.batch = B; la.params = io->params; la.ml = W + c.w.ml; la.noise = io->noise;
     la.eps_out = W + c.w.eps; la.u_out = W + c.w.u; la.z_out = W + c.w.z; la.acc = acc;
+    c.mark(PROF_LATENT);
     CDG_TRY(launch_latent_fwd(la, s));
 
     LatentArgs al;
@@ -224,9 +259,11 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     } else {
         al.batch = B; al.ml = W + c.w.ml; al.y = io->y; al.ld_y = io->ld_y;
     }
+    c.mark(PROF_LATENT);
     CDG_TRY(launch_align(al, s));
 
     CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
+    c.mark(PROF_RECON);
     CDG_TRY(launch_recon(W + c.w.pre, io->x, io->xhat, B, Pd, acc, 1, s));
 
     // ---- backward ----
@@ -240,8 +277,8 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         const float* a2 = W + c.w.a2[k];
         const float* zk = W + c.w.z + p->lat_off[k];
         if (n > 0) {
-            CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B));
-            CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B));
+            CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B, PROF_DEC2_WGRAD));
+            CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B, PROF_DEC2_DGRAD));
         } else {
             CDG_CHECK_CUDA(cudaMemsetAsync(ga2, 0, sizeof(float) * B * H, s));
         }
@@ -254,12 +291,15 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     fill_latent(cf, lb);
     lb.batch = B; lb.params = io->params; lb.grads = io->grads; lb.ml = W + c.w.ml; lb.noise = io->noise;
     lb.u_in = W + c.w.u; lb.g_z = g_z; lb.g_align = semi ? nullptr : W + c.w.g_align; lb.g_out = W + c.w.g_ml;
+    c.mark(PROF_LATENT);
     CDG_TRY(launch_latent_bwd(lb, s));
     CDG_TRY(encoder_bwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.g_ml, W + c.w.g_h2, W + c.w.g_h1));
     if (semi)
         CDG_TRY(encoder_bwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.g_align, W + c.w.g_h2l, W + c.w.g_h1l));
 
+    c.mark(PROF_MISC);
     CDG_TRY(launch_finalize_logs(acc, io->logs, (int)d, (float)B, (float)B, (float)(semi ? BL : B), cf.beta, cf.lambda_, s));
+    c.mark(-1);
     return CDG_OK;
 }
 

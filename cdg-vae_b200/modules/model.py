@@ -188,6 +188,15 @@ class CDGVAE(ArenaModule):
                 segs.append((o, shapes[n]))
         return self._merge(segs)
 
+    def profile(self, enable=True):
+        """Per-category device timing of the step (cudaEvents inside the library)."""
+        _lib.check(_lib.lib().cdg_pendulum_profile_enable(self._get_plan(), int(enable)))
+
+    def profile_read(self):
+        out = (C.c_double * len(_lib.PROF_CATS))()
+        _lib.check(_lib.lib().cdg_pendulum_profile_read(self._get_plan(), out))
+        return dict(zip(_lib.PROF_CATS, list(out)))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.arena_device).cuda_stream)
 

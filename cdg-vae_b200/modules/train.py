@@ -78,13 +78,19 @@ def train_CDGVAE(dataloader, model, config, optimizer, device):
 
 
 def train_CDGVAE_semi(datasetL, datasetU, model, config, optimizer, device):
+    # the reference builds both loaders on every call (train.py:222-223)
+    dataloaderU = DataLoader(datasetU, batch_size=config["batch_size"], shuffle=True)
+    dataloaderL = DataLoader(datasetL, batch_size=config["batch_sizeL"], shuffle=True)
+    return train_CDGVAE_semi_loaders(dataloaderL, dataloaderU, model, config, optimizer, device)
+
+
+def train_CDGVAE_semi_loaders(dataloaderL, dataloaderU, model, config, optimizer, device):
+    """train_CDGVAE_semi with the two loaders supplied by the caller (any iterables of batches): the body
+    of the reference loop, train.py:225-282, without the per-call DataLoader construction."""
     _sync_config(model, config)
     model.bind_optimizer(optimizer)
     width = 4 + config["node"]
     s = config["image_size"] if "image_size" in config else model.config["image_size"]
-    # the reference builds both loaders on every call (train.py:222-223)
-    dataloaderU = DataLoader(datasetU, batch_size=config["batch_size"], shuffle=True)
-    dataloaderL = DataLoader(datasetL, batch_size=config["batch_sizeL"], shuffle=True)
     iterL = None
     xhat, n = None, 0
     for x_batchU, last in _lookahead(dataloaderU):

@@ -41,6 +41,8 @@ const char* cdg_last_error(void);
 int cdg_version(void);
 /* 1 when the current device is sm_100 (the only target this library is built for). */
 int cdg_device_ok(void);
+/* Number of kernels this library has launched so far in this process (host-side counter). */
+long long cdg_launch_count(void);
 
 /* A Linear layer's weight [out,in] and bias [out] as float offsets into the parameter arena
  * (the gradient / exp_avg / exp_avg_sq arenas share the layout). */
@@ -133,6 +135,14 @@ typedef struct {
 } cdg_pendulum_fwd_io;
 
 int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd_io* io, void* stream);
+
+/* Optional device-side timing of the step by kernel category (cudaEvents recorded on the caller's stream
+ * between the launches of cdg_pendulum_forward_backward).  cdg_pendulum_profile_read synchronises on the
+ * recorded events, ADDS the elapsed milliseconds per category to out_ms[CDG_PROF_NCAT] and clears the record. */
+enum { CDG_PROF_ENC0_FWD = 0, CDG_PROF_DEC2_FWD, CDG_PROF_DEC2_DGRAD, CDG_PROF_DEC2_WGRAD, CDG_PROF_ENC0_WGRAD,
+       CDG_PROF_GEMM_OTHER, CDG_PROF_LATENT, CDG_PROF_RECON, CDG_PROF_MISC, CDG_PROF_NCAT };
+int cdg_pendulum_profile_enable(cdg_pendulum_plan* p, int enable);
+int cdg_pendulum_profile_read(cdg_pendulum_plan* p, double* out_ms);
 
 /* ------------------------------------------------------------------------------------------
  * Tabular CDG-VAE and CDG-TVAE (tabular/modules/model.py:234-460; tabular/modules/train.py:173-320):

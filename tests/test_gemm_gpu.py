@@ -45,7 +45,7 @@ def test_gemm_layouts(mode, layout, shape):
         sa, sb, ref = (1, M), (1, N), A.double().t() @ B.double()
     out = run(mode, A, sa, B, sb, M, N, K)
     err = float((out.double() - ref).norm() / ref.norm())
-    tol = 2e-3 if mode == "tc1x" else 2e-6          # fp32-faithful modes vs single-pass TF32
+    tol = 2e-3 if mode == "tc1x" else (2e-6 if mode == "simt" else 2e-5)   # 3xTF32: K <= 4096 per accumulation
     assert err < tol, (mode, layout, shape, err)
     if layout == "tn" and M * N < 1 << 22:
         C0 = torch.randn(M, N, generator=g).cuda()
