@@ -1,0 +1,72 @@
+"""Drop-in for the reference's tabular/modules/train.py.
+
+    train_CDGVAE(dataset, dataloader, model, config, optimizer, device) -> logs          train.py:173-243
+    train_TVAE(output_info_list, dataset, dataloader, model, config, optimizer, device) -> logs   :245-320
+
+One fused kernel per step (forward + losses + backward), one Adam kernel; the log rows stay on the
+device until the loader is exhausted.
+"""
+from ... import dist as _dist
+
+
+def _log_keys(config):
+    return ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i + 1}" for i in range(config["node"])]
+
+
+def _finish(model, config, n_steps):
+    keys = _log_keys(config)
+    logs = {k: [] for k in keys}
+    if n_steps:
+        rows = model._logs[:n_steps]
+        if _dist.world() > 1:
+            rows = _dist.allreduce_mean_(rows.clone())
+        host = rows.cpu()
+        for j, k in enumerate(keys):
+            logs[k] = host[:, j].tolist()
+    model._grad_views(set(model.live_param_names()))
+    return logs
+
+
+def _sync_config(model, config):
+    for k in ("beta", "lambda", "dataset", "sigma_range"):
+        if k in config:
+            model.config[k] = config[k]
+
+
+def train_CDGVAE(dataset, dataloader, model, config, optimizer, device):
+    if config["dataset"] not in ("loan", "adult", "covtype"):
+        raise ValueError("Not supported dataset!")                       # train.py:210
+    _sync_config(model, config)
+    model.bind_optimizer(optimizer)
+    ft = None
+    if config["dataset"] in ("loan", "adult"):
+        ft = tuple(int(v) for v in dataset.flatten_topology)             # train.py:200-202
+    model._last_aux = (ft, None)
+    width, n = 4 + config["node"], 0
+    for (x_batch, y_batch) in iter(dataloader):
+        rows = model._log_rows(n + 1, width)
+        noise = model._noise(x_batch.shape[0])
+        model.forward_backward(x_batch, y_batch, noise, rows[n], flatten_topology=ft)
+        model.adam_step(grad_scale=model.exchange_gradients())
+        n += 1
+    return _finish(model, config, n)
+
+
+def train_TVAE(output_info_list, dataset, dataloader, model, config, optimizer, device):
+    _sync_config(model, config)
+    model.bind_optimizer(optimizer)
+    oil = [[(int(s.dim), str(s.activation_fn)) if hasattr(s, "dim") else (int(s[0]), str(s[1])) for s in col]
+           for col in output_info_list]
+    model._last_aux = (None, oil)
+    lo, hi = config["sigma_range"]
+    sig = model._offsets["sigma"]
+    D = model.config["input_dim"]
+    width, n = 4 + config["node"], 0
+    for (x_batch, y_batch) in iter(dataloader):
+        rows = model._log_rows(n + 1, width)
+        noise = model._noise(x_batch.shape[0])
+        model.forward_backward(x_batch, y_batch, noise, rows[n], output_info_list=oil)
+        # optimizer.step() then sigma.data.clamp_(lo, hi)  (train.py:313-314)
+        model.adam_step(grad_scale=model.exchange_gradients(), clamp=(sig, D, float(lo), float(hi)))
+        n += 1
+    return _finish(model, config, n)

@@ -117,3 +117,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("restatement", ""), os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("name", ["tabular_loan", "tabular_adult", "tabular_covtype", "tvae_loan", "tvae_covtype"])
+def test_tabular_same_seed_init_and_state_dict(golden, name):
+    from cdgvae_b200.tabular.modules import model as M
+    c = golden(name)
+    spec, Bm, batches, cfg = case_setup(c)
+    torch.manual_seed(cfg["seed"])
+    cls = M.TVAE if c["family"] == "tvae" else M.CDGVAE
+    model = cls(Bm, c["mask"], cfg, "cpu")
+    sd = model.state_dict()
+    assert list(sd) == list(c["init"])
+    for k, v in sd.items():
+        exact_check(v, c["init"][k], k)
+    assert model.I_B_inv.tolist() == c["I_B_inv"]                 # covtype: general (non-triangular) inverse
+    if name == "tabular_covtype":
+        live = model.live_param_names()
+        assert not any(n.startswith("decoder.6.") for n in live) and "decoder.6.6.weight" in sd
+        assert sum(p.numel() for p in model.parameters()) == 390
+    if name in ("tabular_loan", "tabular_adult"):
+        assert sum(p.numel() for p in model.parameters()) == 87
