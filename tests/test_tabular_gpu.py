@@ -85,7 +85,7 @@ def test_tabular_step_matches_reference_and_oracle(golden, name):
                               atol_scale=1e-6)
         if c["family"] == "tvae":
             lo, hi = cfg["sigma_range"]
-            assert float(model.sigma.min()) >= lo and float(model.sigma.max()) <= hi      # train.py:314
+            assert float(model.sigma.min()) >= lo - 1e-8 and float(model.sigma.max()) <= hi + 1e-8   # train.py:314 (fp32 bounds)
 
 
 @pytest.mark.parametrize("name", ["tabular_adult", "tabular_covtype", "tvae_loan"])
