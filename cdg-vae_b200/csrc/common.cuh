@@ -51,11 +51,12 @@ enum Epi : int {
     EPI_BIAS = 1,       // C = acc + bias[n]
     EPI_BIAS_ACT = 2,   // C = act(acc + bias[n])
     EPI_MUL_DACT = 3,   // C = acc * act'(aux[m,n])   (aux holds the post-activation value)
+    EPI_RECON = 4,      // pre = acc + bias[n]; xhat = tanh(pre); loss += 0.5 (xhat - x)^2; C = (xhat - x)(1 - xhat^2)/batch
 };
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
     // ELU(alpha=1): modules/model.py:221 (nn.ELU);  ReLU: tabular/modules/model.py:373
-    if (act == CDG_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    if (act == CDG_ACT_ELU) return v > 0.f ? v : expf(v) - 1.f;   // ATen's ELU computes exp(x) - 1, not expm1
     return v > 0.f ? v : 0.f;
 }
 // derivative expressed through the post-activation value h
@@ -121,12 +122,19 @@ struct GemmDesc {
     const float* aux = nullptr;      // [M, ld_aux]
     int64_t ld_aux = 0;
     int accumulate = 0;              // C += result (EPI_NONE only)
+    // EPI_RECON (tensor-core kernel only): the reconstruction head fused into the last decoder Linear
+    const float* recon_x = nullptr;  // [M, ld_x] target, same columns as C
+    int64_t ld_x = 0;
+    float* recon_xhat = nullptr;     // optional tanh output, laid out like C
+    double* recon_acc = nullptr;     // += sum 0.5 (xhat - x)^2
+    float inv_batch = 0.f;
 };
 
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
 // tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the
 // dispatcher can route it to the SIMT kernel.
 int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+bool gemm_tc_can(const GemmDesc& g);   // would gemm_tc accept this contraction (without split-K)?
 int gemm_dispatch(int mode, const GemmDesc& g, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 
 int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,

@@ -8,14 +8,19 @@
 //   D += A_lo*B_hi;  D += A_hi*B_lo;  D += A_hi*B_hi        (tcgen05.mma.kind::tf32, fp32 accumulate in TMEM)
 // which recovers ~21 mantissa bits per product.
 //
-// CTA = 128 x BN output tile, one per SM (shared memory bound), 10 warps:
-//   warp 0      TMA producer: cp.async.bulk.tensor of the raw fp32 tiles (2-stage ring, mbarrier tx-count)
-//   warp 1      allocates TMEM, issues tcgen05.mma (one lane), commits to the ring's "empty" barriers
-//   warps 2-9   converter: split raw tiles into hi/lo K-major SWIZZLE_128B tiles in shared memory
-//               (operands whose contraction index is not the contiguous one -- dgrad weights, both wgrad
-//               operands -- arrive as [k][mn] boxes and are transposed here), then, after the last
-//               K-block, the epilogue: tcgen05.ld the accumulator, bias / ELU / ELU' / accumulate, store.
-// Partial tiles rely on TMA zero fill.  Split-K over gridDim.z adds into C with red.global.add.f32.
+// Persistent kernel, one CTA per SM (shared memory bound), looping over (tile, K-split) work items of
+// 128 x BN outputs; 14 warps:
+//   warp 0       TMA producer: cp.async.bulk.tensor of the raw fp32 tiles (2-stage ring, mbarrier tx-count),
+//                running ahead across work items
+//   warp 1       allocates TMEM, issues tcgen05.mma (one lane), commits to the ring's "empty" barriers and
+//                to the accumulator-full barrier; accumulators are double-buffered in TMEM when 2*BN <= 512
+//   warps 2-9    converter: split raw tiles into hi/lo K-major SWIZZLE_128B tiles in shared memory (operands
+//                whose contraction index is not the contiguous one -- dgrad weights, both wgrad operands --
+//                arrive as [k][mn] boxes and are transposed here)
+//   warps 10-13  epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row per thread), bias /
+//                ELU / ELU' / accumulate / fused tanh-MSE reconstruction head, 128-bit stores; overlaps the
+//                next work item's main loop
+// Partial tiles rely on TMA zero fill.  K-splits add into C with red.global.add.f32.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -31,17 +36,21 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements per K-block = one 128-byte swizzle row
 constexpr int NUM_CONV_WARPS = 8;
-constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS);
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS + NUM_EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
 constexpr int STAGES = 2;
 
 struct Params {
     float* C; int64_t sc_m, sc_n;
     int64_t M, N;
-    int epi, act, accumulate, atomic;
+    int epi, act, accumulate, atomic, vec;      // vec: row-major output, 16-byte aligned rows -> float4 path
     const float* bias; int bias_on_m;
     const float* aux; int64_t aux_sm, aux_sn;
-    int kb_total, kb_per_split;        // K-blocks (of BK) in total / per blockIdx.z
+    const float* rx; int64_t rx_ld; float* rxhat; double* racc; float inv_batch;   // EPI_RECON
+    int kb_total, kb_per_split;                 // K-blocks (of BK) in total / per split
+    int tiles_n, splits;
+    int64_t work_total;                         // tiles_m * tiles_n * splits
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +105,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -129,7 +149,8 @@ struct Cfg {
     static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4);   // MN-major chunk width (<= 128)
     static constexpr int N0 = BN <= 256 ? BN : 160;                 // first MMA's N
     static constexpr int N1 = BN - N0;                              // second MMA's N (0 = none)
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+    static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;            // TMEM accumulator buffers
+    static constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
 };
@@ -195,27 +216,44 @@ __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct
     }
 }
 
+// one output element group of the epilogue -------------------------------------------------------
+__device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t m, int64_t n, float* cptr) {
+    if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) val += p.bias[p.bias_on_m ? m : n];
+    if (p.epi == EPI_BIAS_ACT) val = act_fwd(val, p.act);
+    if (p.epi == EPI_MUL_DACT) val *= act_bwd_from_out(p.aux[m * p.aux_sm + n * p.aux_sn], p.act);
+    if (p.accumulate) val += *cptr;
+    return val;
+}
+
 template <int BN, int PASSES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     using C_ = Cfg<BN>;
+    constexpr int NACC = C_::NACC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
-    // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, [3S] accumulator ready
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, then NACC acc-full, NACC acc-empty
+    uint64_t* acc_full = bars + 3 * STAGES;
+    uint64_t* acc_empty = acc_full + NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-    const int kb_beg = blockIdx.z * p.kb_per_split;
-    const int kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
-    const int nkb = kb_end - kb_beg;
 
     auto stage_ptr = [&](int s) { return smem + (size_t)s * C_::STAGE_BYTES; };
     auto a_hi = [&](int s) { return stage_ptr(s); };
     auto a_lo = [&](int s) { return stage_ptr(s) + A_BYTES; };
     auto b_hi = [&](int s) { return stage_ptr(s) + 2 * A_BYTES; };
     auto b_lo = [&](int s) { return stage_ptr(s) + 2 * A_BYTES + C_::B_BYTES; };
+    // work item -> (m block, n block, first K-block, number of K-blocks)
+    auto decode = [&](int64_t w, int& m_blk, int& n_blk, int& kb_beg, int& nkb) {
+        const int sp = (int)(w % p.splits);
+        const int64_t t = w / p.splits;
+        n_blk = (int)(t % p.tiles_n);
+        m_blk = (int)(t / p.tiles_n);
+        kb_beg = sp * p.kb_per_split;
+        nkb = min(p.kb_total, kb_beg + p.kb_per_split) - kb_beg;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -223,7 +261,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(smem_u32(&bars[STAGES + s]), 32 * NUM_CONV_WARPS);
             mbar_init(smem_u32(&bars[2 * STAGES + s]), 1);
         }
-        mbar_init(smem_u32(&bars[3 * STAGES]), 1);
+        for (int b = 0; b < NACC; ++b) {
+            mbar_init(smem_u32(&acc_full[b]), 1);
+            mbar_init(smem_u32(&acc_empty[b]), 32 * NUM_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -237,109 +278,190 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && nkb > 0) {
+        if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(smem_u32(&bars[2 * STAGES + s]), ph ^ 1u);
-                const uint32_t full = smem_u32(&bars[s]);
-                mbar_expect_tx(full, A_BYTES + C_::B_BYTES);
-                const int k0 = (kb_beg + i) * BK;
-                if (!A_MN) {
-                    tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
-                } else {
-                    tma_load_2d(smem_u32(a_lo(s)), &tmA, full, m_blk * BM, k0);
-                }
-                if (!B_MN) {
+            uint32_t it = 0;
+            for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+                int m_blk, n_blk, kb_beg, nkb;
+                decode(w, m_blk, n_blk, kb_beg, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&bars[2 * STAGES + s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bars[s]);
+                    mbar_expect_tx(full, A_BYTES + C_::B_BYTES);
+                    const int k0 = (kb_beg + i) * BK;
+                    if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
+                    else tma_load_2d(smem_u32(a_lo(s)), &tmA, full, m_blk * BM, k0);
+                    if (!B_MN) {
 #pragma unroll
-                    for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
-                        tma_load_2d(smem_u32(b_hi(s) + r * 128), &tmB, full, k0, n_blk * BN + r);
-                } else {
+                        for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
+                            tma_load_2d(smem_u32(b_hi(s) + r * 128), &tmB, full, k0, n_blk * BN + r);
+                    } else {
 #pragma unroll
-                    for (int r = 0; r < BN; r += C_::B_CW)
-                        tma_load_2d(smem_u32(b_lo(s) + r * 128), &tmB, full, n_blk * BN + r, k0);
+                        for (int r = 0; r < BN; r += C_::B_CW)
+                            tma_load_2d(smem_u32(b_lo(s) + r * 128), &tmB, full, n_blk * BN + r, k0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && nkb > 0) {
+        if (lane == 0) {
             constexpr uint32_t idesc0 = make_idesc(BM, C_::N0);
             constexpr uint32_t idesc1 = make_idesc(BM, C_::N1 > 0 ? C_::N1 : 16);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(smem_u32(&bars[STAGES + s]), ph);
+            uint32_t it = 0, j = 0;
+            for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x, ++j) {
+                int m_blk, n_blk, kb_beg, nkb;
+                decode(w, m_blk, n_blk, kb_beg, nkb);
+                const uint32_t buf = j % NACC;
+                mbar_wait(smem_u32(&acc_empty[buf]), ((j / NACC) & 1u) ^ 1u);     // epilogue drained this buffer
                 tc_fence_after();
-                const uint64_t dah = make_kmajor_desc(smem_u32(a_hi(s))), dal = make_kmajor_desc(smem_u32(a_lo(s)));
-                const uint64_t dbh = make_kmajor_desc(smem_u32(b_hi(s))), dbl = make_kmajor_desc(smem_u32(b_lo(s)));
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&bars[STAGES + s]), ph);
+                    tc_fence_after();
+                    const uint64_t dah = make_kmajor_desc(smem_u32(a_hi(s))), dal = make_kmajor_desc(smem_u32(a_lo(s)));
+                    const uint64_t dbh = make_kmajor_desc(smem_u32(b_hi(s))), dbl = make_kmajor_desc(smem_u32(b_lo(s)));
 #pragma unroll
-                for (int pass = 0; pass < PASSES; ++pass) {
-                    // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
-                    const uint64_t da = (PASSES == 3 && pass == 0) ? dal : dah;
-                    const uint64_t db = (PASSES == 3 && pass == 1) ? dbl : dbh;
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
+                        const uint64_t da = (PASSES == 3 && pass == 0) ? dal : dah;
+                        const uint64_t db = (PASSES == 3 && pass == 1) ? dbl : dbh;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
-                        const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                        umma_tf32(tmem_base, da + koff, db + koff, idesc0, acc);
-                        if (C_::N1 > 0)
-                            umma_tf32(tmem_base + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 128) >> 4), idesc1, acc);
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
+                            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                            umma_tf32(tacc, da + koff, db + koff, idesc0, acc);
+                            if (C_::N1 > 0)
+                                umma_tf32(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 128) >> 4), idesc1, acc);
+                        }
                     }
+                    umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
                 }
-                umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
+                umma_commit(smem_u32(&acc_full[buf]));                  // accumulator of this work item complete
             }
-            umma_commit(smem_u32(&bars[3 * STAGES]));               // accumulator complete
+        }
+    } else if (warp < 2 + NUM_CONV_WARPS) {
+        // ================= converter =================
+        const int ct = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+            int m_blk, n_blk, kb_beg, nkb;
+            decode(w, m_blk, n_blk, kb_beg, nkb);
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct);
+                else convert_mnmajor<PASSES, BM, 128>(a_hi(s), a_lo(s), ct);
+                if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct);
+                else convert_mnmajor<PASSES, BN, C_::B_CW>(b_hi(s), b_lo(s), ct);
+                fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(smem_u32(&bars[STAGES + s]));
+            }
         }
     } else {
-        // ================= converter, then epilogue =================
-        const int ct = threadIdx.x - 64;
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-            mbar_wait(smem_u32(&bars[s]), ph);
-            if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct);
-            else convert_mnmajor<PASSES, BM, 128>(a_hi(s), a_lo(s), ct);
-            if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct);
-            else convert_mnmajor<PASSES, BN, C_::B_CW>(b_hi(s), b_lo(s), ct);
-            fence_async_smem();                                      // generic-proxy writes -> async proxy (UMMA)
-            mbar_arrive(smem_u32(&bars[STAGES + s]));
-        }
-        if (nkb > 0) {
-            mbar_wait(smem_u32(&bars[3 * STAGES]), 0);
+        // ================= epilogue =================
+        const int q = warp & 3;                                      // TMEM lane quarter this warp may access
+        uint32_t j = 0;
+        float rloss = 0.f;
+        for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x, ++j) {
+            int m_blk, n_blk, kb_beg, nkb;
+            decode(w, m_blk, n_blk, kb_beg, nkb);
+            const uint32_t buf = j % NACC;
+            mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
             tc_fence_after();
-            const int cw = warp - 2;
-            const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-            const int half = cw >> 2;                                // column half handled by this warp
-            constexpr int HALF = BN / 2;
             const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+            const bool row_ok = m < p.M;
 #pragma unroll 1
-            for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 8) {
-                float v[8];
-                tmem_ld8(trow + (uint32_t)c0, v);
-                if (m < p.M) {
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                const int64_t n0 = (int64_t)n_blk * BN + c0;
+                if (!row_ok || n0 >= p.N) continue;
+                if (p.vec && !p.atomic && n0 + 16 <= p.N) {
+                    float* crow = p.C + m * p.sc_m + n0;
+                    if (p.epi == EPI_RECON) {
+                        const float* xr = p.rx + m * p.rx_ld + n0;
+                        float* xh = p.rxhat ? p.rxhat + m * p.sc_m + n0 : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int64_t n = (int64_t)n_blk * BN + c0 + j;
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * g);
+                            const float4 xx = __ldg(reinterpret_cast<const float4*>(xr + 4 * g));
+                            float t[4] = {tanhf(v[4 * g] + bb.x), tanhf(v[4 * g + 1] + bb.y), tanhf(v[4 * g + 2] + bb.z),
+                                          tanhf(v[4 * g + 3] + bb.w)};
+                            const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float df = t[e] - xs[e];
+                                rloss += 0.5f * df * df;
+                                o[e] = df * (1.f - t[e] * t[e]) * p.inv_batch;
+                            }
+                            *reinterpret_cast<float4*>(crow + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+                            if (xh) *reinterpret_cast<float4*>(xh + 4 * g) = make_float4(t[0], t[1], t[2], t[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float o[4] = {v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]};
+                            if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) {
+                                if (p.bias_on_m) {
+                                    const float bm = p.bias[m];
+                                    o[0] += bm; o[1] += bm; o[2] += bm; o[3] += bm;
+                                } else {
+                                    const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * g);
+                                    o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+                                }
+                            }
+                            if (p.epi == EPI_BIAS_ACT) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) o[e] = act_fwd(o[e], p.act);
+                            }
+                            if (p.epi == EPI_MUL_DACT) {
+                                const float4 hh = *reinterpret_cast<const float4*>(p.aux + m * p.aux_sm + n0 + 4 * g);
+                                o[0] *= act_bwd_from_out(hh.x, p.act); o[1] *= act_bwd_from_out(hh.y, p.act);
+                                o[2] *= act_bwd_from_out(hh.z, p.act); o[3] *= act_bwd_from_out(hh.w, p.act);
+                            }
+                            if (p.accumulate) {
+                                const float4 cc = *reinterpret_cast<const float4*>(crow + 4 * g);
+                                o[0] += cc.x; o[1] += cc.y; o[2] += cc.z; o[3] += cc.w;
+                            }
+                            *reinterpret_cast<float4*>(crow + 4 * g) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int64_t n = n0 + e;
                         if (n < p.N) {
                             float* cptr = p.C + m * p.sc_m + n * p.sc_n;
-                            float val = v[j];
                             if (p.atomic) {
-                                atomicAdd(cptr, val);
+                                atomicAdd(cptr, v[e]);
+                            } else if (p.epi == EPI_RECON) {
+                                const float t = tanhf(v[e] + p.bias[n]);
+                                const float df = t - p.rx[m * p.rx_ld + n];
+                                rloss += 0.5f * df * df;
+                                *cptr = df * (1.f - t * t) * p.inv_batch;
+                                if (p.rxhat) p.rxhat[m * p.sc_m + n * p.sc_n] = t;
                             } else {
-                                if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) val += p.bias[p.bias_on_m ? m : n];
-                                if (p.epi == EPI_BIAS_ACT) val = act_fwd(val, p.act);
-                                if (p.epi == EPI_MUL_DACT) val *= act_bwd_from_out(p.aux[m * p.aux_sm + n * p.aux_sn], p.act);
-                                if (p.accumulate) val += *cptr;
-                                *cptr = val;
+                                *cptr = epi_scalar(p, v[e], m, n, cptr);
                             }
                         }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&acc_empty[buf]));                  // TMEM buffer may be overwritten
+        }
+        if (p.epi == EPI_RECON && p.racc) {
+            const float s = warp_sum(rloss);
+            if (lane == 0) atomicAdd(p.racc, (double)s);
         }
     }
     tc_fence_before();
@@ -441,7 +563,16 @@ static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUte
 
 }  // namespace tc
 
-int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
+struct Plan {
+    GemmDesc g;
+    int64_t sc_m, sc_n, aux_sm, aux_sn;
+    int bias_on_m, BN, splits, kb_total, kb_per;
+    int64_t tm, tn;
+    bool a_mn, b_mn;
+};
+
+// shape / layout analysis shared by gemm_tc and gemm_tc_can
+static int plan_gemm(const GemmDesc& g0, Plan* pl) {
     using namespace tc;
     GemmDesc g = g0;
     int64_t sc_m = g.ldc, sc_n = 1, aux_sm = g.ld_aux, aux_sn = 1;
@@ -449,7 +580,7 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     // Tensor-core tiles need real extents: tiny N (encoder head 2d = 8) / tiny K (decoder inputs 1-2) stay on SIMT.
     if (g.K < 16 || (g.M < 32 && g.N < 32) || g.M * g.N < 4096) return CDG_ERR_UNSUPPORTED;
     // put the long output dimension on M (128-row tiles) when the other fits one N tile
-    if (g.N > 304 && g.M <= 304) {
+    if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON) {
         std::swap(g.A, g.B); std::swap(g.sa_m, g.sb_n); std::swap(g.sa_k, g.sb_k); std::swap(g.M, g.N);
         std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
         bias_on_m = 1;
@@ -458,14 +589,13 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     bool a_mn, b_mn;
     if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn) || !operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn))
         return CDG_ERR_UNSUPPORTED;
-
     int BN;
     if (g.N <= 128) BN = 128;
     else if (g.N <= 256) BN = 256;
     else if (g.N <= 304) BN = 304;
     else BN = 256;
     const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
-    if (tm > 65535 || tn > 65535) return CDG_ERR_UNSUPPORTED;
+    if (tn > (1 << 30) || tm > (1 << 30)) return CDG_ERR_UNSUPPORTED;
     const int kb_total = (int)((g.K + BK - 1) / BK);
     // split-K, for two reasons:
     //  (1) accuracy: the tensor core accumulates in fp32 with truncation, whose error grows linearly with the
@@ -476,20 +606,50 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     constexpr int KB_CAP = 64;
     int splits = (kb_total + KB_CAP - 1) / KB_CAP;
     const int64_t tiles = tm * tn;
-    if (tiles * splits < kNumSMs && kb_total >= 8) {
+    if (tiles * splits < kNumSMs && kb_total >= 8 && g.epi != EPI_RECON) {
         int want = (int)imin64((kNumSMs + tiles - 1) / tiles, kb_total / 4);
         splits = (int)imax64(splits, imin64(want, 64));
     }
     if (splits < 1) splits = 1;
     int kb_per = (kb_total + splits - 1) / splits;
     splits = (kb_total + kb_per - 1) / kb_per;
-    if (splits > 65535) return CDG_ERR_UNSUPPORTED;
+    if (g.epi == EPI_RECON && splits > 1) return CDG_ERR_UNSUPPORTED;
+    pl->g = g; pl->sc_m = sc_m; pl->sc_n = sc_n; pl->aux_sm = aux_sm; pl->aux_sn = aux_sn; pl->bias_on_m = bias_on_m;
+    pl->BN = BN; pl->splits = splits; pl->kb_total = kb_total; pl->kb_per = kb_per; pl->tm = tm; pl->tn = tn;
+    pl->a_mn = a_mn; pl->b_mn = b_mn;
+    return CDG_OK;
+}
+
+bool gemm_tc_can(const GemmDesc& g) {
+    Plan pl;
+    return plan_gemm(g, &pl) == CDG_OK;
+}
+
+static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
+    using namespace tc;
+    Plan pl;
+    const int pr = plan_gemm(g0, &pl);
+    if (pr != CDG_OK) return pr;
+    const GemmDesc& g = pl.g;
+    const int BN = pl.BN, splits = pl.splits;
 
     Params p;
-    p.C = g.C; p.sc_m = sc_m; p.sc_n = sc_n; p.M = g.M; p.N = g.N;
+    p.C = g.C; p.sc_m = pl.sc_m; p.sc_n = pl.sc_n; p.M = g.M; p.N = g.N;
     p.epi = g.epi; p.act = g.act; p.accumulate = g.accumulate; p.atomic = splits > 1;
-    p.bias = g.bias; p.bias_on_m = bias_on_m; p.aux = g.aux; p.aux_sm = aux_sm; p.aux_sn = aux_sn;
-    p.kb_total = kb_total; p.kb_per_split = kb_per;
+    p.bias = g.bias; p.bias_on_m = pl.bias_on_m; p.aux = g.aux; p.aux_sm = pl.aux_sm; p.aux_sn = pl.aux_sn;
+    p.rx = g.recon_x; p.rx_ld = g.ld_x; p.rxhat = g.recon_xhat; p.racc = g.recon_acc; p.inv_batch = g.inv_batch;
+    p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per;
+    p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
+    // 128-bit epilogue path: row-major output whose rows, bias, aux and recon operands are 16-byte aligned
+    p.vec = (p.sc_n == 1 && p.sc_m % 4 == 0 && al16(p.C)) ? 1 : 0;
+    if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT || g.epi == EPI_RECON) && !pl.bias_on_m && !al16(g.bias)) p.vec = 0;
+    if (g.epi == EPI_MUL_DACT && !(p.aux_sn == 1 && p.aux_sm % 4 == 0 && al16(g.aux))) p.vec = 0;
+    if (g.epi == EPI_RECON) {
+        if (!g.recon_x) { set_error("EPI_RECON without target"); return CDG_ERR_INVALID; }
+        if (!(g.ld_x % 4 == 0 && al16(g.recon_x) && (!g.recon_xhat || al16(g.recon_xhat)))) p.vec = 0;
+    }
 
     if (p.atomic && !g.accumulate) {
         // zero C (in the caller's orientation) before the partial sums are added
@@ -498,22 +658,22 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     }
 
     CUtensorMap ta, tb;
-    const int b_box = b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4)) : (BN <= 256 ? BN : BN / 2);
-    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, a_mn, 128, &ta));
-    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, b_mn, b_box, &tb));
-    dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+    const int b_box = pl.b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4)) : (BN <= 256 ? BN : BN / 2);
+    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, &ta));
+    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, &tb));
+    dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
     if (passes == 1) {
-        if (BN == 128) r = launch_layout<128, 1>(a_mn, b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 1>(a_mn, b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 1>(a_mn, b_mn, ta, tb, p, grid, s);
+        if (BN == 128) r = launch_layout<128, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
     } else {
-        if (BN == 128) r = launch_layout<128, 3>(a_mn, b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 3>(a_mn, b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 3>(a_mn, b_mn, ta, tb, p, grid, s);
+        if (BN == 128) r = launch_layout<128, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
     }
     CDG_TRY(r);
-    if (p.atomic && g.epi != EPI_NONE)
+    if (p.atomic && g0.epi != EPI_NONE)
         CDG_TRY(launch_bias_act(g0.C, g0.ldc, g0.M, g0.N, g0.bias, g0.epi, g0.act, g0.aux, g0.ld_aux, s));
     return CDG_OK;
 }

@@ -127,19 +127,57 @@ static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1,
     return CDG_OK;
 }
 
-// decoders: z[B,d] -> pre[B,P] (live columns only)
-static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre) {
+// last decoder Linear of decoder k restricted to its live columns, optionally with the reconstruction
+// head (tanh, 0.5*(xhat-x)^2, d/d pre) fused into the GEMM epilogue
+static GemmDesc dec_out_desc(const Ctx& c, int k, int64_t B, float* pre, const float* x, float* xhat, double* acc) {
     const cdg_pendulum_config& cf = c.p->c;
-    const int64_t H = cf.hidden, d = cf.node, P = cf.input_dim;
+    const int64_t H = cf.hidden, P = cf.input_dim;
+    const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
+    const cdg_linear& L = cf.dec[k][2];
+    GemmDesc g;
+    g.A = c.W + c.w.a2[k]; g.sa_m = H; g.sa_k = 1;
+    g.B = c.P + L.w + lo * L.in; g.sb_n = L.in; g.sb_k = 1;
+    g.C = pre + lo; g.ldc = P; g.M = B; g.N = n; g.K = L.in;
+    g.bias = c.P + L.b + lo; g.act = CDG_ACT_ELU;
+    if (x) {
+        g.epi = EPI_RECON; g.recon_x = x + lo; g.ld_x = P; g.recon_xhat = xhat ? xhat + lo : nullptr;
+        g.recon_acc = acc + ACC_RECON; g.inv_batch = 1.f / (float)B;
+    } else {
+        g.epi = EPI_BIAS;
+    }
+    return g;
+}
+
+// decoders: z[B,d] -> pre[B,P] (live columns only).  With x != nullptr the reconstruction head is fused.
+static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, const float* x = nullptr,
+                        float* xhat = nullptr, double* acc = nullptr) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node;
     for (int k = 0; k < cf.n_dec; ++k) {
         float* a1 = c.W + c.w.a1[k];
         float* a2 = c.W + c.w.a2[k];
         CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
-        const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
-        if (n > 0) CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], lo, n, pre + lo, P, B, false, PROF_DEC2_FWD));
+        if (cf.col_hi[k] - cf.col_lo[k] > 0) {
+            c.mark(PROF_DEC2_FWD);
+            const GemmDesc g = dec_out_desc(c, k, B, pre, x, xhat, acc);
+            if (x) CDG_TRY(gemm_tc(g, c.mode == CDG_GEMM_TC1X ? 1 : 3, nullptr, 0, c.s));
+            else CDG_TRY(gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s));
+        }
     }
     return CDG_OK;
+}
+
+static bool covers_all(const cdg_pendulum_config& c);
+// can the reconstruction head be fused into every decoder's output GEMM?
+static bool recon_fusable(const Ctx& c, int64_t B, float* pre, const float* x, float* xhat, double* acc) {
+    const cdg_pendulum_config& cf = c.p->c;
+    if (c.mode == CDG_GEMM_SIMT || !covers_all(cf)) return false;
+    for (int k = 0; k < cf.n_dec; ++k) {
+        if (cf.col_hi[k] - cf.col_lo[k] <= 0) continue;
+        if (!gemm_tc_can(dec_out_desc(c, k, B, pre, x, xhat, acc))) return false;
+    }
+    return true;
 }
 
 static bool covers_all(const cdg_pendulum_config& c) {
@@ -262,9 +300,13 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     c.mark(PROF_LATENT);
     CDG_TRY(launch_align(al, s));
 
-    CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
-    c.mark(PROF_RECON);
-    CDG_TRY(launch_recon(W + c.w.pre, io->x, io->xhat, B, Pd, acc, 1, s));
+    if (recon_fusable(c, B, W + c.w.pre, io->x, io->xhat, acc)) {
+        CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre, io->x, io->xhat, acc));
+    } else {
+        CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
+        c.mark(PROF_RECON);
+        CDG_TRY(launch_recon(W + c.w.pre, io->x, io->xhat, B, Pd, acc, 1, s));
+    }
 
     // ---- backward ----
     float* g_pre = W + c.w.pre;
