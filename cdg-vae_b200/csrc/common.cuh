@@ -131,6 +131,7 @@ struct GemmDesc {
 };
 
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
+int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG_ERR_UNSUPPORTED otherwise
 // tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the
 // dispatcher can route it to the SIMT kernel.
 int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_bytes, cudaStream_t s);

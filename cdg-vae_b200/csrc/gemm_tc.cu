@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -34,12 +35,11 @@ namespace cdg {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per K-block = one 128-byte swizzle row
+// K-block = one swizzle row: 32 floats (SWIZZLE_128B, 2-stage ring) or 16 floats (SWIZZLE_64B, 4-stage ring).
+// The ring holds the same bytes either way; the finer blocks keep more TMA loads in flight per byte.
 constexpr int NUM_CONV_WARPS = 8;
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS + NUM_EPI_WARPS);
-constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int STAGES = 2;
 
 struct Params {
     float* C; int64_t sc_m, sc_n;
@@ -50,6 +50,7 @@ struct Params {
     const float* rx; int64_t rx_ld; float* rxhat; double* racc; float inv_batch;   // EPI_RECON
     int kb_total, kb_per_split;                 // K-blocks (of BK) in total / per split
     int tiles_n, splits;
+    int rawhi;                                  // K-major operands: leave the raw tile as `hi` (tensor core truncates)
     int64_t work_total;                         // tiles_m * tiles_n * splits
 };
 
@@ -92,6 +93,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// A operand from tensor memory (128 lanes = rows, one column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -117,13 +133,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
+template <int BK>
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address            bits [0,14)
     d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset       bits [32,46)
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;       // stride byte offset: one 8-row swizzle group, bits [32,46)
     d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;        // layout type SWIZZLE_128B (2) / SWIZZLE_64B (4)
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -137,11 +154,20 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-// byte offset of element (row r, k) inside a K-major SWIZZLE_128B tile (16-byte chunk index XOR row%8)
-__device__ __forceinline__ uint32_t sw128_chunk(uint32_t r, uint32_t chunk) { return r * 128u + ((chunk ^ (r & 7u)) << 4); }
+// byte offset of the 16-byte chunk `chunk` of row r inside a K-major swizzled tile:
+//   SWIZZLE_128B: address bits [4,7) ^= bits [7,10)  -> chunk ^ (r % 8)      (rows of 128 B)
+//   SWIZZLE_64B : address bits [4,6) ^= bits [7,9)   -> chunk ^ ((r / 2) % 4) (rows of 64 B)
+template <int BK>
+__device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
+    if (BK == 32) return r * 128u + ((chunk ^ (r & 7u)) << 4);
+    return r * 64u + ((chunk ^ ((r >> 1) & 3u)) << 4);
+}
 
-template <int BN>
+template <int BN, int BK>
 struct Cfg {
+    static constexpr int STAGES = BK == 32 ? 2 : 4;
+    static constexpr int ROW_BYTES = BK * 4;
+    static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // hi + lo for both operands
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -150,6 +176,12 @@ struct Cfg {
     static constexpr int N0 = BN <= 256 ? BN : 160;                 // first MMA's N
     static constexpr int N1 = BN - N0;                              // second MMA's N (0 = none)
     static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;            // TMEM accumulator buffers
+    // With a single accumulator (BN = 304) the remaining TMEM columns hold the A operand ring (hi and lo,
+    // BK columns each per stage): the MMA then reads A from tensor memory, which removes A from the shared
+    // memory data path -- the path ncu shows saturated (LSU + tensor wavefronts at 92 % of peak).
+    static constexpr bool A_TMEM = (NACC == 1);
+    static constexpr int A_COL0 = (BN + 31) / 32 * 32;
+    static_assert(!A_TMEM || A_COL0 + STAGES * 2 * BK <= 512, "A ring does not fit tensor memory");
     static constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
@@ -158,12 +190,24 @@ struct Cfg {
 // ---- converter --------------------------------------------------------------------------------
 // K-major source: the raw tile already sits in the `hi` buffer in its final (swizzled) place.  Any
 // element-wise rewrite keeps the layout, so the tile is processed as a flat float4 array.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 template <int PASSES>
-__device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int bytes, int ct) {
+__device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int bytes, int ct, int rawhi) {
     if (PASSES == 1) return;
     float4* h = reinterpret_cast<float4*>(hi);
     float4* l = reinterpret_cast<float4*>(lo);
     const int n = bytes / 16;
+    if (rawhi) {
+        // the tensor core ignores the 13 low mantissa bits of a tf32 operand: hi = trunc(raw) is implicit
+#pragma unroll 4
+        for (int i = ct; i < n; i += 32 * NUM_CONV_WARPS) {
+            const float4 r = h[i];
+            l[i] = make_float4(r.x - tf32_trunc(r.x), r.y - tf32_trunc(r.y), r.z - tf32_trunc(r.z), r.w - tf32_trunc(r.w));
+        }
+        return;
+    }
+#pragma unroll 4
     for (int i = ct; i < n; i += 32 * NUM_CONV_WARPS) {
         const float4 r = h[i];
         float4 a, b;
@@ -174,11 +218,48 @@ __device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int byt
     }
 }
 
+// A operand -> tensor memory.  Converter warp w owns TMEM lane quarter w % 4 (rows 32q..32q+31, one per lane); the
+// two warps of a quarter split the K-block.  Source: K-major raw tile (swizzled, in `hi`) or MN-major raw box
+// ([k][128], in `lo`).
+template <int PASSES, int BK, bool MN>
+__device__ __forceinline__ void convert_a_tmem(const uint8_t* hi, const uint8_t* lo, uint32_t tmem_hi, int warp, int lane) {
+    constexpr int NV = BK / 2;                       // values per thread: 16 (BK = 32) or 8 (BK = 16)
+    const int q = warp & 3, khalf = (warp - 2) >> 2;
+    const uint32_t row = (uint32_t)(q * 32 + lane);
+    const int kbeg = khalf * NV;
+    float v[NV];
+    if (!MN) {
+#pragma unroll
+        for (int c = 0; c < NV / 4; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(hi + sw_chunk<BK>(row, (uint32_t)(kbeg / 4 + c)));
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        }
+    } else {
+        const float* raw = reinterpret_cast<const float*>(lo);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = raw[(kbeg + j) * BM + row];
+    }
+    uint32_t h[NV], l[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float a = PASSES == 1 ? v[j] : tf32_rna(v[j]);
+        h[j] = __float_as_uint(a);
+        l[j] = __float_as_uint(v[j] - a);
+    }
+    const uint32_t base = tmem_hi + ((uint32_t)(q * 32) << 16) + (uint32_t)kbeg;
+#pragma unroll
+    for (int j = 0; j < NV; j += 8) {
+        tmem_st8(base + j, h + j);
+        if (PASSES == 3) tmem_st8(base + BK + j, l + j);
+    }
+    tmem_st_wait();
+}
+
 // MN-major source: raw boxes [BK k-rows][CW mn] landed in the `lo` buffer (chunk c at byte c*CW*128).
 // Each thread owns one mn column of a chunk: read its BK values (conflict-free), wait until every
 // converter thread has read the chunk (its bytes are about to be overwritten), then write the K-major
 // rows of hi and lo.
-template <int PASSES, int ROWS, int CW>
+template <int PASSES, int ROWS, int CW, int BK>
 __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct) {
     constexpr int NT = 32 * NUM_CONV_WARPS;
     constexpr int IT = (ROWS + NT - 1) / NT;
@@ -188,7 +269,7 @@ __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct
         const int j = ct + it * NT;                       // mn index inside the tile
         if (j < ROWS) {
             const int c = j / CW, col = j - c * CW;
-            const float* raw = reinterpret_cast<const float*>(lo + (size_t)c * CW * 128);
+            const float* raw = reinterpret_cast<const float*>(lo + (size_t)c * CW * (BK * 4));
 #pragma unroll
             for (int k = 0; k < BK; ++k) v[it][k] = raw[k * CW + col];
         }
@@ -202,7 +283,7 @@ __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct
 #pragma unroll
             for (int ch = 0; ch < BK / 4; ++ch) {
                 const float x0 = v[it][4 * ch], x1 = v[it][4 * ch + 1], x2 = v[it][4 * ch + 2], x3 = v[it][4 * ch + 3];
-                const uint32_t off = sw128_chunk((uint32_t)j, ch);
+                const uint32_t off = sw_chunk<BK>((uint32_t)j, ch);
                 if (PASSES == 1) {
                     *reinterpret_cast<float4*>(hi + off) = make_float4(x0, x1, x2, x3);
                 } else {
@@ -225,11 +306,14 @@ __device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t 
     return val;
 }
 
-template <int BN, int PASSES, bool A_MN, bool B_MN>
+template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-    using C_ = Cfg<BN>;
+    using C_ = Cfg<BN, BK>;
     constexpr int NACC = C_::NACC;
+    constexpr int STAGES = C_::STAGES;
+    constexpr int A_BYTES = C_::A_BYTES;
+    constexpr int ROWB = C_::ROW_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
@@ -297,11 +381,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!B_MN) {
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
-                            tma_load_2d(smem_u32(b_hi(s) + r * 128), &tmB, full, k0, n_blk * BN + r);
+                            tma_load_2d(smem_u32(b_hi(s) + r * ROWB), &tmB, full, k0, n_blk * BN + r);
                     } else {
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_CW)
-                            tma_load_2d(smem_u32(b_lo(s) + r * 128), &tmB, full, n_blk * BN + r, k0);
+                            tma_load_2d(smem_u32(b_lo(s) + r * ROWB), &tmB, full, n_blk * BN + r, k0);
                     }
                 }
             }
@@ -324,8 +408,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(smem_u32(&bars[STAGES + s]), ph);
                     tc_fence_after();
-                    const uint64_t dah = make_kmajor_desc(smem_u32(a_hi(s))), dal = make_kmajor_desc(smem_u32(a_lo(s)));
-                    const uint64_t dbh = make_kmajor_desc(smem_u32(b_hi(s))), dbl = make_kmajor_desc(smem_u32(b_lo(s)));
+                    const uint64_t dah = make_kmajor_desc<BK>(smem_u32(a_hi(s))), dal = make_kmajor_desc<BK>(smem_u32(a_lo(s)));
+                    const uint64_t dbh = make_kmajor_desc<BK>(smem_u32(b_hi(s))), dbl = make_kmajor_desc<BK>(smem_u32(b_lo(s)));
 #pragma unroll
                     for (int pass = 0; pass < PASSES; ++pass) {
                         // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
@@ -335,9 +419,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int k = 0; k < BK / 8; ++k) {
                             const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                            umma_tf32(tacc, da + koff, db + koff, idesc0, acc);
-                            if (C_::N1 > 0)
-                                umma_tf32(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 128) >> 4), idesc1, acc);
+                            if (C_::A_TMEM) {
+                                const uint32_t ta = tmem_base + C_::A_COL0 + s * 2 * BK + ((PASSES == 3 && pass == 0) ? BK : 0) + k * 8;
+                                umma_tf32_ts(tacc, ta, db + koff, idesc0, acc);
+                                if (C_::N1 > 0)
+                                    umma_tf32_ts(tacc + C_::N0, ta, db + koff + (uint64_t)((C_::N0 * ROWB) >> 4), idesc1, acc);
+                            } else {
+                                umma_tf32(tacc, da + koff, db + koff, idesc0, acc);
+                                if (C_::N1 > 0)
+                                    umma_tf32(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * ROWB) >> 4), idesc1, acc);
+                            }
                         }
                     }
                     umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
@@ -356,10 +447,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
-                if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct);
-                else convert_mnmajor<PASSES, BM, 128>(a_hi(s), a_lo(s), ct);
-                if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct);
-                else convert_mnmajor<PASSES, BN, C_::B_CW>(b_hi(s), b_lo(s), ct);
+                if (C_::A_TMEM) {
+                    convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), tmem_base + C_::A_COL0 + s * 2 * BK, warp, lane);
+                } else {
+                    if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct, p.rawhi);
+                    else convert_mnmajor<PASSES, BM, 128, BK>(a_hi(s), a_lo(s), ct);
+                }
+                if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
+                else convert_mnmajor<PASSES, BN, C_::B_CW, BK>(b_hi(s), b_lo(s), ct);
+                tc_fence_before();                                   // tcgen05.st (A ring) ordered before the arrive
                 fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
                 mbar_arrive(smem_u32(&bars[STAGES + s]));
             }
@@ -378,21 +474,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
             const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
             const bool row_ok = m < p.M;
+            // side operand of the vector path, read one 16-column chunk ahead of its use so that its DRAM
+            // latency overlaps the previous chunk's math (one warp per SM sub-partition has no other cover)
+            const float* side = nullptr;
+            if (p.vec && !p.atomic && row_ok) {
+                if (p.epi == EPI_RECON) side = p.rx + m * p.rx_ld + (int64_t)n_blk * BN;
+                else if (p.epi == EPI_MUL_DACT) side = p.aux + m * p.aux_sm + (int64_t)n_blk * BN;
+            }
+            float4 nxt[4];
+            auto fetch = [&](int c0) {
+                const int64_t n0 = (int64_t)n_blk * BN + c0;
+                if (side && c0 < BN && n0 + 16 <= p.N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) nxt[g] = __ldg(reinterpret_cast<const float4*>(side + c0 + 4 * g));
+                }
+            };
+            fetch(0);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
+                float4 cur[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
+                fetch(c0 + 16);
                 const int64_t n0 = (int64_t)n_blk * BN + c0;
                 if (!row_ok || n0 >= p.N) continue;
                 if (p.vec && !p.atomic && n0 + 16 <= p.N) {
                     float* crow = p.C + m * p.sc_m + n0;
                     if (p.epi == EPI_RECON) {
-                        const float* xr = p.rx + m * p.rx_ld + n0;
                         float* xh = p.rxhat ? p.rxhat + m * p.sc_m + n0 : nullptr;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * g);
-                            const float4 xx = __ldg(reinterpret_cast<const float4*>(xr + 4 * g));
+                            const float4 xx = cur[g];
                             float t[4] = {tanhf(v[4 * g] + bb.x), tanhf(v[4 * g + 1] + bb.y), tanhf(v[4 * g + 2] + bb.z),
                                           tanhf(v[4 * g + 3] + bb.w)};
                             const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
@@ -424,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int e = 0; e < 4; ++e) o[e] = act_fwd(o[e], p.act);
                             }
                             if (p.epi == EPI_MUL_DACT) {
-                                const float4 hh = *reinterpret_cast<const float4*>(p.aux + m * p.aux_sm + n0 + 4 * g);
+                                const float4 hh = cur[g];
                                 o[0] *= act_bwd_from_out(hh.x, p.act); o[1] *= act_bwd_from_out(hh.y, p.act);
                                 o[2] *= act_bwd_from_out(hh.z, p.act); o[3] *= act_bwd_from_out(hh.w, p.act);
                             }
@@ -491,7 +606,7 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-    const void* ptr; int64_t rows, k, row_stride, k_stride; int box0, box1, mn;
+    const void* ptr; int64_t rows, k, row_stride, k_stride; int box0, box1, mn;   // box0/box1 include BK
     bool operator<(const MapKey& o) const {
         return std::tie(ptr, rows, k, row_stride, k_stride, box0, box1, mn) <
                std::tie(o.ptr, o.rows, o.k, o.row_stride, o.k_stride, o.box0, o.box1, o.mn);
@@ -503,7 +618,7 @@ static std::mutex g_maps_mu;
 // Operand X(r,k) = X[r*s_r + k*s_k], r < rows, k < K.  K-major (s_k == 1): dims {K, rows}, box {32, box_rows},
 // SWIZZLE_128B.  MN-major (s_r == 1): dims {rows, K}, box {cw, 32}, no swizzle.
 static int make_map(const float* X, int64_t rows, int64_t K, int64_t s_r, int64_t s_k, bool mn_major, int box_rows,
-                    CUtensorMap* out) {
+                    int BK, CUtensorMap* out) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
     MapKey key{X, rows, K, s_r, s_k, mn_major ? box_rows : BK, mn_major ? BK : box_rows, mn_major ? 1 : 0};
@@ -517,10 +632,10 @@ static int make_map(const float* X, int64_t rows, int64_t K, int64_t s_r, int64_
     CUtensorMapSwizzle sw;
     if (!mn_major) {
         dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; strides[0] = (cuuint64_t)s_r * 4;
-        box[0] = BK; box[1] = (cuuint32_t)box_rows; sw = CU_TENSOR_MAP_SWIZZLE_128B;
+        box[0] = (cuuint32_t)BK; box[1] = (cuuint32_t)box_rows; sw = BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     } else {
         dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; strides[0] = (cuuint64_t)s_k * 4;
-        box[0] = (cuuint32_t)box_rows; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+        box[0] = (cuuint32_t)box_rows; box[1] = (cuuint32_t)BK; sw = CU_TENSOR_MAP_SWIZZLE_NONE;
     }
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -539,26 +654,26 @@ static bool operand_ok(const float* X, int64_t s_r, int64_t s_k, int64_t rows, i
     return false;
 }
 
-template <int BN, int PASSES, bool A_MN, bool B_MN>
+template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t s) {
-    auto kern = gemm_tc_kernel<BN, PASSES, A_MN, B_MN>;
+    auto kern = gemm_tc_kernel<BN, BK, PASSES, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
-        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK>::SMEM));
         attr_done = true;
     }
-    kern<<<grid, THREADS, Cfg<BN>::SMEM, s>>>(ta, tb, p);
+    kern<<<grid, THREADS, Cfg<BN, BK>::SMEM, s>>>(ta, tb, p);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }
 
-template <int BN, int PASSES>
+template <int BN, int BK, int PASSES>
 static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid,
                          cudaStream_t s) {
-    if (!a_mn && !b_mn) return launch<BN, PASSES, false, false>(ta, tb, p, grid, s);
-    if (!a_mn && b_mn) return launch<BN, PASSES, false, true>(ta, tb, p, grid, s);
-    if (a_mn && !b_mn) return launch<BN, PASSES, true, false>(ta, tb, p, grid, s);
-    return launch<BN, PASSES, true, true>(ta, tb, p, grid, s);
+    if (!a_mn && !b_mn) return launch<BN, BK, PASSES, false, false>(ta, tb, p, grid, s);
+    if (!a_mn && b_mn) return launch<BN, BK, PASSES, false, true>(ta, tb, p, grid, s);
+    if (a_mn && !b_mn) return launch<BN, BK, PASSES, true, false>(ta, tb, p, grid, s);
+    return launch<BN, BK, PASSES, true, true>(ta, tb, p, grid, s);
 }
 
 }  // namespace tc
@@ -572,7 +687,7 @@ struct Plan {
 };
 
 // shape / layout analysis shared by gemm_tc and gemm_tc_can
-static int plan_gemm(const GemmDesc& g0, Plan* pl) {
+static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     using namespace tc;
     GemmDesc g = g0;
     int64_t sc_m = g.ldc, sc_n = 1, aux_sm = g.ld_aux, aux_sn = 1;
@@ -603,7 +718,7 @@ static int plan_gemm(const GemmDesc& g0, Plan* pl) {
     //      KB_CAP K-blocks (K = 2048) keeps a partial sum at ~7e-6; partials are combined with fp32
     //      round-to-nearest adds (red.global.add.f32).
     //  (2) occupancy: fill the chip when the tile grid is small.
-    constexpr int KB_CAP = 64;
+    const int KB_CAP = 2048 / BK;
     int splits = (kb_total + KB_CAP - 1) / KB_CAP;
     const int64_t tiles = tm * tn;
     if (tiles * splits < kNumSMs && kb_total >= 8 && g.epi != EPI_RECON) {
@@ -620,9 +735,19 @@ static int plan_gemm(const GemmDesc& g0, Plan* pl) {
     return CDG_OK;
 }
 
+// K-block of the 3xTF32 kernels: 16 (SWIZZLE_64B, 4 stages) unless CDG_TC_BK=32 asks for the 2-stage variant
+static int default_bk() {
+    static int bk = 0;
+    if (bk == 0) {
+        const char* e = getenv("CDG_TC_BK");
+        bk = (e && atoi(e) == 32) ? 32 : 16;
+    }
+    return bk;
+}
+
 bool gemm_tc_can(const GemmDesc& g) {
     Plan pl;
-    return plan_gemm(g, &pl) == CDG_OK;
+    return plan_gemm(g, default_bk(), &pl) == CDG_OK;
 }
 
 static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -630,7 +755,8 @@ static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     using namespace tc;
     Plan pl;
-    const int pr = plan_gemm(g0, &pl);
+    const int BK = passes == 1 ? 32 : default_bk();
+    const int pr = plan_gemm(g0, BK, &pl);
     if (pr != CDG_OK) return pr;
     const GemmDesc& g = pl.g;
     const int BN = pl.BN, splits = pl.splits;
@@ -642,6 +768,13 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     p.rx = g.recon_x; p.rx_ld = g.ld_x; p.rxhat = g.recon_xhat; p.racc = g.recon_acc; p.inv_batch = g.inv_batch;
     p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per;
     p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
+    {
+        static int rawhi = -1;
+        // default on: measured on B200, tcgen05 kind::tf32 ignores the 13 low mantissa bits (results with the raw
+        // tile as `hi` match the explicitly rounded split to 2e-7); CDG_TC_RAWHI=0 restores the explicit rewrite
+        if (rawhi < 0) { const char* e = getenv("CDG_TC_RAWHI"); rawhi = (e && atoi(e) == 0) ? 0 : 1; }
+        p.rawhi = rawhi;
+    }
     // 128-bit epilogue path: row-major output whose rows, bias, aux and recon operands are 16-byte aligned
     p.vec = (p.sc_n == 1 && p.sc_m % 4 == 0 && al16(p.C)) ? 1 : 0;
     if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT || g.epi == EPI_RECON) && !pl.bias_on_m && !al16(g.bias)) p.vec = 0;
@@ -659,18 +792,22 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
 
     CUtensorMap ta, tb;
     const int b_box = pl.b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : BN / 4)) : (BN <= 256 ? BN : BN / 2);
-    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, &ta));
-    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, &tb));
+    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, BK, &ta));
+    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
     if (passes == 1) {
-        if (BN == 128) r = launch_layout<128, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+    } else if (BK == 32) {
+        if (BN == 128) r = launch_layout<128, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
     } else {
-        if (BN == 128) r = launch_layout<128, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 128) r = launch_layout<128, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
     }
     CDG_TRY(r);
     if (p.atomic && g0.epi != EPI_NONE)

@@ -1,0 +1,123 @@
+// Memory-bound kernels for the contractions with one tiny extent, where neither a tensor-core tile nor a
+// 128x128 SIMT tile makes sense (all of them stream one [batch, 300] activation once):
+//   smallk_elem   K <= 8   decoder first Linear (K = 1, 2: modules/model.py:245) and the dgrad of the
+//                          encoder head (K = 2d = 8: model.py:224)
+//   rowdot        N <= 8   encoder head forward (N = 2d) and the dgrad of the decoder first Linear (N = 1, 2)
+//   skinny_wgrad  min(M,N) <= 8, contraction over the batch: wgrad of those two layers
+#include "common.cuh"
+
+namespace cdg {
+
+__global__ void __launch_bounds__(256) smallk_elem_kernel(GemmDesc g) {
+    const int64_t total = g.M * g.N;
+    const int K = (int)g.K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / g.N, n = i - m * g.N;
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(g.A[m * g.sa_m + k * g.sa_k], __ldg(g.B + n * g.sb_n + k * g.sb_k), s);
+        float* c = g.C + m * g.ldc + n;
+        if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) s += g.bias[n];
+        if (g.epi == EPI_BIAS_ACT) s = act_fwd(s, g.act);
+        if (g.epi == EPI_MUL_DACT) s *= act_bwd_from_out(g.aux[m * g.ld_aux + n], g.act);
+        if (g.accumulate) s += *c;
+        *c = s;
+    }
+}
+
+// one warp per output row; N <= 8 accumulators per lane; A rows are contiguous (sa_k == 1)
+__global__ void __launch_bounds__(256) rowdot_kernel(GemmDesc g) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int N = (int)g.N;
+    for (int64_t m = warp0; m < g.M; m += nwarps) {
+        float acc[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+        const float* a = g.A + m * g.sa_m;
+        for (int64_t k = lane; k < g.K; k += 32) {
+            const float av = a[k];
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                if (n < N) acc[n] = fmaf(av, __ldg(g.B + n * g.sb_n + k * g.sb_k), acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+            if (n < N) acc[n] = warp_sum(acc[n]);
+        if (lane < N) {
+            float s = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                if (n == lane) s = acc[n];
+            float* c = g.C + m * g.ldc + lane;
+            if (g.epi == EPI_BIAS) s += g.bias[lane];
+            if (g.accumulate) s += *c;
+            *c = s;
+        }
+    }
+}
+
+// C[m*ldc + n] += sum_k A[m + k*sa_k] * B[n + k*sb_k]; `wide_is_m` tells which side has the long extent
+struct SkinnyW {
+    const float* wide; int64_t wide_ld; const float* narrow; int64_t narrow_ld;
+    float* C; int64_t c_sw, c_sr;          // C[w*c_sw + r*c_sr]
+    int64_t W, K; int R; int k_chunk;
+};
+__global__ void __launch_bounds__(128) skinny_wgrad_kernel(SkinnyW a) {
+    const int64_t w = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t kbeg = (int64_t)blockIdx.y * a.k_chunk, kend = min(a.K, kbeg + (int64_t)a.k_chunk);
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    if (w < a.W) {
+        for (int64_t k = kbeg; k < kend; ++k) {
+            const float wv = a.wide[k * a.wide_ld + w];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < a.R) acc[r] = fmaf(wv, __ldg(a.narrow + k * a.narrow_ld + r), acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < a.R) atomicAdd(a.C + w * a.c_sw + r * a.c_sr, acc[r]);
+    }
+}
+
+// returns CDG_ERR_UNSUPPORTED when the contraction is not one of the skinny shapes
+int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0) return CDG_OK;
+    if (g.K <= 8) {
+        const int64_t total = g.M * g.N;
+        const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 16);
+        smallk_elem_kernel<<<blocks, 256, 0, s>>>(g);
+        CDG_CHECK_LAUNCH();
+        return CDG_OK;
+    }
+    if (g.N <= 8 && g.sa_k == 1 && (g.epi == EPI_NONE || g.epi == EPI_BIAS)) {
+        const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 16);
+        rowdot_kernel<<<blocks, 256, 0, s>>>(g);
+        CDG_CHECK_LAUNCH();
+        return CDG_OK;
+    }
+    if ((g.M <= 8 || g.N <= 8) && g.sa_m == 1 && g.sb_n == 1 && g.epi == EPI_NONE) {
+        SkinnyW a;
+        const bool wide_is_m = g.M > g.N;
+        a.wide = wide_is_m ? g.A : g.B; a.wide_ld = wide_is_m ? g.sa_k : g.sb_k;
+        a.narrow = wide_is_m ? g.B : g.A; a.narrow_ld = wide_is_m ? g.sb_k : g.sa_k;
+        a.C = g.C; a.c_sw = wide_is_m ? g.ldc : 1; a.c_sr = wide_is_m ? 1 : g.ldc;
+        a.W = wide_is_m ? g.M : g.N; a.R = (int)(wide_is_m ? g.N : g.M); a.K = g.K;
+        const int wb = (int)((a.W + 127) / 128);
+        int ksplit = (int)imax64(1, imin64((kNumSMs * 8) / wb, (g.K + 255) / 256));
+        a.k_chunk = (int)((g.K + ksplit - 1) / ksplit);
+        ksplit = (int)((g.K + a.k_chunk - 1) / a.k_chunk);
+        if (!g.accumulate) {
+            if (g.ldc == g.N) CDG_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * g.M * g.N, s));
+            else CDG_CHECK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, s));
+        }
+        skinny_wgrad_kernel<<<dim3(wb, ksplit), 128, 0, s>>>(a);
+        CDG_CHECK_LAUNCH();
+        return CDG_OK;
+    }
+    return CDG_ERR_UNSUPPORTED;
+}
+
+}  // namespace cdg
