@@ -26,6 +26,13 @@ MACS_U = 19_522_800      # fwd 7,736,400 + wgrad 7,736,400 + dgra
 MACS_L = 3_778_800 * 2 + 92_400   # labeled sample: encoder fwd + wgrad + dgrad (L1, L2)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_enc0_fwd_tc3x.txt): encoder first Linear forward,
+# x[32768,12288] @ W0[300,12288]^T.  Algorithmic bytes of that launch: x once + W0 once + h1 written once.
+NCU_TRAFFIC = {"bytes": 1.791965e9 + 39.7696e6, "launch": "gemm_tc_kernel<304,16,3,0,0> enc0 forward, M=32768 N=300 K=12288",
+               "algorithmic": 32768 * 12288 * 4 + 300 * 12288 * 4 + 32768 * 300 * 4}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -176,6 +183,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     B, BL = args.batch, args.batch // 4
@@ -263,7 +271,10 @@ def main():
                        "l2_policy": f"inputs larger than L2: x is {B * 49152 / 1e9:.1f} GB per step",
                        "samples_counted": "unlabeled samples (the labeled quarter-batch rides along)"},
             "roofline": {"bound": "tensor", "kernel": "the GEMM kernel family (all Linear fwd/dgrad/wgrad launches of the step)",
-                         "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+                         "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+                         "traffic": NCU_TRAFFIC["bytes"], "traffic_launch": NCU_TRAFFIC["launch"],
+                         "traffic_algorithmic": NCU_TRAFFIC["algorithmic"],
+                         "frac_of_fp32_faithful_ceiling": ach / (tf_sus / 6.0),
                          "peak_source": f"bf16 dense sustained, {src} (MEASURED_PEAKS.json)",
                          "algorithmic_flops_per_step": flops / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,
                          "note": "fp32-faithful arithmetic: 3xTF32 costs 6 bf16-equivalent passes, so frac <= 1/6 in that mode",
