@@ -125,32 +125,60 @@ int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bi
 }
 
 // out[n] += sum_m G[m*ld + n]   (bias gradients: the batch sum autograd performs for nn.Linear)
+// block = 32 lanes x 8 row-lanes; VEC: each lane owns 4 adjacent columns (128-bit loads), 4 rows in flight.
+template <int VEC>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ G, int64_t ld, int64_t M, int64_t N,
                                                      float* __restrict__ out, int rows_per_block) {
-    __shared__ float red[8][33];
+    __shared__ float red[8][32 * VEC + 1];
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
-    const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+    const int64_t n = ((int64_t)blockIdx.x * 32 + lane) * VEC;
     const int64_t mbeg = (int64_t)blockIdx.y * rows_per_block;
     const int64_t mend = min(M, mbeg + rows_per_block);
-    float s = 0.f;
-    if (n < N)
-        for (int64_t m = mbeg + r; m < mend; m += 8) s += G[m * ld + n];
-    red[r][lane] = s;
+    float s[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s[e] = 0.f;
+    if (n < N) {
+        int64_t m = mbeg + r;
+        if (VEC == 4) {
+            for (; m + 24 < mend; m += 32) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(G + (m + 8 * u) * ld + n);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w; }
+            }
+            for (; m < mend; m += 8) {
+                const float4 v = *reinterpret_cast<const float4*>(G + m * ld + n);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            }
+        } else {
+            for (; m < mend; m += 8) s[0] += G[m * ld + n];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) red[r][lane * VEC + e] = s[e];
     __syncthreads();
     if (r == 0 && n < N) {
 #pragma unroll
-        for (int i = 1; i < 8; ++i) s += red[i][lane];
-        atomicAdd(out + n, s);
+        for (int e = 0; e < VEC; ++e) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][lane * VEC + e];
+            atomicAdd(out + n + e, t);
+        }
     }
 }
 
 int launch_colsum(const float* G, int64_t ld, int64_t M, int64_t N, float* out, cudaStream_t s) {
     if (M == 0 || N == 0) return CDG_OK;
-    const int cb = (int)((N + 31) / 32);
-    int rsplit = (int)imin64((M + 255) / 256, imax64(1, (kNumSMs * 4) / cb));
+    const bool vec = N % 4 == 0 && ld % 4 == 0 && (((uintptr_t)G) & 15) == 0;
+    const int cols_per_block = vec ? 128 : 32;
+    const int cb = (int)((N + cols_per_block - 1) / cols_per_block);
+    int rsplit = (int)imin64((M + 255) / 256, imax64(1, (kNumSMs * 8) / cb));
     const int rows = (int)((M + rsplit - 1) / rsplit);
     rsplit = (int)((M + rows - 1) / rows);
-    colsum_kernel<<<dim3(cb, rsplit), 256, 0, s>>>(G, ld, M, N, out, rows);
+    if (vec) colsum_kernel<4><<<dim3(cb, rsplit), 256, 0, s>>>(G, ld, M, N, out, rows);
+    else colsum_kernel<1><<<dim3(cb, rsplit), 256, 0, s>>>(G, ld, M, N, out, rows);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }

@@ -8,9 +8,43 @@
 
 namespace cdg {
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) smallk_elem_kernel(GemmDesc g) {
-    const int64_t total = g.M * g.N;
     const int K = (int)g.K;
+    if (VEC) {
+        // 4 consecutive outputs per thread, 128-bit stores (N % 4 == 0, 16-byte aligned rows)
+        const int64_t n4 = g.N / 4, total = g.M * n4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t m = i / n4, n = (i - m * n4) * 4;
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < K; ++k) {
+                const float a = g.A[m * g.sa_m + k * g.sa_k];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] = fmaf(a, __ldg(g.B + (n + e) * g.sb_n + k * g.sb_k), s[e]);
+            }
+            float* c = g.C + m * g.ldc + n;
+            if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) {
+                const float4 b = *reinterpret_cast<const float4*>(g.bias + n);
+                s[0] += b.x; s[1] += b.y; s[2] += b.z; s[3] += b.w;
+            }
+            if (g.epi == EPI_BIAS_ACT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] = act_fwd(s[e], g.act);
+            }
+            if (g.epi == EPI_MUL_DACT) {
+                const float4 h = *reinterpret_cast<const float4*>(g.aux + m * g.ld_aux + n);
+                s[0] *= act_bwd_from_out(h.x, g.act); s[1] *= act_bwd_from_out(h.y, g.act);
+                s[2] *= act_bwd_from_out(h.z, g.act); s[3] *= act_bwd_from_out(h.w, g.act);
+            }
+            if (g.accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(c);
+                s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
+            }
+            *reinterpret_cast<float4*>(c) = make_float4(s[0], s[1], s[2], s[3]);
+        }
+        return;
+    }
+    const int64_t total = g.M * g.N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / g.N, n = i - m * g.N;
         float s = 0.f;
@@ -70,7 +104,18 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(SkinnyW a) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.f;
     if (w < a.W) {
-        for (int64_t k = kbeg; k < kend; ++k) {
+        int64_t k = kbeg;
+        for (; k + 4 <= kend; k += 4) {                 // four independent rows in flight per thread
+            float wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = a.wide[(k + u) * a.wide_ld + w];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < a.R) acc[r] = fmaf(wv[u], __ldg(a.narrow + (k + u) * a.narrow_ld + r), acc[r]);
+        }
+        for (; k < kend; ++k) {
             const float wv = a.wide[k * a.wide_ld + w];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -86,9 +131,13 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(SkinnyW a) {
 int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
     if (g.M <= 0 || g.N <= 0) return CDG_OK;
     if (g.K <= 8) {
-        const int64_t total = g.M * g.N;
+        const bool vec = g.N % 4 == 0 && g.ldc % 4 == 0 && (((uintptr_t)g.C) & 15) == 0 &&
+                         (!(g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) || (((uintptr_t)g.bias) & 15) == 0) &&
+                         (g.epi != EPI_MUL_DACT || (g.ld_aux % 4 == 0 && (((uintptr_t)g.aux) & 15) == 0));
+        const int64_t total = vec ? g.M * g.N / 4 : g.M * g.N;
         const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 16);
-        smallk_elem_kernel<<<blocks, 256, 0, s>>>(g);
+        if (vec) smallk_elem_kernel<true><<<blocks, 256, 0, s>>>(g);
+        else smallk_elem_kernel<false><<<blocks, 256, 0, s>>>(g);
         CDG_CHECK_LAUNCH();
         return CDG_OK;
     }
@@ -106,7 +155,7 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
         a.C = g.C; a.c_sw = wide_is_m ? g.ldc : 1; a.c_sr = wide_is_m ? 1 : g.ldc;
         a.W = wide_is_m ? g.M : g.N; a.R = (int)(wide_is_m ? g.N : g.M); a.K = g.K;
         const int wb = (int)((a.W + 127) / 128);
-        int ksplit = (int)imax64(1, imin64((kNumSMs * 8) / wb, (g.K + 255) / 256));
+        int ksplit = (int)imax64(1, imin64((kNumSMs * 16) / wb, (g.K + 63) / 64));
         a.k_chunk = (int)((g.K + ksplit - 1) / ksplit);
         ksplit = (int)((g.K + a.k_chunk - 1) / a.k_chunk);
         if (!g.accumulate) {
