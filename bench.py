@@ -101,6 +101,18 @@ def synth(batch, batch_l, seed):
     return x, xl, yl, noise
 
 
+def synth_device(batch, batch_l, seed, dev):
+    """Same distribution as synth(), generated on the device (a 131072-image batch is 6.4 GB: building it on the
+    host would cost tens of seconds and a second host copy per rank)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.rand(batch, 64, 64, 3, device=dev, generator=g) * 2 - 1
+    x.masked_fill_(torch.rand(batch, 64, 64, 3, device=dev, generator=g) < 0.9, 1.0)
+    xl = x[:batch_l].roll(1, 0).contiguous()
+    yl = torch.rand(batch_l, 5, device=dev, generator=g)
+    noise = torch.randn(batch, 4, device=dev, generator=g)
+    return x, xl, yl, noise
+
+
 def cpu_baseline(threads, target_s=12.0, batch=1024, batch_l=256):
     """The oracle port of the reference step, timed on the host cores (a reported baseline)."""
     from oracle import cdgvae_oracle as orc
@@ -197,8 +209,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(os.cpu_count() or 1)
 
-    x, xl, yl, noise = synth(B, BL, 1234 + rank)
-    xd, xld, yld, nd = (t.to(dev) for t in (x, xl, yl, noise))
+    xd, xld, yld, nd = synth_device(B, BL, 1234 + rank, dev)
     model.noise_fn = lambda n, d: nd
 
     def barrier():
@@ -236,9 +247,12 @@ def main():
     # ---- end to end: pinned host inputs, H2D every step, logs read back -------------------------
     e2e = None
     if not args.no_e2e:
-        xp, xlp, ylp = x.pin_memory(), xl.pin_memory(), yl.pin_memory()
-        h2d = xp.numel() * 4 + xlp.numel() * 4 + ylp.numel() * 4 + noise.numel() * 4
-        noise_p = noise.pin_memory()
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h
+        xp, xlp, ylp, noise_p = pinned(xd), pinned(xld), pinned(yld), pinned(nd)
+        h2d = xp.numel() * 4 + xlp.numel() * 4 + ylp.numel() * 4 + noise_p.numel() * 4
         model.noise_fn = lambda n, d: noise_p                     # CPU noise, copied H2D per step (model.py:276)
         def run(k):
             return train_CDGVAE_semi_loaders(DevicePrefetcher([(xlp, ylp)] * k, dev), DevicePrefetcher([xp] * k, dev),

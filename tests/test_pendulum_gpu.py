@@ -208,3 +208,28 @@ def test_ragged_last_batch_and_multi_batch_logs(golden):
         for k in ol:
             assert abs(logs[k][i] - ol[k]) <= 3 * RTOL * abs(ol[k]) + 1e-7, (i, k, logs[k][i], ol[k])
     assert list(logs) == ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i+1}" for i in range(4)]
+
+
+def test_device_prefetcher_matches_direct_feeding(golden):
+    """Host batches staged through the rotating device buffers give the same logs as device-resident batches,
+    also with the train loop's one-batch look-ahead (the race the three-slot ring exists for)."""
+    from cdgvae_b200.data import DevicePrefetcher
+    from cdgvae_b200.modules import train as T
+    c = golden("pendulum_small_linear")
+    data, noises = [], []
+    for i in range(7):
+        x, y, nz = orc.synth_pendulum(16, 8, 4, 300 + i, 400 + i)
+        data.append((x.pin_memory(), y.pin_memory()))
+        noises.append(nz)
+    runs = []
+    for use_prefetch in (False, True):
+        model, opt, spec, Bm, batches, cfg = build(c)
+        q = list(noises)
+        model.noise_fn = lambda n, d: q.pop(0)
+        loader = DevicePrefetcher(data, "cuda") if use_prefetch else [(x.cuda(), y.cuda()) for x, y in data]
+        logs, xhat = T.train_CDGVAE(loader, model, cfg, opt, "cuda")
+        runs.append((logs, xhat.clone(), model._arena.clone()))
+    for k in runs[0][0]:                                              # same kernels, same inputs (split-K atomics
+        for a, b in zip(runs[0][0][k], runs[1][0][k]):                # make the last bits order dependent)
+            assert abs(a - b) <= 1e-5 * abs(a) + 1e-7, k
+    assert rel(runs[0][1], runs[1][1]) < 1e-5 and rel(runs[0][2], runs[1][2]) < 1e-5
