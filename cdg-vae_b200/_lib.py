@@ -19,7 +19,8 @@ class AdamArgs(C.Structure):
     _fields_ = [("n_seg", C.c_int32), ("seg_off", C.c_int64 * MAX_SEG), ("seg_len", C.c_int64 * MAX_SEG),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
                 ("weight_decay", C.c_double), ("grad_scale", C.c_float), ("step", C.c_int32),
-                ("clamp_off", C.c_int64), ("clamp_len", C.c_int64), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float)]
+                ("clamp_off", C.c_int64), ("clamp_len", C.c_int64), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
+                ("dev_step", C.c_void_p)]
 
 
 class PendulumConfig(C.Structure):

@@ -106,12 +106,28 @@ int launch_finalize_logs(double* acc, float* logs, int d, float recon_div, float
 struct AdamK {
     int64_t off[CDG_MAX_SEG], len[CDG_MAX_SEG];
     float one_minus_b1, b2, one_minus_b2, eps, wd, gscale, step_size, bc2_sqrt;
+    const int32_t* dev_step;     // graph replay: t lives on the device
+    double lr, beta1, beta2;
     int64_t clamp_off, clamp_len;
     float clamp_lo, clamp_hi;
 };
 
+__global__ void bump_step_kernel(int32_t* t) { *t += 1; }
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, AdamK k) {
+    __shared__ float s_hyper[2];
+    if (k.dev_step) {
+        // bias corrections from the device-resident step count, in double like the host path
+        if (threadIdx.x == 0) {
+            const double t = (double)*k.dev_step;
+            s_hyper[0] = (float)(k.lr / (1.0 - pow(k.beta1, t)));
+            s_hyper[1] = (float)sqrt(1.0 - pow(k.beta2, t));
+        }
+        __syncthreads();
+        k.step_size = s_hyper[0];
+        k.bc2_sqrt = s_hyper[1];
+    }
     const int64_t off = k.off[blockIdx.y], len = k.len[blockIdx.y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = off + i;
@@ -136,7 +152,7 @@ extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, 
     using namespace cdg;
     CDG_REQUIRE(params && grads && exp_avg && exp_avg_sq && a, "cdg_adam_step: null argument");
     CDG_REQUIRE(a->n_seg >= 0 && a->n_seg <= CDG_MAX_SEG, "cdg_adam_step: n_seg out of range");
-    CDG_REQUIRE(a->step >= 1, "cdg_adam_step: step must be >= 1");
+    CDG_REQUIRE(a->step >= 1 || a->dev_step, "cdg_adam_step: step must be >= 1");
     if (a->n_seg == 0) return CDG_OK;
     AdamK k;
     int64_t maxlen = 0;
@@ -146,8 +162,10 @@ extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, 
         CDG_REQUIRE(k.off[i] >= 0 && k.len[i] >= 0, "cdg_adam_step: bad segment");
         if (k.len[i] > maxlen) maxlen = k.len[i];
     }
-    const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
-    const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
+    const double tt = a->dev_step ? 1.0 : (double)a->step;
+    const double bc1 = 1.0 - pow(a->beta1, tt);
+    const double bc2 = 1.0 - pow(a->beta2, tt);
+    k.dev_step = a->dev_step; k.lr = a->lr; k.beta1 = a->beta1; k.beta2 = a->beta2;
     k.one_minus_b1 = (float)(1.0 - a->beta1);
     k.b2 = (float)a->beta2;
     k.one_minus_b2 = (float)(1.0 - a->beta2);
@@ -158,6 +176,10 @@ extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, 
     k.bc2_sqrt = (float)sqrt(bc2);
     k.clamp_off = a->clamp_off; k.clamp_len = a->clamp_len; k.clamp_lo = a->clamp_lo; k.clamp_hi = a->clamp_hi;
     if (maxlen == 0) return CDG_OK;
+    if (a->dev_step) {
+        bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->dev_step);
+        CDG_CHECK_LAUNCH();
+    }
     const int bx = (int)imin64((maxlen + 255) / 256, kNumSMs * 8);
     adam_kernel<<<dim3(bx, a->n_seg), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, k);
     CDG_CHECK_LAUNCH();

@@ -66,6 +66,8 @@ class ArenaModule(nn.Module):
         self._destroy_plan()
         self._workspace = None
         self._logs = None
+        self.__dict__["_graphs"] = {}
+        self._dev_step = None
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
@@ -102,6 +104,7 @@ class ArenaModule(nn.Module):
         ws = self._workspace
         if ws is None or ws.numel() < nbytes:
             self._workspace = ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.arena_device)
+            self.drop_graphs()                      # captured graphs hold the old workspace address
         return ws
 
     def _log_rows(self, n_rows, width):
@@ -177,6 +180,63 @@ class ArenaModule(nn.Module):
         self._step_count = step
         self._bound_opt = opt
 
+    # -- CUDA graphs for launch-bound (small-batch) steps ---------------------------------------
+    GRAPH_MAX_ROWS = 4096      # above this the step is GPU-bound and graphs buy nothing
+
+    def graphed_step(self, key, inputs, body):
+        """Run `body(static_inputs) -> dict of output tensors` as a replayed CUDA graph.
+
+        A step at the reference's own batch sizes (128 / 256 rows) is ~70 short launches: host launch
+        latency, not the GPU, sets the pace.  The first time a `key` (shapes + hyper-parameters) is seen the
+        step runs eagerly (lazy one-time initialisation happens there), the second time it is captured, from
+        then on it is replayed: inputs are copied into the graph's static buffers, outputs are read from them.
+        """
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            cache[key] = "seen"
+            return body(inputs)
+        if ent == "seen":
+            static = {k: (None if v is None else torch.empty_like(v)) for k, v in inputs.items()}
+            for k, v in inputs.items():
+                if v is not None:
+                    static[k].copy_(v)
+            if getattr(self, "_dev_step", None) is None:
+                self._dev_step = torch.zeros(1, dtype=torch.int32, device=self.arena_device)
+            self._dev_step.fill_(self._step_count)
+            self._use_dev_step = True
+            torch.cuda.synchronize(self.arena_device)
+            graph = torch.cuda.CUDAGraph()
+            count0, tensors0 = self._step_count, [float(t) for t in self._step_tensors[:1]]
+            try:
+                with torch.cuda.graph(graph):
+                    outs = body(static)
+            finally:
+                self._use_dev_step = False
+            # capturing does not execute: undo the host-side step bookkeeping the body did
+            undo = self._step_count - count0
+            self._step_count = count0
+            if undo:
+                torch._foreach_add_(self._step_tensors, -float(undo))
+            ent = cache[key] = (graph, static, outs)
+        graph, static, outs = ent
+        for k, v in inputs.items():
+            if v is not None:
+                static[k].copy_(v, non_blocking=True)
+        if int(self._dev_step_mirror) != self._step_count:
+            self._dev_step.fill_(self._step_count)
+        graph.replay()
+        self._step_count += 1
+        self._dev_step_mirror = self._step_count
+        torch._foreach_add_(self._step_tensors, 1.0)
+        return outs
+
+    _dev_step_mirror = -1
+    _use_dev_step = False
+
+    def drop_graphs(self):
+        self.__dict__["_graphs"] = {}
+
     def adam_step(self, grad_scale=1.0, clamp=None):
         g = self._opt_group
         a = _lib.AdamArgs()
@@ -193,6 +253,7 @@ class ArenaModule(nn.Module):
         a.grad_scale = float(grad_scale)
         self._step_count += 1
         a.step = self._step_count
+        a.dev_step = _ptr(self._dev_step) if self._use_dev_step else None
         if clamp is not None:
             a.clamp_off, a.clamp_len, a.clamp_lo, a.clamp_hi = clamp
         else:

@@ -191,6 +191,7 @@ class CDGVAE(ArenaModule):
     def profile(self, enable=True):
         """Per-category device timing of the step (cudaEvents inside the library)."""
         _lib.check(_lib.lib().cdg_pendulum_profile_enable(self._get_plan(), int(enable)))
+        self.use_graphs = not enable          # events recorded between launches cannot live inside a captured graph
 
     def profile_read(self):
         out = (C.c_double * len(_lib.PROF_CATS))()

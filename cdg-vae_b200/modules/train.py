@@ -45,12 +45,38 @@ def _finish(model, config, n_steps):
     return logs
 
 
+def _hyper_key(model):
+    g = model._opt_group
+    lr = g["lr"]
+    return (float(lr.item() if torch.is_tensor(lr) else lr), tuple(g["betas"]), g["eps"], g["weight_decay"],
+            model.config.get("beta"), model.config.get("lambda"), model.gemm_mode)
+
+
 def _step(model, config, optimizer, row, x, y, noise, x_l=None, y_l=None, xhat=None):
-    model._plan_key_check = (config.get("beta"), config.get("lambda"))
-    keep = model.forward_backward(x, y, noise, row, x_l=x_l, y_l=y_l, xhat=xhat)
-    scale = model.exchange_gradients()
-    model.adam_step(grad_scale=scale)
-    return keep
+    rows = x.shape[0]
+    if rows > model.GRAPH_MAX_ROWS or _dist.world() > 1 or not getattr(model, "use_graphs", True):
+        model.forward_backward(x, y, noise, row, x_l=x_l, y_l=y_l, xhat=xhat)
+        model.adam_step(grad_scale=model.exchange_gradients())
+        return
+    # launch-bound regime: replay the whole step (forward, backward, Adam) as one CUDA graph
+    from ..engine import _f32c
+    dev = model.arena_device
+    ins = {"x": _f32c(x, dev).reshape(rows, -1), "noise": _f32c(noise, dev),
+           "y": None if y is None else _f32c(y, dev), "x_l": None if x_l is None else _f32c(x_l, dev).reshape(x_l.shape[0], -1),
+           "y_l": None if y_l is None else _f32c(y_l, dev)}
+    key = ("pend", tuple((k, None if v is None else tuple(v.shape)) for k, v in ins.items()), xhat is not None, _hyper_key(model))
+
+    def body(t):
+        out_row = torch.empty_like(row)
+        out_xhat = None if xhat is None else torch.empty_like(xhat)
+        model.forward_backward(t["x"], t["y"], t["noise"], out_row, x_l=t["x_l"], y_l=t["y_l"], xhat=out_xhat)
+        model.adam_step(grad_scale=1.0)
+        return {"row": out_row, "xhat": out_xhat}
+
+    outs = model.graphed_step(key, ins, body)
+    row.copy_(outs["row"], non_blocking=True)
+    if xhat is not None:
+        xhat.copy_(outs["xhat"], non_blocking=True)
 
 
 def _sync_config(model, config):

@@ -27,6 +27,33 @@ def _finish(model, config, n_steps):
     return logs
 
 
+def _graph_step(model, x_batch, y_batch, noise, row, ft, oil, clamp):
+    """One step; replayed as a CUDA graph when the batch is small enough to be launch-bound."""
+    import torch
+    from ...engine import _f32c
+    rows = x_batch.shape[0]
+    if rows > model.GRAPH_MAX_ROWS or _dist.world() > 1 or not getattr(model, "use_graphs", True):
+        model.forward_backward(x_batch, y_batch, noise, row, flatten_topology=ft, output_info_list=oil)
+        model.adam_step(grad_scale=model.exchange_gradients(), clamp=clamp)
+        return
+    dev = model.arena_device
+    ins = {"x": _f32c(x_batch, dev).reshape(rows, -1), "y": _f32c(y_batch, dev), "noise": _f32c(noise, dev)}
+    g = model._opt_group
+    lr = g["lr"]
+    key = ("tab", tuple(tuple(v.shape) for v in ins.values()), float(lr.item() if torch.is_tensor(lr) else lr),
+           tuple(g["betas"]), g["eps"], g["weight_decay"], model.config.get("beta"), model.config.get("lambda"),
+           None if ft is None else tuple(ft), None if oil is None else tuple(map(tuple, map(lambda c: tuple(map(tuple, c)), oil))), clamp)
+
+    def body(t):
+        out_row = torch.empty_like(row)
+        model.forward_backward(t["x"], t["y"], t["noise"], out_row, flatten_topology=ft, output_info_list=oil)
+        model.adam_step(grad_scale=1.0, clamp=clamp)
+        return {"row": out_row}
+
+    outs = model.graphed_step(key, ins, body)
+    row.copy_(outs["row"], non_blocking=True)
+
+
 def _sync_config(model, config):
     for k in ("beta", "lambda", "dataset", "sigma_range"):
         if k in config:
@@ -46,8 +73,7 @@ def train_CDGVAE(dataset, dataloader, model, config, optimizer, device):
     for (x_batch, y_batch) in iter(dataloader):
         rows = model._log_rows(n + 1, width)
         noise = model._noise(x_batch.shape[0])
-        model.forward_backward(x_batch, y_batch, noise, rows[n], flatten_topology=ft)
-        model.adam_step(grad_scale=model.exchange_gradients())
+        _graph_step(model, x_batch, y_batch, noise, rows[n], ft, None, None)
         n += 1
     return _finish(model, config, n)
 
@@ -65,8 +91,7 @@ def train_TVAE(output_info_list, dataset, dataloader, model, config, optimizer, 
     for (x_batch, y_batch) in iter(dataloader):
         rows = model._log_rows(n + 1, width)
         noise = model._noise(x_batch.shape[0])
-        model.forward_backward(x_batch, y_batch, noise, rows[n], output_info_list=oil)
         # optimizer.step() then sigma.data.clamp_(lo, hi)  (train.py:313-314)
-        model.adam_step(grad_scale=model.exchange_gradients(), clamp=(sig, D, float(lo), float(hi)))
+        _graph_step(model, x_batch, y_batch, noise, rows[n], None, oil, (sig, D, float(lo), float(hi)))
         n += 1
     return _finish(model, config, n)

@@ -62,6 +62,8 @@ typedef struct {
     int32_t step;                /* 1-based step count t of this update                      */
     int64_t clamp_off, clamp_len; /* optional clamp of params[clamp_off : +len] after update  */
     float clamp_lo, clamp_hi;
+    int32_t* dev_step;           /* optional device counter: when non-NULL the call first increments it and uses
+                                    its value as t (`step` is ignored), so a captured CUDA graph can be replayed */
 } cdg_adam_args;
 
 int cdg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

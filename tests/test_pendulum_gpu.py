@@ -233,3 +233,31 @@ def test_device_prefetcher_matches_direct_feeding(golden):
         for a, b in zip(runs[0][0][k], runs[1][0][k]):                # make the last bits order dependent)
             assert abs(a - b) <= 1e-5 * abs(a) + 1e-7, k
     assert rel(runs[0][1], runs[1][1]) < 1e-5 and rel(runs[0][2], runs[1][2]) < 1e-5
+
+
+def test_cuda_graph_replay_matches_eager(golden):
+    """Small-batch steps are captured and replayed as CUDA graphs from the third occurrence of a shape on.
+    The replayed trajectory (losses, parameters, Adam step counters) must match the eager one."""
+    from cdgvae_b200.modules import train as T
+    c = golden("pendulum_small_linear")
+    data, noises = [], []
+    for i in range(6):
+        x, y, nz = orc.synth_pendulum(16, 8, 4, 500 + i, 600 + i)
+        data.append((x.cuda(), y.cuda()))
+        noises.append(nz)
+    res = []
+    for graphs in (False, True):
+        model, opt, spec, Bm, batches, cfg = build(c)
+        model.use_graphs = graphs
+        q = list(noises)
+        model.noise_fn = lambda n, d: q.pop(0)
+        logs, xhat = T.train_CDGVAE(data, model, cfg, opt, "cuda")
+        if graphs:
+            assert any(isinstance(v, tuple) for v in model._graphs.values()), "no graph was captured"
+        res.append((logs, xhat.clone(), model._arena.clone(), [float(opt.state[p]["step"]) for p in model.parameters()]))
+    for k in res[0][0]:
+        for a, b in zip(res[0][0][k], res[1][0][k]):
+            assert abs(a - b) <= 2e-5 * abs(a) + 1e-7, (k, a, b)
+    assert rel(res[0][1], res[1][1]) < 1e-4
+    assert rel(res[0][2], res[1][2]) < 1e-4
+    assert res[0][3] == res[1][3] == [6.0] * len(res[0][3])

@@ -30,3 +30,21 @@ for B in (128, 1024):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"pendulum train_CDGVAE batch {B}: {1e3 * dt / 59:.3f} ms/step wall, {B * 59 / dt:.0f} samples/s (host batches)")
+
+from collections import namedtuple
+from cdgvae_b200.tabular.modules import model as TM, train as TT
+cfg = dict(dataset="adult", scm="linear", flow_num=1, inverse_loop=100, lr=0.01, beta=0.01, node=3, factor=[1, 1, 1], input_dim=5)
+cfg["lambda"] = 10.0
+torch.manual_seed(1)
+tm = TM.CDGVAE(orc.tabular_B("adult"), [1, 1, 3], cfg, "cpu").to("cuda")
+topt = torch.optim.Adam(tm.parameters(), lr=0.01)
+DS = namedtuple("DS", ["flatten_topology"])
+x, y, _ = orc.synth_tabular("adult", 256)
+data = [(x.cuda(), y.cuda())] * 157                # one reference epoch: 40,000 rows / 256
+TT.train_CDGVAE(DS([2, 3, 0, 1, 4]), data[:5], tm, cfg, topt, "cuda")
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+TT.train_CDGVAE(DS([2, 3, 0, 1, 4]), data, tm, cfg, topt, "cuda")
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+print(f"tabular adult train_CDGVAE batch 256: {1e3 * dt / 157:.3f} ms/step wall, {256 * 157 / dt:.0f} rows/s")
