@@ -261,3 +261,85 @@ def test_cuda_graph_replay_matches_eager(golden):
     assert rel(res[0][1], res[1][1]) < 1e-4
     assert rel(res[0][2], res[1][2]) < 1e-4
     assert res[0][3] == res[1][3] == [6.0] * len(res[0][3])
+
+
+def _generic_case(image_size, bands_or_masks, scm, flow_num, batch, semi, seed=3, node=4, factor=(1, 1, 2)):
+    """A pendulum-family configuration that is NOT one of the goldens, checked against the oracle only."""
+    from cdgvae_b200.modules.model import CDGVAE
+    cfg = dict(node=node, scm=scm, flow_num=flow_num, inverse_loop=100, factor=list(factor), image_size=image_size,
+               batch_size=batch, batch_sizeL=max(1, batch // 4), lr=1e-3, beta=0.1, seed=seed)
+    cfg["lambda"] = 5.0
+    mask = bands_or_masks if isinstance(bands_or_masks, list) else orc.pendulum_masks(image_size, bands_or_masks)
+    spec = orc.pendulum_spec(cfg, mask)
+    Bm = orc.pendulum_B(4) if node == 4 else torch.triu(torch.ones(node, node), 1) / node
+    torch.manual_seed(seed)
+    model = CDGVAE(Bm, mask, cfg, "cpu").to("cuda")
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    return model, opt, spec, Bm, cfg
+
+
+@pytest.mark.parametrize("case", ["gap_mask", "flow2", "odd_image", "batch1", "five_nodes", "linear_semi"])
+def test_edge_configurations_against_oracle(case):
+    from cdgvae_b200.modules import train as T
+    semi = case == "linear_semi"
+    if case == "gap_mask":                     # rows 2..3 belong to no decoder: xhat = tanh(0) there, unfused head
+        m = []
+        for a, b in ((0, 2), (4, 6), (6, 8)):
+            t = torch.zeros(8, 8, 3); t[a:b] = 1; m.append(t)
+        args = (8, m, "linear", 1, 16, False)
+    elif case == "flow2":
+        args = (8, (3, 6), "nonlinear", 2, 16, False)
+    elif case == "odd_image":                   # P = 108: not a multiple of 16, 128-bit paths partly off
+        args = (6, (2, 4), "linear", 1, 12, False)
+    elif case == "batch1":
+        args = (8, (3, 6), "nonlinear", 1, 1, False)
+    elif case == "five_nodes":                  # DR-like width: 5 latent nodes, factors [1, 2, 2]
+        args = (8, (3, 6), "linear", 1, 16, False)
+    else:
+        args = (8, (3, 6), "linear", 1, 16, True)
+    kw = dict(node=5, factor=(1, 2, 2)) if case == "five_nodes" else {}
+    model, opt, spec, Bm, cfg = _generic_case(*args, **kw)
+    d = cfg["node"]
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    oadam = orc.new_adam_state(oparams)
+    for s in range(2):
+        g = torch.Generator().manual_seed(900 + s)
+        B = args[4]
+        x = torch.rand(B, args[0], args[0], 3, generator=g) * 2 - 1
+        y = torch.rand(B, d + 1, generator=g)
+        nz = torch.randn(B, d, generator=g)
+        xl = torch.rand(max(1, B // 4), args[0], args[0], 3, generator=g) * 2 - 1
+        yl = torch.rand(max(1, B // 4), d + 1, generator=g)
+        if s > 0:
+            sync_oracle_from_model(model, opt, oparams, oadam)
+        model.noise_fn = lambda n, dd: nz
+        if semi:
+            T.DataLoader = lambda ds, batch_size, shuffle: ds
+            logs, xhat = T.train_CDGVAE_semi([(xl, yl)], [x], model, cfg, opt, "cuda")
+            ol, og, oo = orc.train_step(oparams, oadam, spec, A, x, None, nz, xl, yl)
+        else:
+            logs, xhat = T.train_CDGVAE([(x, y)], model, cfg, opt, "cuda")
+            ol, og, oo = orc.train_step(oparams, oadam, spec, A, x, y, nz)
+        for k, v in ol.items():
+            assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (case, s, k, logs[k][0], v)
+        assert rel(xhat, oo["xhat"]) < RTOL
+        named = dict(model.named_parameters())
+        for n, p in named.items():
+            if n.startswith("flows.") and p.numel() == 1:
+                continue
+            r = rel(p.grad, og[n])
+            assert r < RTOL or float((p.grad.cpu() - og[n]).abs().max()) < 1e-7, (case, s, n, r)
+        if cfg["scm"] == "nonlinear":
+            for i in range(d):
+                ks = [k for k in named if k.startswith(f"flows.{i}.")]
+                assert rel(torch.cat([named[k].grad.reshape(-1) for k in ks]), torch.cat([og[k].reshape(-1) for k in ks])) < RTOL
+
+
+def test_empty_loader_returns_empty_logs(golden):
+    from cdgvae_b200.modules import train as T
+    c = golden("pendulum_small_linear")
+    model, opt, spec, Bm, batches, cfg = build(c)
+    logs, xhat = T.train_CDGVAE([], model, cfg, opt, "cuda")
+    assert xhat is None and all(v == [] for v in logs.values())
+    assert list(logs) == ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i+1}" for i in range(4)]
