@@ -154,7 +154,7 @@ class CDGVAE(ArenaModule):
             c.factor[k] = cfg["factor"][k]
             c.col_lo[k], c.col_hi[k] = self._ranges[k]
             for j, idx in enumerate((0, 2, 4)):
-                c.dec[k][j] = self._lin(f"decoder.{k}.{idx}")
+                c.dec[k][j] = self._lin(self._dec_prefix(k) + f".{idx}")
         c.scm, c.flow_num = _lib.SCM[cfg["scm"]], int(cfg.get("flow_num", 1))
         c.input_dim, c.hidden = 3 * cfg["image_size"] ** 2, self.HIDDEN
         c.gemm_mode = _lib.GEMM_MODES[self.gemm_mode]
@@ -172,6 +172,9 @@ class CDGVAE(ArenaModule):
         self._plan, self._plan_key = plan, key
         return plan
 
+    def _dec_prefix(self, k):
+        return f"decoder.{k}"
+
     def adam_segments(self):
         """Skip the decoder output rows the masks zero out: their gradient is exactly 0 in the reference,
         so Adam leaves them bit-unchanged."""
@@ -180,7 +183,7 @@ class CDGVAE(ArenaModule):
         for n in self.live_param_names():
             o = self._offsets[n]
             parts = n.split(".")
-            if parts[0] == "decoder" and parts[2] == "4":
+            if parts[0] == "decoder" and len(parts) == 4 and parts[2] == "4":
                 lo, hi = self._ranges[int(parts[1])]
                 w = H if parts[3] == "weight" else 1
                 segs.append((o + lo * w, (hi - lo) * w))
@@ -314,3 +317,69 @@ class CDGVAE(ArenaModule):
         return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
                 self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]),
                 list(o["xhat_separated"].unbind(0)), o["xhat"].view(-1, s, s, 3))
+
+
+class VAE(CDGVAE):
+    """The single-decoder baseline of modules/model.py:102-189: `VAE(B, config, device)`; forward returns the
+    8-tuple (mean, logvar, epsilon, orig_latent, latent, logdet, align_latent, xhat).  It is the CDG-VAE step with one
+    decoder that reads all `node` latents and owns every output column, so it runs on the same kernels."""
+
+    def __init__(self, B, config, device):
+        ArenaModule.__init__(self)
+        self.config = config
+        self.device = device
+        P, H = 3 * config["image_size"] * config["image_size"], self.HIDDEN
+        self.mask = [torch.ones(config["image_size"], config["image_size"], 3)]
+        self._ranges = [(0, P)]
+        self.encoder = nn.Sequential(nn.Linear(P, H), nn.ELU(), nn.Linear(H, H), nn.ELU(),
+                                     nn.Linear(H, config["node"] * 2)).to(device)          # model.py:110-116
+        self.B = B.to(device)
+        self.I = torch.eye(config["node"]).to(device)
+        self._A_host = torch.inverse(torch.eye(config["node"]) - B.detach().to("cpu", torch.float32))
+        self.I_B_inv = self._A_host.to(device)
+        if config["scm"] == "linear":
+            self.flows = nn.ModuleList([InvertiblePriorLinear(device=device) for _ in range(config["node"])])
+        elif config["scm"] == "nonlinear":
+            self.flows = nn.ModuleList([PlanarFlows(1, config["flow_num"], config["inverse_loop"], device)
+                                        for _ in range(config["node"])])
+        else:
+            raise ValueError("Not supported SCM!")
+        self.decoder = nn.Sequential(nn.Linear(config["node"], H), nn.ELU(), nn.Linear(H, H), nn.ELU(), nn.Linear(H, P),
+                                     nn.Tanh()).to(device)                                   # model.py:133-140
+        self.gemm_mode = config.get("gemm_mode", "auto")
+        self.noise_fn = None
+        self._plan = None
+        self._factor = [config["node"]]
+        self._build_arena()
+
+    def _dec_prefix(self, k):
+        return "decoder"
+
+    def _get_plan(self):
+        # the C plan describes this model as one decoder over all latents
+        cfg = dict(self.config)
+        cfg["factor"] = self._factor
+        saved, self.config = self.config, cfg
+        try:
+            return super()._get_plan()
+        finally:
+            self.config = saved
+
+    def _run_forward(self, *a, **k):
+        cfg = dict(self.config)
+        cfg["factor"] = self._factor
+        saved, self.config = self.config, cfg
+        try:
+            return super()._run_forward(*a, **k)
+        finally:
+            self.config = saved
+
+    def decode(self, input):
+        raise AttributeError("the reference VAE has no decode(); use forward()")
+
+    def forward(self, input, deterministic=False, log_determinant=False):
+        s = self.config["image_size"]
+        o = self._run_forward(x=input, deterministic=deterministic,
+                              want=("mean", "logvar", "epsilon", "orig_latent", "latent", "align_latent", "xhat"))
+        return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
+                self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]), o["xhat"].view(-1, s, s, 3))

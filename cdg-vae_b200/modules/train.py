@@ -103,6 +103,11 @@ def train_CDGVAE(dataloader, model, config, optimizer, device):
     return logs, (None if xhat is None else xhat.view(-1, s, s, 3))
 
 
+def train_VAE(dataloader, model, config, optimizer, device):
+    """modules/train.py:10-69: the VAE baseline's loop has the CDG-VAE losses (recon + beta KL + lambda align)."""
+    return train_CDGVAE(dataloader, model, config, optimizer, device)
+
+
 def train_CDGVAE_semi(datasetL, datasetU, model, config, optimizer, device):
     # the reference builds both loaders on every call (train.py:222-223)
     dataloaderU = DataLoader(datasetU, batch_size=config["batch_size"], shuffle=True)

@@ -60,6 +60,7 @@ class Spec:
     weight_decay: float = 0.0
     betas: Tuple[float, float] = (0.9, 0.999)
     eps: float = 1e-8
+    single_decoder: bool = False      # the VAE baseline (modules/model.py:102-189): one decoder over all latents
 
 
 def pendulum_spec(config: dict, mask: Sequence[Tensor]) -> Spec:
@@ -72,6 +73,17 @@ def pendulum_spec(config: dict, mask: Sequence[Tensor]) -> Spec:
         input_dim=3 * config["image_size"] ** 2, enc_idx=[0, 2, 4], dec_idx=[0, 2, 4],
         act="elu", n_dec_used=len(mask), image_size=config["image_size"], mask=list(mask),
         beta=config["beta"], lam=config["lambda"], lr=config.get("lr", 1e-3),
+    )
+
+
+def vae_spec(config: dict) -> Spec:
+    """modules/model.py:102-140 (VAE.__init__): single decoder Linear(node,300)-ELU-Linear-ELU-Linear-Tanh."""
+    s = config["image_size"]
+    return Spec(
+        family="pendulum", node=config["node"], factor=[config["node"]], scm=config["scm"],
+        flow_num=config.get("flow_num", 1), input_dim=3 * s * s, enc_idx=[0, 2, 4], dec_idx=[0, 2, 4], act="elu",
+        n_dec_used=1, image_size=s, mask=[torch.ones(s, s, 3)], beta=config["beta"], lam=config["lambda"],
+        lr=config.get("lr", 1e-3), single_decoder=True,
     )
 
 
@@ -182,6 +194,9 @@ def decode(params, spec: Spec, latent: List[Tensor]) -> Tuple[List[Tensor], Tens
     """CDGVAE.decode: modules/model.py:281-288 (mask, sum, tanh);
     tabular/modules/model.py:337-342 and :439-444 (plain cat)."""
     z = torch.split(torch.cat(latent, dim=1), spec.factor, dim=-1)
+    if spec.single_decoder:                                     # VAE.forward, modules/model.py:178-180
+        o = mlp(params, "decoder", spec.dec_idx, z[0], spec.act)
+        return [o], torch.tanh(o).view(-1, spec.image_size, spec.image_size, 3)
     sep = [mlp(params, f"decoder.{k}", spec.dec_idx, z[k], spec.act) for k in range(spec.n_dec_used)]
     if spec.family == "pendulum":
         s = spec.image_size
@@ -471,7 +486,7 @@ def init_params(spec: Spec, seed: int = 1, hidden: int = 300) -> Dict[str, Tenso
                 for j in range(spec.flow_num):
                     sd[f"flows.{i}.{nm}.{j}"] = torch.randn(1, 1) * 0.1
     for k, dims in enumerate(decs + extra):
-        seq(f"decoder.{k}", dims, range(0, 2 * len(dims), 2))
+        seq("decoder" if spec.single_decoder else f"decoder.{k}", dims, range(0, 2 * len(dims), 2))
     if fam == "tvae":
         sd["sigma"] = torch.ones(spec.input_dim) * 0.1                 # model.py:407
     return sd

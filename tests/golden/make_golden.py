@@ -102,6 +102,8 @@ def run_case(name, family, config, model, spec, Bmat, batches, ref_step, steps_k
                 out = model(b["x"])
             names = ["mean", "logvar", "epsilon", "orig_latent", "latent", "logdet", "align_latent",
                      "xhat_separated", "xhat"]
+            if len(out) == 8:                       # the VAE baseline has no xhat_separated (model.py:189)
+                names.remove("xhat_separated")
             fo = dict(zip(names, out))
             entry["forward"] = summarize_dict({
                 "mean": fo["mean"], "logvar": fo["logvar"], "epsilon": fo["epsilon"],
@@ -178,6 +180,29 @@ def pendulum_case(name, scm, image_size, bands, batch, nsteps, semi=False, batch
     return case
 
 
+def vae_case(name, scm, image_size, batch, nsteps):
+    config = dict(node=4, scm=scm, flow_num=1, inverse_loop=100, image_size=image_size, batch_size=batch, lr=1e-3,
+                  beta=0.1, cuda=False, seed=1)
+    config["lambda"] = 5.0
+    Bm = orc.pendulum_B(4)
+    torch.manual_seed(config["seed"])
+    model = pm.VAE(Bm, config, "cpu")
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=config["lr"])
+    batches = []
+    for s in range(nsteps):
+        x, y, noise = orc.synth_pendulum(batch, image_size, 4, seed=1234 + s, noise_seed=4321 + s)
+        batches.append(dict(x=x, y=y, noise=noise))
+    spec = orc.vae_spec(config)
+
+    def ref_step(b):
+        logs, _ = pt.train_VAE([(b["x"], b["y"])], model, config, opt, "cpu")
+        return logs
+    case = run_case(name, "vae", config, model, spec, Bm, batches, ref_step)
+    case["semi"] = False
+    return case
+
+
 def tabular_case(dataset, batch, nsteps):
     config = dict(dataset=dataset, scm="linear", flow_num=1, inverse_loop=100, batch_size=batch, lr=0.01,
                   beta=0.01, cuda=False, seed=1)
@@ -239,6 +264,13 @@ def tvae_case(kind, batch, nsteps):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "vae":         # added after the first batch of goldens
+        cases = [vae_case("vae_small_linear", "linear", 8, 16, 4), vae_case("vae_small_nonlinear", "nonlinear", 8, 16, 4)]
+        for c in cases:
+            with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
+                json.dump(c, f)
+            print("wrote", c["name"])
+        return
     cases = [
         pendulum_case("pendulum_small_linear", "linear", 8, (3, 6), 16, 4),
         pendulum_case("pendulum_small_nonlinear", "nonlinear", 8, (3, 6), 16, 4),

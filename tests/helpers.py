@@ -46,6 +46,12 @@ def case_setup(c):
                 xl, yl, _ = orc.synth_pendulum(cfg["batch_sizeL"], cfg["image_size"], 4, 9234 + s, 1)
                 b.update(x_l=xl, y_l=yl, y=None)
             batches.append(b)
+    elif fam == "vae":
+        spec = orc.vae_spec(cfg)
+        Bm = orc.pendulum_B(4)
+        for s in range(nsteps):
+            x, y, noise = orc.synth_pendulum(cfg["batch_size"], cfg["image_size"], 4, 1234 + s, 4321 + s)
+            batches.append(dict(x=x, y=y, noise=noise))
     elif fam == "tabular":
         spec = orc.tabular_spec(cfg, c["mask"], c["flatten_topology"])
         Bm = orc.tabular_B(cfg["dataset"])
@@ -64,4 +70,4 @@ def case_setup(c):
 
 ALL_CASES = ["pendulum_small_linear", "pendulum_small_nonlinear", "pendulum_small_semi",
              "pendulum_full_linear", "pendulum_full_semi", "tabular_loan", "tabular_adult",
-             "tabular_covtype", "tvae_loan", "tvae_covtype"]
+             "tabular_covtype", "tvae_loan", "tvae_covtype", "vae_small_linear", "vae_small_nonlinear"]

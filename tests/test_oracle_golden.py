@@ -28,7 +28,7 @@ def test_oracle_matches_reference_golden(golden, name):
             assert abs(logs[k] - v) <= tol * abs(v) + 1e-12, (name, s, k, logs[k], v)
         if "forward" in e:
             f = e["forward"]
-            for k in ("mean", "logvar", "epsilon", "orig_latent", "xhat"):
+            for k in ("mean", "logvar", "epsilon", "orig_latent", "xhat"):    # (VAE: same keys, one decoder)
                 summary_check(out[k], f[k], 1e-5, k)
             summary_check(torch.cat(out["latent"], 1), f["latent"], 1e-5, "latent")
             summary_check(torch.cat(out["align_latent"], 1), f["align_latent"], 1e-5, "align_latent")

@@ -343,3 +343,46 @@ def test_empty_loader_returns_empty_logs(golden):
     logs, xhat = T.train_CDGVAE([], model, cfg, opt, "cuda")
     assert xhat is None and all(v == [] for v in logs.values())
     assert list(logs) == ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i+1}" for i in range(4)]
+
+
+@pytest.mark.parametrize("name", ["vae_small_linear", "vae_small_nonlinear"])
+def test_vae_baseline_matches_reference_and_oracle(golden, name):
+    """The single-decoder VAE baseline (modules/model.py:102-189, modules/train.py:10-69) on the same kernels."""
+    from cdgvae_b200.modules.model import VAE
+    from cdgvae_b200.modules.train import train_VAE
+    c = golden(name)
+    spec, Bm, batches, cfg = case_setup(c)
+    torch.manual_seed(cfg["seed"])
+    model = VAE(Bm, cfg, "cpu").to("cuda")
+    sd0 = model.state_dict()
+    assert list(sd0) == list(c["init"])
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    for k in oparams:
+        assert torch.equal(sd0[k].cpu(), oparams[k]), k
+    oadam = orc.new_adam_state(oparams)
+    b = batches[0]
+    model.noise_fn = lambda n, d: b["noise"]
+    out = model(b["x"].cuda())
+    assert len(out) == 8                                          # model.py:189
+    o = orc.forward(oparams, spec, A, b["x"], b["noise"])
+    assert rel(out[7], o["xhat"]) < RTOL and rel(out[0], o["mean"]) < RTOL
+    for s, (b, e) in enumerate(zip(batches, c["steps"]), 1):
+        model.noise_fn = lambda n, d, b=b: b["noise"]
+        if s > 1:
+            sync_oracle_from_model(model, opt, oparams, oadam)
+        logs, xhat = train_VAE([(b["x"], b["y"])], model, cfg, opt, "cuda")
+        ol, og, oo = orc.train_step(oparams, oadam, spec, A, b["x"], b["y"], b["noise"])
+        for k, v in e["logs"].items():
+            assert abs(logs[k][0] - ol[k]) <= RTOL * abs(ol[k]) + 1e-7, (name, s, k)
+            if s == 1:
+                assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (name, s, k)
+        assert rel(xhat, oo["xhat"]) < RTOL
+        named = dict(model.named_parameters())
+        for n, p in named.items():
+            if n.startswith("flows.") and p.numel() == 1:
+                continue
+            assert rel(p.grad, og[n]) < RTOL, (name, s, n, rel(p.grad, og[n]))
+            if "grads" in e:
+                summary_check(p.grad, e["grads"][n], RTOL, "golden grad " + n, atol_scale=1e-6)
