@@ -11,8 +11,10 @@
 // tensor-core tiles are used here.
 #include "latent.cuh"
 #include "elementwise.cuh"
+#include "tabular_args.cuh"
 
 #include <new>
+#include <stdlib.h>
 
 struct cdg_tabular_plan {
     cdg_tabular_config c;
@@ -24,18 +26,6 @@ namespace cdg {
 constexpr int TAB_MAX_IN = 64;     // widest input (TVAE D)
 constexpr int TAB_MAX_H = 32;      // widest hidden layer
 constexpr int TAB_MAX_OUT = 64;    // xhat width
-constexpr int TAB_THREADS = 128;
-
-struct TabArgs {
-    cdg_tabular_config c;
-    const float* params;
-    float* grads;
-    const float* x; const float* y; const float* noise;
-    int64_t batch;
-    float* xhat; float* latents;
-    double* acc;
-    int do_bwd, deterministic, out_total;
-};
 
 // sum over the warp, then one shared-memory atomic
 __device__ __forceinline__ void wacc(float* sg, int64_t idx, float v) {
@@ -411,7 +401,10 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
     }
     int64_t blocks = (io->batch + TAB_THREADS - 1) / TAB_THREADS;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
+    // the three fixed CDG-VAE tables have a compile-time specialised kernel (tabular_fixed.cu)
+    static const bool generic_only = getenv("CDG_TAB_GENERIC") != nullptr;
+    if (generic_only || !launch_tab_fixed(a, (unsigned)blocks, smem, s))
+        tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
     CDG_CHECK_LAUNCH();
     if (io->logs)
         CDG_TRY(launch_finalize_logs(a.acc, io->logs, p->c.node, (float)io->batch, (float)io->batch, (float)io->batch,

@@ -1,0 +1,16 @@
+#pragma once
+#include "common.cuh"
+namespace cdg {
+constexpr int TAB_THREADS = 128;
+struct TabArgs {
+    cdg_tabular_config c;
+    const float* params;
+    float* grads;
+    const float* x; const float* y; const float* noise;
+    int64_t batch;
+    float* xhat; float* latents;
+    double* acc;
+    int do_bwd, deterministic, out_total;
+};
+bool launch_tab_fixed(const TabArgs& a, unsigned blocks, size_t smem, cudaStream_t s);
+}  // namespace cdg
