@@ -13,4 +13,5 @@ struct TabArgs {
     int do_bwd, deterministic, out_total;
 };
 bool launch_tab_fixed(const TabArgs& a, unsigned blocks, size_t smem, cudaStream_t s);
+bool launch_tvae_fixed(const TabArgs& a, unsigned blocks, size_t smem, cudaStream_t s);
 }  // namespace cdg
