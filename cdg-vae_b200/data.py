@@ -80,3 +80,57 @@ class DevicePrefetcher:
                 d.record(torch.cuda.current_stream(dev))
                 done[prev_slot] = d
             prev_slot = slot
+
+
+class DeviceDataLoader:
+    """Device-resident replacement for `DataLoader(dataset, batch_size, shuffle=True)` over the reference's
+    map-style datasets (modules/datasets.py:14-65: `x_data` [, `y_data`] numpy arrays converted per item with
+    `torch.FloatTensor`).  The whole dataset is converted to fp32 and uploaded ONCE; every epoch yields the same
+    batches, in the same order, as the reference's DataLoader would under the same global RNG state:
+
+      * `iter()` draws the loader's base seed (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__),
+      * the first `next()` draws the sampler seed and a `torch.randperm(n)` from it (RandomSampler.__iter__),
+
+    so noise draws that follow (`torch.randn` in model.encode, modules/model.py:276) see an identical RNG stream.
+    Batches are gathered on the device: no per-item conversion, no collate, no host->device copy per step.
+    """
+
+    def __init__(self, *arrays, batch_size, shuffle=True, drop_last=False, device="cuda", unpack_single=True):
+        self.tensors = [torch.as_tensor(a).to(dtype=torch.float32).to(device) for a in arrays]
+        n = self.tensors[0].shape[0]
+        assert all(t.shape[0] == n for t in self.tensors)
+        self.n, self.batch_size, self.shuffle, self.drop_last = n, int(batch_size), shuffle, drop_last
+        self.unpack_single = unpack_single
+        self.device = torch.device(device)
+
+    @classmethod
+    def from_dataset(cls, dataset, batch_size, shuffle=True, drop_last=False, device="cuda"):
+        """`dataset`: a reference LabeledDataset / UnLabeledDataset / TabularDataset (has x_data and maybe y_data)."""
+        arrays = [dataset.x_data] + ([dataset.y_data] if hasattr(dataset, "y_data") else [])
+        return cls(*arrays, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last, device=device)
+
+    def __len__(self):
+        return self.n // self.batch_size if self.drop_last else (self.n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        torch.empty((), dtype=torch.int64).random_()                     # the DataLoader iterator's base seed
+        return self._batches()
+
+    def _batches(self):
+        if self.shuffle:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            g = torch.Generator()
+            g.manual_seed(seed)
+            perm = torch.randperm(self.n, generator=g).to(self.device, non_blocking=True)
+        else:
+            perm = None
+        for lo in range(0, self.n, self.batch_size):
+            hi = min(self.n, lo + self.batch_size)
+            if self.drop_last and hi - lo < self.batch_size:
+                return
+            if perm is None:
+                items = [t[lo:hi] for t in self.tensors]
+            else:
+                idx = perm[lo:hi]
+                items = [t.index_select(0, idx) for t in self.tensors]
+            yield items[0] if (len(items) == 1 and self.unpack_single) else tuple(items)

@@ -108,10 +108,24 @@ def train_VAE(dataloader, model, config, optimizer, device):
     return train_CDGVAE(dataloader, model, config, optimizer, device)
 
 
+def _resident_loader(model, dataset, batch_size):
+    """The reference builds `DataLoader(dataset, batch_size, shuffle=True)` on every call (train.py:222-223) and pays
+    per-item float64->float32 conversion + collate + a pageable H2D copy per batch.  Datasets that expose their arrays
+    (`x_data` [, `y_data`], as modules/datasets.py does) are uploaded once and served by DeviceDataLoader, which yields
+    the same batches in the same order under the same RNG state; anything else falls back to torch's DataLoader."""
+    from ..data import DeviceDataLoader
+    if not hasattr(dataset, "x_data"):
+        return DataLoader(dataset, batch_size=batch_size, shuffle=True)
+    cache = model.__dict__.setdefault("_resident", {})
+    key = (id(dataset), int(batch_size))
+    if key not in cache:
+        cache[key] = DeviceDataLoader.from_dataset(dataset, batch_size, shuffle=True, device=model.arena_device)
+    return cache[key]
+
+
 def train_CDGVAE_semi(datasetL, datasetU, model, config, optimizer, device):
-    # the reference builds both loaders on every call (train.py:222-223)
-    dataloaderU = DataLoader(datasetU, batch_size=config["batch_size"], shuffle=True)
-    dataloaderL = DataLoader(datasetL, batch_size=config["batch_sizeL"], shuffle=True)
+    dataloaderU = _resident_loader(model, datasetU, config["batch_size"])
+    dataloaderL = _resident_loader(model, datasetL, config["batch_sizeL"])
     return train_CDGVAE_semi_loaders(dataloaderL, dataloaderU, model, config, optimizer, device)
 
 

@@ -138,3 +138,49 @@ def test_tabular_same_seed_init_and_state_dict(golden, name):
         assert sum(p.numel() for p in model.parameters()) == 390
     if name in ("tabular_loan", "tabular_adult"):
         assert sum(p.numel() for p in model.parameters()) == 87
+
+
+def test_device_dataloader_reproduces_dataloader_order_and_rng_stream():
+    """DeviceDataLoader (here on CPU tensors) yields exactly the batches of torch's DataLoader(shuffle=True) over
+    the reference's map-style datasets, and leaves the global RNG in the same state (the noise draws that follow
+    in model.encode must not shift)."""
+    import numpy as np
+    from torch.utils.data import DataLoader, Dataset
+    from cdgvae_b200.data import DeviceDataLoader
+
+    class Labeled(Dataset):                       # shape of modules/datasets.py::LabeledDataset
+        def __init__(self):
+            rng = np.random.default_rng(0)
+            self.x_data = rng.standard_normal((37, 4, 4, 3))
+            self.y_data = rng.random((37, 5))
+        def __len__(self):
+            return len(self.x_data)
+        def __getitem__(self, i):
+            return torch.FloatTensor(self.x_data[i]), torch.FloatTensor(self.y_data[i])
+
+    class Unlabeled(Labeled):
+        def __getitem__(self, i):
+            return torch.FloatTensor(self.x_data[i])
+
+    for cls, bs, drop in ((Labeled, 8, False), (Labeled, 8, True), (Unlabeled, 5, False)):
+        ds = cls()
+        if cls is Unlabeled:
+            del ds.y_data
+        for epoch_seed in (1, 2):
+            torch.manual_seed(epoch_seed)
+            ref, ref_noise = [], []
+            for b in DataLoader(ds, batch_size=bs, shuffle=True, drop_last=drop):
+                ref.append(b)
+                ref_noise.append(torch.randn(3))               # interleaved draws, like model.encode
+            torch.manual_seed(epoch_seed)
+            mine, my_noise = [], []
+            for b in DeviceDataLoader.from_dataset(ds, bs, shuffle=True, drop_last=drop, device="cpu"):
+                mine.append(b)
+                my_noise.append(torch.randn(3))
+            assert len(ref) == len(mine)
+            for r, m, rn, mn in zip(ref, mine, ref_noise, my_noise):
+                if cls is Unlabeled:
+                    assert torch.equal(r, m)
+                else:
+                    assert torch.equal(r[0], m[0]) and torch.equal(r[1], m[1])
+                assert torch.equal(rn, mn)

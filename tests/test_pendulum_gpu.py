@@ -386,3 +386,52 @@ def test_vae_baseline_matches_reference_and_oracle(golden, name):
             assert rel(p.grad, og[n]) < RTOL, (name, s, n, rel(p.grad, og[n]))
             if "grads" in e:
                 summary_check(p.grad, e["grads"][n], RTOL, "golden grad " + n, atol_scale=1e-6)
+
+
+def test_semi_with_reference_style_datasets_matches_dataloader_path(golden):
+    """train_CDGVAE_semi(datasetL, datasetU, ...) with map-style datasets that expose x_data / y_data (the shape of
+    modules/datasets.py) serves batches from the device-resident loader; it must consume the RNG and order batches
+    exactly like torch's DataLoader(shuffle=True) does, so both give the same trajectory."""
+    import numpy as np
+    from torch.utils.data import Dataset
+    from cdgvae_b200.modules import train as T
+
+    class DSL(Dataset):
+        def __init__(self, n, labeled, seed):
+            rng = np.random.default_rng(seed)
+            self.x_data = rng.uniform(-1, 1, (n, 8, 8, 3))
+            if labeled:
+                self.y_data = rng.random((n, 5))
+            self.labeled = labeled
+        def __len__(self):
+            return len(self.x_data)
+        def __getitem__(self, i):
+            x = torch.FloatTensor(self.x_data[i])
+            return (x, torch.FloatTensor(self.y_data[i])) if self.labeled else x
+
+    class Opaque(Dataset):                       # same data, arrays hidden: forces the torch DataLoader path
+        def __init__(self, ds):
+            self.ds = ds
+        def __len__(self):
+            return len(self.ds)
+        def __getitem__(self, i):
+            return self.ds[i]
+
+    import torch.utils.data
+    T.DataLoader = torch.utils.data.DataLoader         # other tests substitute it with a pass-through
+    c = golden("pendulum_small_semi")
+    dl, du = DSL(12, True, 1), DSL(40, False, 2)
+    res = []
+    for wrap in (False, True):
+        model, opt, spec, Bm, batches, cfg = build(c)
+        cfg["batch_size"], cfg["batch_sizeL"] = 16, 4
+        model.use_graphs = False
+        torch.manual_seed(123)                   # shuffles and the CPU noise draws (model.py:276) share this stream
+        a, b = (Opaque(dl), Opaque(du)) if wrap else (dl, du)
+        logs, xhat = T.train_CDGVAE_semi(a, b, model, cfg, opt, "cuda")
+        res.append((logs, xhat.clone(), model._arena.clone()))
+    assert len(res[0][0]["loss"]) == 3                              # 40 unlabeled rows / 16
+    for k in res[0][0]:
+        for p, q in zip(res[0][0][k], res[1][0][k]):
+            assert abs(p - q) <= 2e-5 * abs(p) + 1e-7, (k, p, q)
+    assert rel(res[0][1], res[1][1]) < 1e-4 and rel(res[0][2], res[1][2]) < 1e-4

@@ -76,5 +76,17 @@ def run(family, name):
                       "cpu_oracle_rows_per_s": cpu_rows, "cpu_cores": os.cpu_count()}), flush=True)
 
 
+import builtins
+_out = open("gpurun_out/tabular_rows.jsonl", "w") if os.path.isdir("gpurun_out") else None
+_print = builtins.print
+
+
+def print(*a, **k):                                    # tee the JSON lines into gpurun_out/
+    _print(*a, **k)
+    if _out:
+        _out.write(" ".join(map(str, a)) + "\n")
+        _out.flush()
+
+
 for fam, nm in (("tabular", "loan"), ("tabular", "adult"), ("tabular", "covtype"), ("tvae", "loan"), ("tvae", "covtype")):
     run(fam, nm)
