@@ -27,7 +27,7 @@ class PendulumConfig(C.Structure):
     _fields_ = [("node", C.c_int32), ("n_dec", C.c_int32), ("factor", C.c_int32 * MAX_DEC),
                 ("col_lo", C.c_int32 * MAX_DEC), ("col_hi", C.c_int32 * MAX_DEC), ("scm", C.c_int32),
                 ("flow_num", C.c_int32), ("input_dim", C.c_int32), ("hidden", C.c_int32), ("gemm_mode", C.c_int32),
-                ("n_params", C.c_int64), ("enc", Linear * 3), ("dec", (Linear * 3) * MAX_DEC),
+                ("general_mask", C.c_int32), ("n_params", C.c_int64), ("enc", Linear * 3), ("dec", (Linear * 3) * MAX_DEC),
                 ("flow_off", C.c_int64 * MAX_NODE), ("I_B_inv", C.c_float * (MAX_NODE * MAX_NODE)),
                 ("beta", C.c_float), ("lambda_", C.c_float)]
 
@@ -36,7 +36,8 @@ class PendulumIO(C.Structure):
     _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("ld_y", C.c_int32),
                 ("noise", C.c_void_p), ("batch", C.c_int64), ("x_l", C.c_void_p), ("y_l", C.c_void_p),
-                ("ld_y_l", C.c_int32), ("batch_l", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p)]
+                ("ld_y_l", C.c_int32), ("batch_l", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p),
+                ("masks", C.c_void_p)]
 
 
 class PendulumFwdIO(C.Structure):
@@ -44,7 +45,7 @@ class PendulumFwdIO(C.Structure):
                 ("x", C.c_void_p), ("noise", C.c_void_p), ("latent_in", C.c_void_p), ("batch", C.c_int64),
                 ("deterministic", C.c_int32), ("mean", C.c_void_p), ("logvar", C.c_void_p), ("epsilon", C.c_void_p),
                 ("orig_latent", C.c_void_p), ("latent", C.c_void_p), ("align_latent", C.c_void_p),
-                ("xhat_separated", C.c_void_p), ("xhat", C.c_void_p)]
+                ("xhat_separated", C.c_void_p), ("xhat", C.c_void_p), ("masks", C.c_void_p)]
 
 
 class TabularConfig(C.Structure):

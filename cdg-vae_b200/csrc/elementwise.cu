@@ -80,6 +80,49 @@ int launch_recon(float* pre, const float* x, float* xhat, int64_t batch, int64_t
     return CDG_OK;
 }
 
+// ---- general masks (modules/model.py:284-287 literally): pre = sum_k out_k * mask_k ; xhat = tanh(pre) ;
+//      recon += 0.5 (xhat - x)^2 ; out_k <- d recon / d out_k = g * mask_k,  g = (xhat - x)(1 - xhat^2) / batch
+struct MaskedArgs { float* sep[CDG_MAX_DEC]; int K; };
+__global__ void __launch_bounds__(256) masked_recon_kernel(MaskedArgs m, const float* __restrict__ masks, const float* __restrict__ x,
+                                                           float* __restrict__ xhat, int64_t batch, int64_t P, float inv_batch,
+                                                           double* acc, int write_grad) {
+    __shared__ double red[32];
+    double local = 0.0;
+    const int64_t total = batch * P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = i % P;
+        float pre = 0.f;
+        for (int k = 0; k < m.K; ++k) pre += m.sep[k][i] * masks[k * P + col];
+        const float xh = tanhf(pre);
+        if (xhat) xhat[i] = xh;
+        if (x) {
+            const float df = xh - x[i];
+            local += (double)(0.5f * df * df);
+            if (write_grad) {
+                const float g = df * (1.f - xh * xh) * inv_batch;
+                for (int k = 0; k < m.K; ++k) m.sep[k][i] = g * masks[k * P + col];
+            }
+        }
+    }
+    if (acc) {
+        const double s = block_sum<double>(local, red);
+        if (threadIdx.x == 0) atomicAdd(acc + ACC_RECON, s);
+    }
+}
+
+int launch_masked_recon(float* const* sep, int K, const float* masks, const float* x, float* xhat, int64_t batch, int64_t P,
+                        double* acc, int write_grad, cudaStream_t s) {
+    MaskedArgs m;
+    m.K = K;
+    for (int k = 0; k < K; ++k) m.sep[k] = sep[k];
+    const int64_t total = batch * P;
+    if (total == 0) return CDG_OK;
+    const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 16);
+    masked_recon_kernel<<<blocks, 256, 0, s>>>(m, masks, x, xhat, batch, P, 1.f / (float)batch, acc, write_grad);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
 // ---- log row (modules/train.py:198-207) --------------------------------------------------
 __global__ void finalize_logs_kernel(double* acc, float* logs, int d, float recon_div, float kl_div, float align_div,
                                      float beta, float lambda_) {

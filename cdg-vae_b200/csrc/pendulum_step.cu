@@ -25,6 +25,7 @@ static inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
         g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, total;
+    int64_t sep[CDG_MAX_DEC];      // general masks: full-width output of every decoder
     int64_t gemm_ws_floats;
 };
 
@@ -40,6 +41,7 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL) {
     w.zal = take(Bal * d); w.g_align = take(Bal * 2 * d);
     for (int k = 0; k < c.n_dec; ++k) { w.a1[k] = take(B * H); w.a2[k] = take(B * H); }
     w.pre = take(B * P);
+    for (int k = 0; k < c.n_dec; ++k) w.sep[k] = c.general_mask ? take(B * P) : 0;
     w.ga2 = take(B * H); w.ga1 = take(B * H); w.g_z = take(B * d); w.g_ml = take(B * 2 * d);
     w.g_h2 = take(B * H); w.g_h1 = take(B * H);
     w.h1l = take(BL * H); w.h2l = take(BL * H); w.mll = take(BL * 2 * d);
@@ -168,6 +170,10 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
     return CDG_OK;
 }
 
+static inline int64_t live_lo(const cdg_pendulum_config& c, int k) { return c.general_mask ? 0 : c.col_lo[k]; }
+static inline int64_t live_n(const cdg_pendulum_config& c, int k) {
+    return c.general_mask ? c.input_dim : c.col_hi[k] - c.col_lo[k];
+}
 static bool covers_all(const cdg_pendulum_config& c);
 // can the reconstruction head be fused into every decoder's output GEMM?
 static bool recon_fusable(const Ctx& c, int64_t B, float* pre, const float* x, float* xhat, double* acc) {
@@ -178,6 +184,20 @@ static bool recon_fusable(const Ctx& c, int64_t B, float* pre, const float* x, f
         if (!gemm_tc_can(dec_out_desc(c, k, B, pre, x, xhat, acc))) return false;
     }
     return true;
+}
+
+// general masks: every decoder evaluates all P columns into its own buffer (model.py:284)
+static int decoders_fwd_general(const Ctx& c, const float* z, int64_t B, float* const* sep) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node, P = cf.input_dim;
+    for (int k = 0; k < cf.n_dec; ++k) {
+        float* a1 = c.W + c.w.a1[k];
+        float* a2 = c.W + c.w.a2[k];
+        CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
+        CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
+        CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], 0, P, sep[k], P, B, false, PROF_DEC2_FWD));
+    }
+    return CDG_OK;
 }
 
 static bool covers_all(const cdg_pendulum_config& c) {
@@ -202,9 +222,11 @@ extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_
     for (int k = 0; k < c.n_dec; ++k) {
         CDG_REQUIRE(c.factor[k] >= 1, "factor[%d] must be >= 1", k);
         s += c.factor[k];
-        CDG_REQUIRE(0 <= c.col_lo[k] && c.col_lo[k] <= c.col_hi[k] && c.col_hi[k] <= c.input_dim, "mask range %d invalid", k);
-        for (int j = 0; j < k; ++j)
-            CDG_REQUIRE(c.col_hi[j] <= c.col_lo[k] || c.col_hi[k] <= c.col_lo[j], "mask ranges %d and %d overlap", j, k);
+        if (!c.general_mask) {
+            CDG_REQUIRE(0 <= c.col_lo[k] && c.col_lo[k] <= c.col_hi[k] && c.col_hi[k] <= c.input_dim, "mask range %d invalid", k);
+            for (int j = 0; j < k; ++j)
+                CDG_REQUIRE(c.col_hi[j] <= c.col_lo[k] || c.col_hi[k] <= c.col_lo[j], "mask ranges %d and %d overlap", j, k);
+        }
         CDG_REQUIRE(c.dec[k][0].in == c.factor[k] && c.dec[k][2].out == c.input_dim, "decoder %d shape mismatch", k);
     }
     CDG_REQUIRE(s == c.node, "sum(factor) != node");               // modules/model.py:214
@@ -300,7 +322,14 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     c.mark(PROF_LATENT);
     CDG_TRY(launch_align(al, s));
 
-    if (recon_fusable(c, B, W + c.w.pre, io->x, io->xhat, acc)) {
+    float* sep[CDG_MAX_DEC] = {nullptr};
+    for (int k = 0; k < cf.n_dec; ++k) sep[k] = W + c.w.sep[k];
+    if (cf.general_mask) {
+        CDG_REQUIRE(io->masks, "general_mask: io->masks missing");
+        CDG_TRY(decoders_fwd_general(c, W + c.w.z, B, sep));
+        c.mark(PROF_RECON);
+        CDG_TRY(launch_masked_recon(sep, cf.n_dec, io->masks, io->x, io->xhat, B, Pd, acc, 1, s));
+    } else if (recon_fusable(c, B, W + c.w.pre, io->x, io->xhat, acc)) {
         CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre, io->x, io->xhat, acc));
     } else {
         CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
@@ -309,12 +338,12 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     }
 
     // ---- backward ----
-    float* g_pre = W + c.w.pre;
     float* ga2 = W + c.w.ga2;
     float* ga1 = W + c.w.ga1;
     float* g_z = W + c.w.g_z;
     for (int k = 0; k < cf.n_dec; ++k) {
-        const int64_t lo = cf.col_lo[k], n = cf.col_hi[k] - cf.col_lo[k];
+        const int64_t lo = live_lo(cf, k), n = live_n(cf, k);
+        float* g_pre = cf.general_mask ? sep[k] : W + c.w.pre;     // d loss / d (decoder k output)
         const float* a1 = W + c.w.a1[k];
         const float* a2 = W + c.w.a2[k];
         const float* zk = W + c.w.z + p->lat_off[k];
@@ -385,7 +414,14 @@ extern "C" int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd
         if (io->logvar)
             CDG_CHECK_CUDA(cudaMemcpy2DAsync(io->logvar, 4 * d, W + c.w.ml + d, 8 * d, 4 * d, B, cudaMemcpyDeviceToDevice, s));
     }
-    if (io->xhat || io->xhat_separated) {
+    if (cf.general_mask && (io->xhat || io->xhat_separated)) {
+        CDG_REQUIRE(io->masks, "general_mask: io->masks missing");
+        float* sep[CDG_MAX_DEC] = {nullptr};
+        for (int k = 0; k < cf.n_dec; ++k)
+            sep[k] = io->xhat_separated ? io->xhat_separated + (int64_t)k * B * Pd : W + c.w.sep[k];
+        CDG_TRY(decoders_fwd_general(c, z, B, sep));
+        if (io->xhat) CDG_TRY(launch_masked_recon(sep, cf.n_dec, io->masks, nullptr, io->xhat, B, Pd, nullptr, 0, s));
+    } else if (io->xhat || io->xhat_separated) {
         float* pre = io->xhat ? io->xhat : W + c.w.pre;
         if (!covers_all(cf)) CDG_CHECK_CUDA(cudaMemsetAsync(pre, 0, sizeof(float) * B * Pd, s));
         CDG_TRY(decoders_fwd(c, z, B, pre));

@@ -102,7 +102,14 @@ class CDGVAE(ArenaModule):
         assert len(config["factor"]) == len(mask)                   # model.py:215
         self.device = device
         P, H = 3 * config["image_size"] * config["image_size"], self.HIDDEN
-        self._ranges = mask_ranges(mask, P)
+        try:
+            self._ranges = mask_ranges(mask, P)        # band masks (main.py:167-179): the fast path
+            self._general_masks = None
+        except ValueError:
+            # anything else (overlapping, scattered, non-binary masks): every decoder computes all P columns and
+            # xhat = tanh(sum_k out_k * mask_k) exactly as model.py:284-287 writes it
+            self._ranges = [(0, P)] * len(mask)
+            self._general_masks = torch.stack([torch.as_tensor(m, dtype=torch.float32).reshape(-1) for m in mask])
 
         # parameter creation order = reference order (encoder, flows, decoders) for same-seed init
         self.encoder = nn.Sequential(nn.Linear(P, H), nn.ELU(), nn.Linear(H, H), nn.ELU(),
@@ -158,6 +165,7 @@ class CDGVAE(ArenaModule):
         c.scm, c.flow_num = _lib.SCM[cfg["scm"]], int(cfg.get("flow_num", 1))
         c.input_dim, c.hidden = 3 * cfg["image_size"] ** 2, self.HIDDEN
         c.gemm_mode = _lib.GEMM_MODES[self.gemm_mode]
+        c.general_mask = int(getattr(self, "_general_masks", None) is not None)
         c.n_params = self._n_params
         for j, idx in enumerate((0, 2, 4)):
             c.enc[j] = self._lin(f"encoder.{idx}")
@@ -201,6 +209,14 @@ class CDGVAE(ArenaModule):
         _lib.check(_lib.lib().cdg_pendulum_profile_read(self._get_plan(), out))
         return dict(zip(_lib.PROF_CATS, list(out)))
 
+    def _masks_dev(self):
+        m = getattr(self, "_general_masks", None)
+        if m is None:
+            return None
+        if m.device != self.arena_device:
+            self._general_masks = m = m.to(self.arena_device).contiguous()
+        return m
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.arena_device).cuda_stream)
 
@@ -234,6 +250,7 @@ class CDGVAE(ArenaModule):
         io.x, io.noise, io.batch = _ptr(x), _ptr(noise), Bn
         io.logs = _ptr(logs_row)
         io.xhat = _ptr(xhat)
+        io.masks = _ptr(self._masks_dev())
         _lib.check(_lib.lib().cdg_pendulum_forward_backward(plan, C.byref(io), self._stream()))
         return keep
 
@@ -269,6 +286,7 @@ class CDGVAE(ArenaModule):
         nbytes = _lib.lib().cdg_pendulum_workspace_bytes(plan, Bn, 0)
         ws = self._get_workspace(nbytes)
         io.workspace, io.workspace_bytes, io.batch, io.deterministic = _ptr(ws), ws.numel(), Bn, int(deterministic)
+        io.masks = _ptr(self._masks_dev())
         _lib.check(_lib.lib().cdg_pendulum_forward(plan, C.byref(io), self._stream()))
         return out
 

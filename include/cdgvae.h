@@ -83,6 +83,9 @@ typedef struct {
     int32_t input_dim;                    /* P = 3 * image_size^2                               */
     int32_t hidden;                       /* H = 300                                            */
     int32_t gemm_mode;                    /* CDG_GEMM_*                                         */
+    int32_t general_mask;                 /* 1: masks are arbitrary [K,P] weights (io->masks), every decoder computes all
+                                             P columns and xhat = tanh(sum_k out_k * mask_k) literally (model.py:284-287);
+                                             0: band masks given as col_lo/col_hi (the fast path)                        */
     int64_t n_params;                     /* arena length in floats                             */
     cdg_linear enc[3];                    /* encoder.{0,2,4}          (model.py:219-225)        */
     cdg_linear dec[CDG_MAX_DEC][3];       /* decoder.k.{0,2,4}        (model.py:243-250)        */
@@ -114,6 +117,7 @@ typedef struct {
     int64_t batch_l;
     float* logs;             /* [4 + d]: loss, recon, KL, alignment, posterior_variance1..d   */
     float* xhat;             /* optional [batch, P] reconstruction output (train.py:209), or NULL */
+    const float* masks;      /* [K, P] decoder masks on the device; required when general_mask = 1 */
 } cdg_pendulum_io;
 
 /* zero_grad + forward + losses + backward of one batch: train.py:168-202 (:235-278 when x_l != NULL).
@@ -134,6 +138,7 @@ typedef struct {
     float* mean; float* logvar; float* epsilon; float* orig_latent; float* latent; float* align_latent;
     float* xhat_separated;   /* [K, batch, P] unmasked per-decoder outputs (model.py:284)       */
     float* xhat;             /* [batch, P]                                                      */
+    const float* masks;      /* [K, P] (general_mask = 1)                                       */
 } cdg_pendulum_fwd_io;
 
 int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd_io* io, void* stream);

@@ -77,7 +77,7 @@ def test_mask_ranges_bit_exact():
     bad = torch.zeros(64, 64, 3)
     bad[::2] = 1
     with pytest.raises(ValueError):
-        mask_ranges([bad], 12288)
+        mask_ranges([bad], 12288)              # not a band: the model switches to the general-mask path
 
 
 def test_adam_segments_skip_dead_decoder_rows(golden):

@@ -435,3 +435,40 @@ def test_semi_with_reference_style_datasets_matches_dataloader_path(golden):
         for p, q in zip(res[0][0][k], res[1][0][k]):
             assert abs(p - q) <= 2e-5 * abs(p) + 1e-7, (k, p, q)
     assert rel(res[0][1], res[1][1]) < 1e-4 and rel(res[0][2], res[1][2]) < 1e-4
+
+
+def test_general_masks_against_oracle():
+    """Masks that are not row bands (interleaved rows, overlapping, non-binary weights) take the literal
+    `tanh(sum_k out_k * mask_k)` path of modules/model.py:284-287: full-width decoders, no skipped columns."""
+    from cdgvae_b200.modules import train as T
+    m0 = torch.zeros(8, 8, 3); m0[::2] = 1.0                    # interleaved rows
+    m1 = torch.zeros(8, 8, 3); m1[1::2] = 1.0; m1[0] = 0.5      # overlaps m0 on row 0 with a non-binary weight
+    m2 = torch.full((8, 8, 3), 0.25)                             # dense fractional mask
+    model, opt, spec, Bm, cfg = _generic_case(8, [m0, m1, m2], "nonlinear", 1, 16, False)
+    assert model._general_masks is not None
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    oadam = orc.new_adam_state(oparams)
+    for s in range(2):
+        g = torch.Generator().manual_seed(70 + s)
+        x = torch.rand(16, 8, 8, 3, generator=g) * 2 - 1
+        y = torch.rand(16, 5, generator=g)
+        nz = torch.randn(16, 4, generator=g)
+        if s > 0:
+            sync_oracle_from_model(model, opt, oparams, oadam)
+        model.noise_fn = lambda n, dd: nz
+        logs, xhat = T.train_CDGVAE([(x, y)], model, cfg, opt, "cuda")
+        ol, og, oo = orc.train_step(oparams, oadam, spec, A, x, y, nz)
+        for k, v in ol.items():
+            assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (s, k, logs[k][0], v)
+        assert rel(xhat, oo["xhat"]) < RTOL
+        named = dict(model.named_parameters())
+        for n, p in named.items():
+            if n.startswith("flows.") and p.numel() == 1:
+                continue
+            assert rel(p.grad, og[n]) < RTOL, (s, n, rel(p.grad, og[n]))
+    out = model(x.cuda())
+    o = orc.forward(oparams, spec, A, x, nz)
+    for k in range(3):
+        assert rel(out[7][k], o["xhat_separated"][k]) < RTOL        # unmasked per-decoder outputs (model.py:284)
+    assert rel(out[8], o["xhat"]) < RTOL
