@@ -25,7 +25,7 @@ class AdamArgs(C.Structure):
 
 class PendulumConfig(C.Structure):
     _fields_ = [("node", C.c_int32), ("n_dec", C.c_int32), ("factor", C.c_int32 * MAX_DEC),
-                ("col_lo", C.c_int32 * MAX_DEC), ("col_hi", C.c_int32 * MAX_DEC), ("scm", C.c_int32),
+                ("dec_extra", C.c_int32 * MAX_DEC), ("col_lo", C.c_int32 * MAX_DEC), ("col_hi", C.c_int32 * MAX_DEC), ("scm", C.c_int32),
                 ("flow_num", C.c_int32), ("input_dim", C.c_int32), ("hidden", C.c_int32), ("gemm_mode", C.c_int32),
                 ("general_mask", C.c_int32), ("n_params", C.c_int64), ("enc", Linear * 3), ("dec", (Linear * 3) * MAX_DEC),
                 ("flow_off", C.c_int64 * MAX_NODE), ("I_B_inv", C.c_float * (MAX_NODE * MAX_NODE)),

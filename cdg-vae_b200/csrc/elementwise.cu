@@ -123,6 +123,38 @@ int launch_masked_recon(float* const* sep, int K, const float* masks, const floa
     return CDG_OK;
 }
 
+// ---- decoder input gather / gradient scatter for the DR variant (DR/modules/model.py:284-287) ----
+// zin[b, 0:f] = z[b, off:off+f], zin[b, f] = z[b, extra]
+__global__ void gather_cols_kernel(const float* __restrict__ z, int d, float* __restrict__ zin, int f, int off, int extra, int64_t B) {
+    const int w = f + 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * w; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / w;
+        const int j = (int)(i - b * w);
+        zin[i] = z[b * d + (j < f ? off + j : extra)];
+    }
+}
+// g_z[b, off + j] += g_zin[b, j] (j < f), g_z[b, extra] += g_zin[b, f]
+__global__ void scatter_add_cols_kernel(const float* __restrict__ gzin, float* __restrict__ gz, int d, int f, int off, int extra, int64_t B) {
+    const int w = f + 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * w; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / w;
+        const int j = (int)(i - b * w);
+        gz[b * d + (j < f ? off + j : extra)] += gzin[i];      // one thread per (row, column): no write conflicts
+    }
+}
+int launch_gather_cols(const float* z, int d, float* zin, int f, int off, int extra, int64_t B, cudaStream_t s) {
+    const int blocks = (int)imin64((B * (f + 1) + 255) / 256, kNumSMs * 8);
+    gather_cols_kernel<<<blocks, 256, 0, s>>>(z, d, zin, f, off, extra, B);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+int launch_scatter_add_cols(const float* gzin, float* gz, int d, int f, int off, int extra, int64_t B, cudaStream_t s) {
+    const int blocks = (int)imin64((B * (f + 1) + 255) / 256, kNumSMs * 8);
+    scatter_add_cols_kernel<<<blocks, 256, 0, s>>>(gzin, gz, d, f, off, extra, B);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
 // ---- log row (modules/train.py:198-207) --------------------------------------------------
 __global__ void finalize_logs_kernel(double* acc, float* logs, int d, float recon_div, float kl_div, float align_div,
                                      float beta, float lambda_) {

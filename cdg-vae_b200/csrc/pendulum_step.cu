@@ -26,6 +26,7 @@ struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
         g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, total;
     int64_t sep[CDG_MAX_DEC];      // general masks: full-width output of every decoder
+    int64_t zin[CDG_MAX_DEC], gzin; // DR variant: gathered decoder inputs [B, f+1] and their gradient
     int64_t gemm_ws_floats;
 };
 
@@ -42,6 +43,8 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL) {
     for (int k = 0; k < c.n_dec; ++k) { w.a1[k] = take(B * H); w.a2[k] = take(B * H); }
     w.pre = take(B * P);
     for (int k = 0; k < c.n_dec; ++k) w.sep[k] = c.general_mask ? take(B * P) : 0;
+    for (int k = 0; k < c.n_dec; ++k) w.zin[k] = c.dec_extra[k] >= 0 ? take(B * (c.factor[k] + 1)) : 0;
+    w.gzin = take(B * (CDG_MAX_NODE + 1));
     w.ga2 = take(B * H); w.ga1 = take(B * H); w.g_z = take(B * d); w.g_ml = take(B * 2 * d);
     w.g_h2 = take(B * H); w.g_h1 = take(B * H);
     w.h1l = take(BL * H); w.h2l = take(BL * H); w.mll = take(BL * 2 * d);
@@ -129,6 +132,16 @@ static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1,
     return CDG_OK;
 }
 
+// input of decoder k: a strided view of z, or (DR variant) a gathered [B, f+1] buffer
+static int dec_input(const Ctx& c, int k, const float* z, int64_t B, const float** zin, int64_t* ld) {
+    const cdg_pendulum_config& cf = c.p->c;
+    if (cf.dec_extra[k] < 0) { *zin = z + c.p->lat_off[k]; *ld = cf.node; return CDG_OK; }
+    float* buf = c.W + c.w.zin[k];
+    CDG_TRY(launch_gather_cols(z, cf.node, buf, cf.factor[k], c.p->lat_off[k], cf.dec_extra[k], B, c.s));
+    *zin = buf; *ld = cf.factor[k] + 1;
+    return CDG_OK;
+}
+
 // last decoder Linear of decoder k restricted to its live columns, optionally with the reconstruction
 // head (tanh, 0.5*(xhat-x)^2, d/d pre) fused into the GEMM epilogue
 static GemmDesc dec_out_desc(const Ctx& c, int k, int64_t B, float* pre, const float* x, float* xhat, double* acc) {
@@ -158,7 +171,9 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
     for (int k = 0; k < cf.n_dec; ++k) {
         float* a1 = c.W + c.w.a1[k];
         float* a2 = c.W + c.w.a2[k];
-        CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
+        const float* zin; int64_t ldz;
+        CDG_TRY(dec_input(c, k, z, B, &zin, &ldz));
+        CDG_TRY(linear_fwd(c, zin, ldz, cf.dec[k][0], 0, H, a1, H, B, true));
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
         if (cf.col_hi[k] - cf.col_lo[k] > 0) {
             c.mark(PROF_DEC2_FWD);
@@ -193,7 +208,9 @@ static int decoders_fwd_general(const Ctx& c, const float* z, int64_t B, float* 
     for (int k = 0; k < cf.n_dec; ++k) {
         float* a1 = c.W + c.w.a1[k];
         float* a2 = c.W + c.w.a2[k];
-        CDG_TRY(linear_fwd(c, z + c.p->lat_off[k], d, cf.dec[k][0], 0, H, a1, H, B, true));
+        const float* zin; int64_t ldz;
+        CDG_TRY(dec_input(c, k, z, B, &zin, &ldz));
+        CDG_TRY(linear_fwd(c, zin, ldz, cf.dec[k][0], 0, H, a1, H, B, true));
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
         CDG_TRY(linear_fwd(c, a2, H, cf.dec[k][2], 0, P, sep[k], P, B, false, PROF_DEC2_FWD));
     }
@@ -227,9 +244,11 @@ extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_
             for (int j = 0; j < k; ++j)
                 CDG_REQUIRE(c.col_hi[j] <= c.col_lo[k] || c.col_hi[k] <= c.col_lo[j], "mask ranges %d and %d overlap", j, k);
         }
-        CDG_REQUIRE(c.dec[k][0].in == c.factor[k] && c.dec[k][2].out == c.input_dim, "decoder %d shape mismatch", k);
+        const int extra = c.dec_extra[k] >= 0 ? 1 : 0;
+        CDG_REQUIRE(c.dec_extra[k] < c.node, "dec_extra[%d] out of range", k);
+        CDG_REQUIRE(c.dec[k][0].in == c.factor[k] + extra && c.dec[k][2].out == c.input_dim, "decoder %d shape mismatch", k);
     }
-    CDG_REQUIRE(s == c.node, "sum(factor) != node");               // modules/model.py:214
+    CDG_REQUIRE(s <= c.node, "sum(factor) > node");                 // == node for CDGVAE (model.py:214), node-1 for DR
     CDG_REQUIRE(c.enc[0].in == c.input_dim && c.enc[2].out == 2 * c.node, "encoder shape mismatch");
     cdg_pendulum_plan* p = new (std::nothrow) cdg_pendulum_plan;
     CDG_REQUIRE(p, "out of host memory");
@@ -341,12 +360,15 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     float* ga2 = W + c.w.ga2;
     float* ga1 = W + c.w.ga1;
     float* g_z = W + c.w.g_z;
+    CDG_CHECK_CUDA(cudaMemsetAsync(g_z, 0, sizeof(float) * B * d, s));     // nodes no decoder reads get zero gradient
     for (int k = 0; k < cf.n_dec; ++k) {
         const int64_t lo = live_lo(cf, k), n = live_n(cf, k);
         float* g_pre = cf.general_mask ? sep[k] : W + c.w.pre;     // d loss / d (decoder k output)
         const float* a1 = W + c.w.a1[k];
         const float* a2 = W + c.w.a2[k];
-        const float* zk = W + c.w.z + p->lat_off[k];
+        const bool dr = cf.dec_extra[k] >= 0;
+        const float* zk = dr ? W + c.w.zin[k] : W + c.w.z + p->lat_off[k];
+        const int64_t ldzk = dr ? cf.factor[k] + 1 : d;
         if (n > 0) {
             CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B, PROF_DEC2_WGRAD));
             CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B, PROF_DEC2_DGRAD));
@@ -355,8 +377,14 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         }
         CDG_TRY(linear_wgrad(c, ga2, H, a1, H, cf.dec[k][1], 0, H, B));
         CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B));
-        CDG_TRY(linear_wgrad(c, ga1, H, zk, d, cf.dec[k][0], 0, H, B));
-        CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, g_z + p->lat_off[k], d, nullptr, 0, B));
+        CDG_TRY(linear_wgrad(c, ga1, H, zk, ldzk, cf.dec[k][0], 0, H, B));
+        if (!dr) {
+            CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, g_z + p->lat_off[k], d, nullptr, 0, B));
+        } else {
+            float* gzin = W + c.w.gzin;
+            CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, gzin, ldzk, nullptr, 0, B));
+            CDG_TRY(launch_scatter_add_cols(gzin, g_z, (int)d, cf.factor[k], p->lat_off[k], cf.dec_extra[k], B, s));
+        }
     }
     LatentArgs lb;
     fill_latent(cf, lb);

@@ -93,13 +93,18 @@ def mask_ranges(mask, n_cols):
 
 class CDGVAE(ArenaModule):
     HIDDEN = 300
+    DEC_EXTRA_INPUTS = 0          # the DR variant appends the last latent to every decoder's input
+
+    @staticmethod
+    def _check_factor(config, mask):
+        assert sum(config["factor"]) == config["node"]              # model.py:214
+        assert len(config["factor"]) == len(mask)                   # model.py:215
 
     def __init__(self, B, mask, config, device):
         super().__init__()
         self.config = config
         self.mask = mask
-        assert sum(config["factor"]) == config["node"]              # model.py:214
-        assert len(config["factor"]) == len(mask)                   # model.py:215
+        self._check_factor(config, mask)
         self.device = device
         P, H = 3 * config["image_size"] * config["image_size"], self.HIDDEN
         try:
@@ -126,7 +131,7 @@ class CDGVAE(ArenaModule):
         else:
             raise ValueError("Not supported SCM!")                   # model.py:240
         self.decoder = nn.ModuleList([
-            nn.Sequential(nn.Linear(k, H), nn.ELU(), nn.Linear(H, H), nn.ELU(), nn.Linear(H, P)).to(device)
+            nn.Sequential(nn.Linear(k + self.DEC_EXTRA_INPUTS, H), nn.ELU(), nn.Linear(H, H), nn.ELU(), nn.Linear(H, P)).to(device)
             for k in config["factor"]])
         self.gemm_mode = config.get("gemm_mode", "auto") if isinstance(config, dict) else "auto"
         self.noise_fn = None      # tests/bench inject noise; default draws like model.py:276
@@ -159,6 +164,7 @@ class CDGVAE(ArenaModule):
         c.node, c.n_dec = d, K
         for k in range(K):
             c.factor[k] = cfg["factor"][k]
+            c.dec_extra[k] = d - 1 if self.DEC_EXTRA_INPUTS else -1
             c.col_lo[k], c.col_hi[k] = self._ranges[k]
             for j, idx in enumerate((0, 2, 4)):
                 c.dec[k][j] = self._lin(self._dec_prefix(k) + f".{idx}")

@@ -76,6 +76,8 @@ typedef struct {
     int32_t node;                         /* d = config["node"]                                 */
     int32_t n_dec;                        /* K = len(config["factor"])                          */
     int32_t factor[CDG_MAX_DEC];          /* latents per decoder (model.py:283)                 */
+    int32_t dec_extra[CDG_MAX_DEC];       /* latent column appended to decoder k's input, or -1: the DR variant feeds
+                                             every decoder the last ("spurious") latent too (DR/modules/model.py:284-287) */
     int32_t col_lo[CDG_MAX_DEC];          /* live flat output columns of decoder k: the support */
     int32_t col_hi[CDG_MAX_DEC];          /*   [lo,hi) of its {0,1} mask (main.py:167-179)      */
     int32_t scm;                          /* CDG_SCM_LINEAR | CDG_SCM_PLANAR (model.py:233-240) */

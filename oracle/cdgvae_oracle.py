@@ -61,6 +61,7 @@ class Spec:
     betas: Tuple[float, float] = (0.9, 0.999)
     eps: float = 1e-8
     single_decoder: bool = False      # the VAE baseline (modules/model.py:102-189): one decoder over all latents
+    dr: bool = False                  # DR variant (DR/modules/model.py:245, :284-287): decoders also see the last latent
 
 
 def pendulum_spec(config: dict, mask: Sequence[Tensor]) -> Spec:
@@ -74,6 +75,17 @@ def pendulum_spec(config: dict, mask: Sequence[Tensor]) -> Spec:
         act="elu", n_dec_used=len(mask), image_size=config["image_size"], mask=list(mask),
         beta=config["beta"], lam=config["lambda"], lr=config.get("lr", 1e-3),
     )
+
+
+def dr_spec(config: dict, mask: Sequence[Tensor]) -> Spec:
+    """DR/modules/model.py:209-250: like CDGVAE but `sum(factor) == node - 1` and every decoder's first Linear takes
+    its factor's latents plus the last ("spurious") latent: nn.Linear(k+1, 300)."""
+    assert len(config["factor"]) == len(mask)
+    assert sum(config["factor"]) == config["node"] - 1
+    sp = pendulum_spec(dict(config, node=sum(config["factor"])), mask)
+    sp.node = config["node"]
+    sp.dr = True
+    return sp
 
 
 def vae_spec(config: dict) -> Spec:
@@ -193,7 +205,12 @@ def transform(params, spec: Spec, A: Tensor, eps: Tensor) -> Tuple[Tensor, List[
 def decode(params, spec: Spec, latent: List[Tensor]) -> Tuple[List[Tensor], Tensor]:
     """CDGVAE.decode: modules/model.py:281-288 (mask, sum, tanh);
     tabular/modules/model.py:337-342 and :439-444 (plain cat)."""
-    z = torch.split(torch.cat(latent, dim=1), spec.factor, dim=-1)
+    zc = torch.cat(latent, dim=1)
+    if spec.dr:                                                 # DR/modules/model.py:284-287
+        spurious = zc[:, [-1]]
+        z = [torch.cat([t, spurious], dim=1) for t in torch.split(zc[:, :-1], spec.factor, dim=-1)]
+    else:
+        z = torch.split(zc, spec.factor, dim=-1)
     if spec.single_decoder:                                     # VAE.forward, modules/model.py:178-180
         o = mlp(params, "decoder", spec.dec_idx, z[0], spec.act)
         return [o], torch.tanh(o).view(-1, spec.image_size, spec.image_size, 3)
@@ -462,7 +479,7 @@ def init_params(spec: Spec, seed: int = 1, hidden: int = 300) -> Dict[str, Tenso
     d, fam = spec.node, spec.family
     if fam == "pendulum":
         enc = [spec.input_dim, hidden, hidden, 2 * d]
-        decs = [[k, hidden, hidden, spec.input_dim] for k in spec.factor]
+        decs = [[k + (1 if spec.dr else 0), hidden, hidden, spec.input_dim] for k in spec.factor]
         extra = []
     elif fam == "tabular":
         if spec.dataset == "covtype":

@@ -203,6 +203,36 @@ def vae_case(name, scm, image_size, batch, nsteps):
     return case
 
 
+def dr_case(name, scm, image_size, bands, batch, nsteps):
+    drm = load("ref_dr_model", f"{REF}/DR/modules/model.py")
+    config = dict(node=5, scm=scm, flow_num=1, inverse_loop=100, factor=[1, 1, 2], image_size=image_size,
+                  batch_size=batch, lr=1e-3, beta=0.1, cuda=False, seed=1)
+    config["lambda"] = 5.0
+    Bm = torch.zeros(5, 5)
+    Bm[0, 2] = Bm[0, 3] = Bm[1, 2] = Bm[1, 3] = 1
+    indeg = Bm.sum(0); m = indeg != 0
+    Bm[:, m] = Bm[:, m] / indeg[m]                      # DR/main.py:137-147
+    mask = orc.pendulum_masks(image_size, bands)
+    torch.manual_seed(config["seed"])
+    model = drm.CDGVAE(Bm, mask, config, "cpu")
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=config["lr"])
+    batches = []
+    for s in range(nsteps):
+        x, y, noise = orc.synth_pendulum(batch, image_size, 5, seed=1234 + s, noise_seed=4321 + s)
+        batches.append(dict(x=x, y=y, noise=noise))
+    spec = orc.dr_spec(config, mask)
+
+    def ref_step(b):
+        logs, _ = pt.train_CDGVAE([(b["x"], b["y"])], model, config, opt, "cpu")
+        return logs
+    case = run_case(name, "dr", config, model, spec, Bm, batches, ref_step)
+    case["bands"] = list(bands)
+    case["semi"] = False
+    case["B"] = Bm.tolist()
+    return case
+
+
 def tabular_case(dataset, batch, nsteps):
     config = dict(dataset=dataset, scm="linear", flow_num=1, inverse_loop=100, batch_size=batch, lr=0.01,
                   beta=0.01, cuda=False, seed=1)
@@ -264,6 +294,12 @@ def tvae_case(kind, batch, nsteps):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "dr":
+        c = dr_case("dr_small_linear", "linear", 8, (3, 6), 16, 4)
+        with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
+            json.dump(c, f)
+        print("wrote", c["name"])
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "vae":         # added after the first batch of goldens
         cases = [vae_case("vae_small_linear", "linear", 8, 16, 4), vae_case("vae_small_nonlinear", "nonlinear", 8, 16, 4)]
         for c in cases:

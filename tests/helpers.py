@@ -46,6 +46,13 @@ def case_setup(c):
                 xl, yl, _ = orc.synth_pendulum(cfg["batch_sizeL"], cfg["image_size"], 4, 9234 + s, 1)
                 b.update(x_l=xl, y_l=yl, y=None)
             batches.append(b)
+    elif fam == "dr":
+        mask = orc.pendulum_masks(cfg["image_size"], tuple(c["bands"]))
+        spec = orc.dr_spec(cfg, mask)
+        Bm = torch.tensor(c["B"])
+        for s in range(nsteps):
+            x, y, noise = orc.synth_pendulum(cfg["batch_size"], cfg["image_size"], 5, 1234 + s, 4321 + s)
+            batches.append(dict(x=x, y=y, noise=noise))
     elif fam == "vae":
         spec = orc.vae_spec(cfg)
         Bm = orc.pendulum_B(4)
@@ -70,4 +77,4 @@ def case_setup(c):
 
 ALL_CASES = ["pendulum_small_linear", "pendulum_small_nonlinear", "pendulum_small_semi",
              "pendulum_full_linear", "pendulum_full_semi", "tabular_loan", "tabular_adult",
-             "tabular_covtype", "tvae_loan", "tvae_covtype", "vae_small_linear", "vae_small_nonlinear"]
+             "tabular_covtype", "tvae_loan", "tvae_covtype", "vae_small_linear", "vae_small_nonlinear", "dr_small_linear"]

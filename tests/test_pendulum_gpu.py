@@ -472,3 +472,38 @@ def test_general_masks_against_oracle():
     for k in range(3):
         assert rel(out[7][k], o["xhat_separated"][k]) < RTOL        # unmasked per-decoder outputs (model.py:284)
     assert rel(out[8], o["xhat"]) < RTOL
+
+
+def test_dr_variant_matches_reference_and_oracle(golden):
+    """DR/modules/model.py CDGVAE: node 5, factors [1,1,2], every decoder also reads the last (spurious) latent."""
+    from cdgvae_b200.DR.modules.model import CDGVAE as DRCDGVAE
+    from cdgvae_b200.DR.modules.train import train_CDGVAE
+    c = golden("dr_small_linear")
+    spec, Bm, batches, cfg = case_setup(c)
+    torch.manual_seed(cfg["seed"])
+    model = DRCDGVAE(Bm, spec.mask, cfg, "cpu").to("cuda")
+    sd0 = model.state_dict()
+    assert list(sd0) == list(c["init"]) and sd0["decoder.2.0.weight"].shape == (300, 3)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    A = orc.i_b_inv(Bm)
+    oparams = orc.init_params(spec, cfg["seed"])
+    for k in oparams:
+        assert torch.equal(sd0[k].cpu(), oparams[k]), k
+    oadam = orc.new_adam_state(oparams)
+    for s, (b, e) in enumerate(zip(batches, c["steps"]), 1):
+        model.noise_fn = lambda n, d, b=b: b["noise"]
+        if s > 1:
+            sync_oracle_from_model(model, opt, oparams, oadam)
+        logs, xhat = train_CDGVAE([(b["x"], b["y"])], model, cfg, opt, "cuda")
+        ol, og, oo = orc.train_step(oparams, oadam, spec, A, b["x"], b["y"], b["noise"])
+        for k, v in e["logs"].items():
+            assert abs(logs[k][0] - ol[k]) <= RTOL * abs(ol[k]) + 1e-7, (s, k)
+            if s == 1:
+                assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (s, k)
+        assert rel(xhat, oo["xhat"]) < RTOL
+        for n, p in model.named_parameters():
+            assert rel(p.grad, og[n]) < RTOL, (s, n, rel(p.grad, og[n]))
+            if "grads" in e:
+                summary_check(p.grad, e["grads"][n], RTOL, "golden grad " + n, atol_scale=1e-6)
+    out = model(batches[0]["x"].cuda())
+    assert len(out) == 9 and len(out[4]) == 5
