@@ -65,12 +65,59 @@ class TabularIO(C.Structure):
                 ("batch", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p), ("latents", C.c_void_p)]
 
 
+N_GEN, N_GEN_BLOCKS, N_RES = 5, 5, 8
+
+
+class Conv(C.Structure):
+    _fields_ = [("w", C.c_int64), ("b", C.c_int64), ("u", C.c_int64), ("v", C.c_int64), ("cin", C.c_int32),
+                ("cout", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32)]
+
+
+class BNorm(C.Structure):
+    _fields_ = [("weight", C.c_int64), ("bias", C.c_int64), ("running_mean", C.c_int64), ("running_var", C.c_int64),
+                ("c", C.c_int32), ("momentum", C.c_float), ("eps", C.c_float)]
+
+
+class GenBlock(C.Structure):
+    _fields_ = [("conv1", Conv), ("conv2", Conv), ("conv0", Conv), ("bn1", BNorm), ("bn2", BNorm)]
+
+
+class GeneratorDesc(C.Structure):
+    _fields_ = [("z_dim", C.c_int32), ("z_src", C.c_int32 * MAX_NODE), ("lin0", Conv), ("blk", GenBlock * N_GEN_BLOCKS),
+                ("attn", Conv * 4), ("bn", BNorm), ("to_rgb", Conv)]
+
+
+class ResBlock(C.Structure):
+    _fields_ = [("conv1", Conv), ("conv2", Conv), ("down", Conv), ("bn1", BNorm), ("bn2", BNorm), ("bn_down", BNorm),
+                ("has_down", C.c_int32)]
+
+
+class CelebaConfig(C.Structure):
+    _fields_ = [("node", C.c_int32), ("latent_dim", C.c_int32), ("scm", C.c_int32), ("flow_num", C.c_int32),
+                ("image_size", C.c_int32), ("gemm_mode", C.c_int32), ("n_params", C.c_int64), ("n_frozen", C.c_int64),
+                ("fc", Linear), ("flow_off", C.c_int64 * MAX_NODE), ("I_B_inv", C.c_float * (MAX_NODE * MAX_NODE)),
+                ("beta", C.c_float), ("lambda_", C.c_float), ("rn_conv1", Conv), ("rn_bn1", BNorm),
+                ("rn_blk", ResBlock * N_RES), ("gen", GeneratorDesc * N_GEN)]
+
+
+class CelebaIO(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("frozen", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64), ("x", C.c_void_p), ("ld_x", C.c_int32), ("y", C.c_void_p),
+                ("ld_y", C.c_int32), ("masks", C.c_void_p), ("noise1", C.c_void_p), ("noise2", C.c_void_p),
+                ("batch", C.c_int64), ("backward", C.c_int32), ("deterministic", C.c_int32),
+                ("encoder_passes", C.c_int32), ("logs", C.c_void_p), ("xhat", C.c_void_p),
+                ("xhat_separated", C.c_void_p), ("latents", C.c_void_p), ("encode_only", C.c_int32),
+                ("latent_in", C.c_void_p), ("epsilon2_in", C.c_void_p)]
+
+
 # every symbol include/cdgvae.h declares
 EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
-           "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm"]
+           "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
+           "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
+           "cdg_conv2d_dgrad"]
 
 _lib = None
 
@@ -111,6 +158,18 @@ def lib():
     L.cdg_tabular_forward.argtypes = [C.c_void_p, C.POINTER(TabularIO), C.c_int32, C.c_void_p]
     L.cdg_gemm.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                            C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_celeba_create.argtypes = [C.POINTER(CelebaConfig), C.POINTER(C.c_void_p)]
+    L.cdg_celeba_destroy.argtypes = [C.c_void_p]
+    L.cdg_celeba_destroy.restype = None
+    L.cdg_celeba_workspace_bytes.restype = C.c_int64
+    L.cdg_celeba_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.cdg_celeba_step.argtypes = [C.c_void_p, C.POINTER(CelebaIO), C.c_void_p]
+    L.cdg_conv2d_workspace_bytes.restype = C.c_int64
+    L.cdg_conv2d_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(Conv), C.c_int32]
+    L.cdg_conv2d_forward.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.POINTER(Conv), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_conv2d_dgrad.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Conv),
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L
     return L
 

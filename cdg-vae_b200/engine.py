@@ -37,8 +37,12 @@ class ArenaModule(nn.Module):
             return ".".join(name.split(".")[:2])
         return name
 
+    def _arena_named_parameters(self):
+        """Parameters that live in the (trainable) arena; the CelebA model keeps its frozen encoder elsewhere."""
+        return list(self.named_parameters())
+
     def _build_arena(self):
-        named = list(self.named_parameters())
+        named = self._arena_named_parameters()
         if not named:
             return
         device = named[0][1].device
@@ -83,7 +87,7 @@ class ArenaModule(nn.Module):
 
     def _lin(self, prefix):
         w, b = prefix + ".weight", prefix + ".bias"
-        shape = dict(self.named_parameters())[w].shape
+        shape = dict(self._arena_named_parameters())[w].shape
         return _lib.Linear(self._offsets[w], self._offsets[b], shape[1], shape[0])
 
     def _flow_offsets(self, node):
@@ -92,7 +96,7 @@ class ArenaModule(nn.Module):
 
     def _grad_views(self, live_names=None):
         """Expose gradients the way autograd would: p.grad is a view of the gradient arena."""
-        for name, p in self.named_parameters():
+        for name, p in self._arena_named_parameters():
             if live_names is not None and name not in live_names:
                 p.grad = None
                 continue
@@ -119,12 +123,12 @@ class ArenaModule(nn.Module):
     # -- optimizer -----------------------------------------------------------------------------
     def live_param_names(self):
         """Parameters that receive a gradient in the reference (all, except covtype's unused decoder)."""
-        return [n for n, _ in self.named_parameters()]
+        return [n for n, _ in self._arena_named_parameters()]
 
     def adam_segments(self):
         """(offset, length) ranges of the arena the optimizer touches."""
         segs = []
-        shapes = {n: p.numel() for n, p in self.named_parameters()}
+        shapes = {n: p.numel() for n, p in self._arena_named_parameters()}
         for n in self.live_param_names():
             segs.append((self._offsets[n], shapes[n]))
         return self._merge(segs)
@@ -146,7 +150,7 @@ class ArenaModule(nn.Module):
             return
         if not isinstance(opt, torch.optim.Adam) or isinstance(opt, torch.optim.AdamW):
             raise TypeError("the reference trains with torch.optim.Adam; got %s" % type(opt).__name__)
-        mine = {id(p): n for n, p in self.named_parameters()}
+        mine = {id(p): n for n, p in self._arena_named_parameters()}
         groups = [g for g in opt.param_groups if any(id(p) in mine for p in g["params"])]
         if not groups:
             raise ValueError("optimizer does not hold this model's parameters")
@@ -163,7 +167,7 @@ class ArenaModule(nn.Module):
         step = 0
         self._step_tensors = []
         live = set(self.live_param_names())
-        for name, p in self.named_parameters():
+        for name, p in self._arena_named_parameters():
             if name not in live:
                 continue
             st = opt.state[p]

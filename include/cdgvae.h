@@ -206,6 +206,94 @@ int cdg_tabular_forward_backward(cdg_tabular_plan* p, const cdg_tabular_io* io, 
 int cdg_tabular_forward(cdg_tabular_plan* p, const cdg_tabular_io* io, int32_t deterministic, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * CelebA CDG-VAE (celeba/module/model.py:106-218 CDGVAE; celeba/module/sagan.py:137-210 Generator;
+ * celeba/module/train.py:10-76 train_CDGVAE): frozen train-mode ResNet-18 encoder with a trainable
+ * fc, two Gaussian posteriors, 5 SAGAN generators (never optimised: only their input gradient is
+ * computed), L1 reconstruction.  Two arenas: `params` (trainable: encoder.fc, flows) and `frozen`
+ * (everything else, including the state the reference mutates on every forward: BatchNorm running
+ * statistics and the spectral-norm u / v vectors).  Activations are NHWC.
+ * ---------------------------------------------------------------------------------------- */
+#define CDG_CELEBA_GEN 5        /* decoders (model.py:146-151)          */
+#define CDG_CELEBA_BLOCKS 5     /* GenBlocks per generator at 128 px    */
+#define CDG_CELEBA_RES 8        /* BasicBlocks of ResNet-18             */
+
+/* nn.Conv2d / nn.Linear weight in torch layout (OIHW) at float offset `w` of the frozen arena; bias / spectral-norm
+ * u / v offsets are -1 when the layer has none. */
+typedef struct { int64_t w, b, u, v; int32_t cin, cout, k, stride, pad; } cdg_conv;
+/* nn.BatchNorm2d: weight, bias, running_mean, running_var offsets in the frozen arena */
+typedef struct { int64_t weight, bias, running_mean, running_var; int32_t c; float momentum, eps; } cdg_bnorm;
+typedef struct { cdg_conv conv1, conv2, conv0; cdg_bnorm bn1, bn2; } cdg_gen_block;          /* sagan.py:104-140 */
+typedef struct {
+    int32_t z_dim;
+    int32_t z_src[CDG_MAX_NODE];           /* latent column i >= 0 that input j of this decoder reads (model.py:190-194);
+                                              -(i+1) = column i of epsilon2 (model.py:195)                                 */
+    cdg_conv lin0;                         /* GenIniBlock.snlinear0: cin = z_dim, cout = 512*16 (sagan.py:91)            */
+    cdg_gen_block blk[CDG_CELEBA_BLOCKS];
+    cdg_conv attn[4];                      /* Self_Attn convolutions: sigma == 0, only their power iteration runs        */
+    cdg_bnorm bn;                          /* sagan.py:184 (momentum 1e-4) */
+    cdg_conv to_rgb;
+} cdg_generator;
+typedef struct { cdg_conv conv1, conv2, down; cdg_bnorm bn1, bn2, bn_down; int32_t has_down; } cdg_res_block;
+
+typedef struct {
+    int32_t node, latent_dim, scm, flow_num;
+    int32_t image_size;                    /* 128 */
+    int32_t gemm_mode;
+    int64_t n_params, n_frozen;
+    cdg_linear fc;                         /* encoder.fc in the TRAINABLE arena: 512 -> 2*node + 2*latent_dim (model.py:118) */
+    int64_t flow_off[CDG_MAX_NODE];        /* trainable arena */
+    float I_B_inv[CDG_MAX_NODE * CDG_MAX_NODE];
+    float beta, lambda_;
+    cdg_conv rn_conv1; cdg_bnorm rn_bn1;   /* torchvision resnet18 stem */
+    cdg_res_block rn_blk[CDG_CELEBA_RES];
+    cdg_generator gen[CDG_CELEBA_GEN];
+} cdg_celeba_config;
+
+typedef struct cdg_celeba_plan cdg_celeba_plan;
+int cdg_celeba_create(const cdg_celeba_config* cfg, cdg_celeba_plan** out);
+void cdg_celeba_destroy(cdg_celeba_plan* p);
+int64_t cdg_celeba_workspace_bytes(cdg_celeba_plan* p, int64_t batch);
+
+typedef struct {
+    const float* params;     /* trainable arena */
+    float* grads;            /* its gradient arena (written when backward != 0) */
+    float* frozen;           /* frozen arena; running statistics and u / v are updated in place */
+    void* workspace;
+    int64_t workspace_bytes;
+    const float* x;          /* [batch, S, S, ld_x]: channels 0-2 = image in [0,1] (train.py:31) */
+    int32_t ld_x;
+    const float* y;          /* [batch, ld_y]; first `node` columns used (train.py:55) */
+    int32_t ld_y;
+    const float* masks;      /* [5][batch, S, S] decoder masks (celeba/main.py:111; model.py:198) */
+    const float* noise1;     /* [batch, node]  (model.py:182) */
+    const float* noise2;     /* [batch, node]  (model.py:184) */
+    int64_t batch;
+    int32_t backward;        /* 1: losses + gradients (train.py:27-69); 0: forward only (model.py:202-218) */
+    int32_t deterministic;   /* eps = mean (model.py:178-180) */
+    int32_t encoder_passes;  /* encode() calls this evaluation stands for: each one updates the ResNet BatchNorm
+                                running statistics (2 for forward(), model.py:204 + :212) */
+    float* logs;             /* [5]: loss, recon, KL, alignment, active */
+    float* xhat;             /* optional [batch, S, S, 3] */
+    float* xhat_separated;   /* optional [5][batch, S, S, 3] generator outputs, NHWC */
+    float* latents;          /* optional [9][batch, node]: mean1, logvar1, epsilon1, orig_latent, latent, align_latent,
+                                mean2, logvar2, epsilon2 */
+    int32_t encode_only;     /* 1: stop after the latent block (model.encode / get_posterior): the generators and their
+                                BatchNorm / spectral-norm state are not touched */
+    const float* latent_in;  /* decode-only entry (model.py:188): [batch, node] latents ... */
+    const float* epsilon2_in;/* ... and [batch, latent_dim] epsilon2; when both are given the encoder is skipped */
+} cdg_celeba_io;
+
+int cdg_celeba_step(cdg_celeba_plan* p, const cdg_celeba_io* io, void* stream);
+
+/* Single layers of that path, exposed for unit tests against torch (tests/test_celeba_gpu.py):
+ * NHWC convolution  out[B,Ho,Wo,Co] = conv(x[B,H,W,Ci], w[Co,Ci,k,k]) + bias, and its input gradient. */
+int64_t cdg_conv2d_workspace_bytes(int64_t batch, int32_t h, int32_t w, const cdg_conv* cv, int32_t up);
+int cdg_conv2d_forward(int mode, const float* x, int64_t batch, int32_t h, int32_t w, const float* weight, const float* bias,
+                       const cdg_conv* cv, int32_t up, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int cdg_conv2d_dgrad(int mode, const float* gout, int64_t batch, int32_t h, int32_t w, const float* weight, const cdg_conv* cv,
+                     float* gin, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The dense contraction used by every pendulum Linear layer, exposed for tests and profiling:
  *   C[M,N] (ldc) = sum_k A(m,k) * B(n,k),  A(m,k) = A[m*sa_m + k*sa_k],  B(n,k) = B[n*sb_n + k*sb_k]
  * mode selects the SIMT fp32 kernel or the tcgen05 3xTF32 (fp32-faithful) / 1xTF32 kernels.
