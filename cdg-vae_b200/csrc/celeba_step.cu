@@ -86,6 +86,36 @@ static int conv_fwd(Cx& cx, const float* src, int64_t B, int Hs, int Ws, int C, 
         RUN(gemm_nt(cx, src, C, wf, g.Kp, out, Co, g.M, Co, g.Kp, bias));
         return CDG_OK;
     }
+    // implicit GEMM (gemm_tc.cu conv mode): stride-1 "same" convolutions over >= 32 channels read the activation itself
+    // through 4-D TMA boxes with a zero-filled halo; only the activated / upsampled input is materialised (1x, not k*k x)
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    const int Hin = Hs * up, Win = Ws * up;
+    if (cx.mode != CDG_GEMM_SIMT && k > 1 && (k & 1) && stride == 1 && pad == (k - 1) / 2 && C % 32 == 0 && ld == C && Co >= 16 &&
+        pow2(Hin) && pow2(Win) && (Win < 128 || Win % 128 == 0) && g.M * Co >= 4096) {
+        const bool materialise = bn || relu || up != 1;
+        if (materialise && g.M * C > cx.col_need) cx.col_need = g.M * C;
+        if (cx.dry) return CDG_OK;
+        const float* act = src;
+        if (materialise) {
+            CDG_REQUIRE(g.M * C <= cx.col_cap, "activation scratch too small");
+            Im2colArgs a{};
+            a.src = src; a.B = B; a.Hs = Hs; a.Ws = Ws; a.C = C; a.ld = ld;
+            a.scale = bn ? bn->scale : nullptr; a.shift = bn ? bn->shift : nullptr;
+            a.relu = relu; a.up = up; a.k = 1; a.stride = 1; a.pad = 0; a.Ho = Hin; a.Wo = Win;
+            a.col = cx.col; a.Kp = C;
+            CDG_TRY(launch_im2col(a, cx.s));
+            act = cx.col;
+        }
+        GemmDesc d{};
+        d.A = act; d.sa_m = C; d.sa_k = 1;
+        d.B = wf; d.sb_n = g.Kp; d.sb_k = 1;
+        d.C = out; d.ldc = Co; d.M = g.M; d.N = Co; d.K = g.K;
+        d.epi = bias ? EPI_BIAS : EPI_NONE; d.bias = bias;
+        d.conv_C = C; d.conv_H = Hin; d.conv_W = Win; d.conv_k = k; d.conv_B = B;
+        const int r = gemm_tc(d, cx.mode == CDG_GEMM_TC1X ? 1 : 3, nullptr, 0, cx.s);
+        if (r != CDG_ERR_UNSUPPORTED) return r;
+        CDG_REQUIRE(false, "implicit-GEMM convolution rejected a shape the planner accepted (C=%d H=%d W=%d Co=%d)", C, Hin, Win, Co);
+    }
     if (g.M * g.Kp > cx.col_need) cx.col_need = g.M * g.Kp;
     if (cx.dry) return CDG_OK;
     CDG_REQUIRE(g.M * g.Kp <= cx.col_cap, "im2col scratch too small");

@@ -128,6 +128,11 @@ struct GemmDesc {
     float* recon_xhat = nullptr;     // optional tanh output, laid out like C
     double* recon_acc = nullptr;     // += sum 0.5 (xhat - x)^2
     float inv_batch = 0.f;
+    // Implicit-GEMM convolution (tensor-core kernel only): when conv_C > 0, A is an NHWC activation [conv_B, conv_H,
+    // conv_W, conv_C] (contiguous), M = conv_B*conv_H*conv_W output pixels of a stride-1 "same" conv_k x conv_k
+    // convolution, K = conv_k^2 * conv_C in (kh, kw, c) order; the halo is zero-filled by TMA.  sa_m / sa_k are ignored.
+    int conv_C = 0, conv_H = 0, conv_W = 0, conv_k = 0;
+    int64_t conv_B = 0;
 };
 
 int gemm_simt(const GemmDesc& g, cudaStream_t s);

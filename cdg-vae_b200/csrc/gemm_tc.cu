@@ -54,6 +54,7 @@ struct Params {
     int probe;                                  // timing experiments only (results invalid): 1 = no conversion, 2 = no TMA
     int rawhi;                                  // K-major operands: leave the raw tile as `hi` (tensor core truncates)
     int64_t work_total;                         // tiles_m * tiles_n * splits
+    int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +83,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// 4-D box {channels, w, h, b} of an NHWC activation; out-of-range coordinates (the convolution halo) are zero-filled
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0),
@@ -405,11 +412,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int k0 = (kb_beg + i) * BK;
                     // the streamed operand comes from HBM: pull the tile needed PF K-blocks from now into L2
                     constexpr int PF = 2 * STAGES;
-                    if (i + PF < nkb) {
+                    if (i + PF < nkb && p.conv_cb == 0) {
                         if (!A_MN) tma_prefetch_2d(&tmA, k0 + PF * BK, m_blk * BM);
                         else tma_prefetch_2d(&tmA, m_blk * BM, k0 + PF * BK);
                     }
-                    if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
+                    if (!A_MN && p.conv_cb > 0) {
+                        // implicit GEMM: K-block -> (tap, channel block); the tile's 128 pixels are a {w, h, b} box
+                        const int kb = kb_beg + i, tap = kb / p.conv_cb, c0 = (kb - tap * p.conv_cb) * BK;
+                        const int kh = tap / p.conv_k, kw = tap - kh * p.conv_k, pad = (p.conv_k - 1) >> 1;
+                        const int64_t m0 = (int64_t)m_blk * BM;
+                        const int w0 = (int)(m0 % p.conv_W);
+                        const int64_t r = m0 / p.conv_W;
+                        tma_load_4d(smem_u32(a_hi(s)), &tmA, full, c0, w0 + kw - pad, (int)(r % p.conv_H) + kh - pad, (int)(r / p.conv_H));
+                    } else if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
                     else tma_load_2d(smem_u32(a_lo(s)), &tmA, full, m_blk * BM, k0);
                     if (!B_MN) {
 #pragma unroll
@@ -710,6 +725,38 @@ static int make_map(const float* X, int64_t rows, int64_t K, int64_t s_r, int64_
     return CDG_OK;
 }
 
+// NHWC activation [B, H, W, C] as a 4-D map {C, W, H, B}; box = BK channels x (Wt x Ht x Bt = 128 pixels in output-row order)
+static int make_conv_map(const float* X, int64_t B, int H, int W, int C, int BK, CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
+    MapKey key{X, B, (int64_t)H * 100000 + W, C, -4, BK, 128, 2};
+    {
+        std::lock_guard<std::mutex> g(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return CDG_OK; }
+    }
+    const int Wt = W < 128 ? W : 128, Ht = (128 / Wt) < H ? 128 / Wt : H, Bt = 128 / (Wt * Ht);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)Wt, (cuuint32_t)Ht, (cuuint32_t)Bt}, estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(X), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (4-D) failed (%d)", (int)r); return CDG_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *out;
+    return CDG_OK;
+}
+// spatial extents whose 128-pixel tiles are boxes: powers of two (W >= 128: multiples of 128)
+static bool conv_ok(const GemmDesc& g, int BK) {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (g.conv_C % BK != 0 || ((uintptr_t)g.A & 15) != 0 || g.conv_k < 1 || g.conv_k % 2 == 0) return false;
+    if (g.conv_W >= 128) { if (g.conv_W % 128 != 0) return false; }
+    else if (!pow2(g.conv_W) || !pow2(g.conv_H)) return false;
+    return g.M == g.conv_B * g.conv_H * g.conv_W && g.K == (int64_t)g.conv_k * g.conv_k * g.conv_C;
+}
+
 // an operand is usable when it is K-major or MN-major with TMA-legal strides and alignment
 static bool operand_ok(const float* X, int64_t s_r, int64_t s_k, int64_t rows, int64_t K, bool* mn_major) {
     if (((uintptr_t)X & 15) != 0) return false;
@@ -759,15 +806,17 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     // Tensor-core tiles need real extents: tiny N (encoder head 2d = 8) / tiny K (decoder inputs 1-2) stay on SIMT.
     if (g.K < 16 || (g.M < 32 && g.N < 32) || g.M * g.N < 4096) return CDG_ERR_UNSUPPORTED;
     // put the long output dimension on M (128-row tiles) when the other fits one N tile
-    if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON) {
+    if (g.conv_C > 0 && !conv_ok(g, BK)) return CDG_ERR_UNSUPPORTED;
+    if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON && g.conv_C == 0) {
         std::swap(g.A, g.B); std::swap(g.sa_m, g.sb_n); std::swap(g.sa_k, g.sb_k); std::swap(g.M, g.N);
         std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
         bias_on_m = 1;
     }
     if (g.N < 16) return CDG_ERR_UNSUPPORTED;
     bool a_mn, b_mn;
-    if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn) || !operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn))
-        return CDG_ERR_UNSUPPORTED;
+    if (g.conv_C > 0) a_mn = false;
+    else if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn)) return CDG_ERR_UNSUPPORTED;
+    if (!operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn)) return CDG_ERR_UNSUPPORTED;
     int BN;
     if (g.N <= 128) BN = 128;
     else if (g.N <= 160) BN = 160;
@@ -833,6 +882,7 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     p.rx = g.recon_x; p.rx_ld = g.ld_x; p.rxhat = g.recon_xhat; p.racc = g.recon_acc; p.inv_batch = g.inv_batch;
     p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per;
     p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
+    p.conv_cb = g.conv_C > 0 ? g.conv_C / BK : 0; p.conv_W = g.conv_W; p.conv_H = g.conv_H; p.conv_k = g.conv_k;
     {
         static int rawhi = -1;
         // default on: measured on B200, tcgen05 kind::tf32 ignores the 13 low mantissa bits (results with the raw
@@ -864,7 +914,8 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
 
     CUtensorMap ta, tb;
     const int b_box = pl.b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4))) : (BN <= 256 ? BN : BN / 2);
-    CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, BK, &ta));
+    if (g.conv_C > 0) CDG_TRY(make_conv_map(g.A, g.conv_B, g.conv_H, g.conv_W, g.conv_C, BK, &ta));
+    else CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, BK, &ta));
     CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
