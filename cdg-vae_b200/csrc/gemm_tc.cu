@@ -179,7 +179,8 @@ __device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
 template <int BN, int BK>
 struct Cfg {
     // (a 6-stage ring was tried for BN = 160 and changed nothing: the ring depth is not what limits the main loop)
-    static constexpr int STAGES = BK == 32 ? 2 : 4;
+    // narrow tiles (BN <= 64: the convolutions with 32 / 64 output channels) leave room for a 4-deep ring of 32-float blocks
+    static constexpr int STAGES = BK == 32 ? (BN <= 64 ? 4 : 2) : 4;
     static constexpr int ROW_BYTES = BK * 4;
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
@@ -818,7 +819,8 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     else if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn)) return CDG_ERR_UNSUPPORTED;
     if (!operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn)) return CDG_ERR_UNSUPPORTED;
     int BN;
-    if (g.N <= 128) BN = 128;
+    if (g.N <= 64 && BK == 32) BN = 64;
+    else if (g.N <= 128) BN = 128;
     else if (g.N <= 160) BN = 160;
     else if (g.N <= 256) BN = 256;
     else if (g.N <= 304) BN = (g.K <= 1024 && g.M >= 128 * 64) ? 160 : 304;   // short K: two 160-wide tiles with
@@ -869,7 +871,10 @@ static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     using namespace tc;
     Plan pl;
-    const int BK = passes == 1 ? 32 : default_bk();
+    // narrow outputs (N <= 64) run the 64-wide tile with 32-float K-blocks: the main loop of this kernel has a fixed cost per
+    // K-block (TMA -> convert -> MMA hand-offs), so halving the block count matters more than ring depth there
+    const bool narrow = g0.N <= 64 && passes != 1 && g0.K >= 32 && (g0.conv_C == 0 || g0.conv_C % 32 == 0);
+    const int BK = (passes == 1 || narrow) ? 32 : default_bk();
     const int pr = plan_gemm(g0, BK, &pl);
     if (pr != CDG_OK) return pr;
     const GemmDesc& g = pl.g;
@@ -920,12 +925,14 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
     if (passes == 1) {
-        if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 64) r = launch_layout<64, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 160) r = launch_layout<160, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 256) r = launch_layout<256, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else r = launch_layout<304, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
     } else if (BK == 32) {
-        if (BN == 128) r = launch_layout<128, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 64) r = launch_layout<64, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 160) r = launch_layout<160, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 256) r = launch_layout<256, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else r = launch_layout<304, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
