@@ -90,7 +90,7 @@ static int conv_fwd(Cx& cx, const float* src, int64_t B, int Hs, int Ws, int C, 
     // through 4-D TMA boxes with a zero-filled halo; only the activated / upsampled input is materialised (1x, not k*k x)
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
     const int Hin = Hs * up, Win = Ws * up;
-    if (cx.mode != CDG_GEMM_SIMT && k > 1 && (k & 1) && stride == 1 && pad == (k - 1) / 2 && C % 32 == 0 && ld == C && Co >= 16 &&
+    if (cx.mode != CDG_GEMM_SIMT && k > 1 && (k & 1) && stride == 1 && pad == (k - 1) / 2 && C % 32 == 0 && ld == C &&
         pow2(Hin) && pow2(Win) && (Win < 128 || Win % 128 == 0) && g.M * Co >= 4096) {
         const bool materialise = bn || relu || up != 1;
         if (materialise && g.M * C > cx.col_need) cx.col_need = g.M * C;

@@ -38,6 +38,10 @@ constexpr int BM = 128;
 // K-block = one swizzle row: 32 floats (SWIZZLE_128B, 2-stage ring) or 16 floats (SWIZZLE_64B, 4-stage ring).
 // The ring holds the same bytes either way; the finer blocks keep more TMA loads in flight per byte.
 constexpr int NUM_CONV_WARPS = 8;
+#ifndef CDG_TC_CONV_GROUPS
+#define CDG_TC_CONV_GROUPS 2
+#endif
+constexpr int CONV_GROUPS = CDG_TC_CONV_GROUPS;   // 1: all eight converter warps share every stage; 2: two groups alternate stages
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS + NUM_EPI_WARPS);
 
@@ -207,7 +211,7 @@ struct Cfg {
 // element-wise rewrite keeps the layout, so the tile is processed as a flat float4 array.
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <int PASSES>
+template <int PASSES, int NT>
 __device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int bytes, int ct, int rawhi) {
     if (PASSES == 1) return;
     float4* h = reinterpret_cast<float4*>(hi);
@@ -216,14 +220,14 @@ __device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int byt
     if (rawhi) {
         // the tensor core ignores the 13 low mantissa bits of a tf32 operand: hi = trunc(raw) is implicit
 #pragma unroll 4
-        for (int i = ct; i < n; i += 32 * NUM_CONV_WARPS) {
+        for (int i = ct; i < n; i += NT) {
             const float4 r = h[i];
             l[i] = make_float4(r.x - tf32_trunc(r.x), r.y - tf32_trunc(r.y), r.z - tf32_trunc(r.z), r.w - tf32_trunc(r.w));
         }
         return;
     }
 #pragma unroll 4
-    for (int i = ct; i < n; i += 32 * NUM_CONV_WARPS) {
+    for (int i = ct; i < n; i += NT) {
         const float4 r = h[i];
         float4 a, b;
         a.x = tf32_rna(r.x); a.y = tf32_rna(r.y); a.z = tf32_rna(r.z); a.w = tf32_rna(r.w);
@@ -237,9 +241,9 @@ __device__ __forceinline__ void convert_kmajor(uint8_t* hi, uint8_t* lo, int byt
 // two warps of a quarter split the K-block.  Source: K-major raw tile (swizzled, in `hi`) or MN-major raw box
 // ([k][128], in `lo`).
 template <int PASSES, int BK, bool MN>
-__device__ __forceinline__ void convert_a_tmem(const uint8_t* hi, const uint8_t* lo, uint32_t tmem_hi, int warp, int lane) {
+__device__ __forceinline__ void convert_a_tmem(const uint8_t* hi, const uint8_t* lo, uint32_t tmem_hi, int warp, int lane, int khalf) {
     constexpr int NV = BK / 2;                       // values per thread: 16 (BK = 32) or 8 (BK = 16)
-    const int q = warp & 3, khalf = (warp - 2) >> 2;
+    const int q = warp & 3;
     const uint32_t row = (uint32_t)(q * 32 + lane);
     const int kbeg = khalf * NV;
     float v[NV];
@@ -274,9 +278,8 @@ __device__ __forceinline__ void convert_a_tmem(const uint8_t* hi, const uint8_t*
 // Each thread owns one mn column of a chunk: read its BK values (conflict-free), wait until every
 // converter thread has read the chunk (its bytes are about to be overwritten), then write the K-major
 // rows of hi and lo.
-template <int PASSES, int ROWS, int CW, int BK>
-__device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct) {
-    constexpr int NT = 32 * NUM_CONV_WARPS;
+template <int PASSES, int ROWS, int CW, int BK, int NT>
+__device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct, int bar_id) {
     constexpr int IT = (ROWS + NT - 1) / NT;
     float v[IT][BK];
 #pragma unroll
@@ -290,7 +293,7 @@ __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct
         }
     }
     // every raw byte has been read before any of them is overwritten by the lo rows
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const int j = ct + it * NT;
@@ -376,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[STAGES + s]), NUM_CONV_WARPS);
+            mbar_init(smem_u32(&bars[STAGES + s]), NUM_CONV_WARPS / CONV_GROUPS);
             mbar_init(smem_u32(&bars[2 * STAGES + s]), 1);
         }
         for (int b = 0; b < NACC; ++b) {
@@ -487,12 +490,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp < 2 + NUM_CONV_WARPS) {
         // ================= converter =================
-        const int ct = threadIdx.x - 64;
+        // Two groups of four warps alternate ring stages: a stage's conversion is a latency chain (shared-memory read,
+        // tcgen05.st + wait, proxy fence, arrive), so two stages in flight hide most of it.  Each group covers all four
+        // TMEM lane quarters (warps 2-5 and 6-9: warp % 4 = 2,3,0,1).
+        constexpr int GT = 32 * NUM_CONV_WARPS / CONV_GROUPS;       // threads per group
+        const int grp = CONV_GROUPS == 1 ? 0 : (warp - 2) / (NUM_CONV_WARPS / CONV_GROUPS);
+        const int ct = (threadIdx.x - 64) - grp * GT;
         uint32_t it = 0;
         for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
             int m_blk, n_blk, kb_beg, nkb;
             decode(w, m_blk, n_blk, kb_beg, nkb);
             for (int i = 0; i < nkb; ++i, ++it) {
+                if (CONV_GROUPS == 2 && (int)(it & 1u) != grp) continue;
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
@@ -502,13 +511,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     continue;
                 }
                 if (C_::A_TMEM) {
-                    convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), tmem_base + C_::A_COL0 + s * 2 * BK, warp, lane);
+                    const uint32_t ta = tmem_base + C_::A_COL0 + s * 2 * BK;
+                    if (CONV_GROUPS == 2) {
+                        convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), ta, warp, lane, 0);
+                        convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), ta, warp, lane, 1);
+                    } else {
+                        convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), ta, warp, lane, (warp - 2) >> 2);
+                    }
                 } else {
-                    if (!A_MN) convert_kmajor<PASSES>(a_hi(s), a_lo(s), A_BYTES, ct, p.rawhi);
-                    else convert_mnmajor<PASSES, BM, 128, BK>(a_hi(s), a_lo(s), ct);
+                    if (!A_MN) convert_kmajor<PASSES, GT>(a_hi(s), a_lo(s), A_BYTES, ct, p.rawhi);
+                    else convert_mnmajor<PASSES, BM, 128, BK, GT>(a_hi(s), a_lo(s), ct, 1 + grp);
                 }
-                if (!B_MN) convert_kmajor<PASSES>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
-                else convert_mnmajor<PASSES, BN, C_::B_CW, BK>(b_hi(s), b_lo(s), ct);
+                if (!B_MN) convert_kmajor<PASSES, GT>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
+                else convert_mnmajor<PASSES, BN, C_::B_CW, BK, GT>(b_hi(s), b_lo(s), ct, 3 + grp);
                 tc_fence_before();                                   // tcgen05.st (A ring) ordered before the arrive
                 fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
                 __syncwarp();
@@ -813,7 +828,7 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
         std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
         bias_on_m = 1;
     }
-    if (g.N < 16) return CDG_ERR_UNSUPPORTED;
+    if (g.N < 16 && g.conv_C == 0) return CDG_ERR_UNSUPPORTED;   // (conv mode: a 3-channel toRGB still beats im2col + rowdot)
     bool a_mn, b_mn;
     if (g.conv_C > 0) a_mn = false;
     else if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn)) return CDG_ERR_UNSUPPORTED;
