@@ -30,9 +30,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     """ctypes mirrors vs the C compiler's view of include/cdgvae.h."""
     import subprocess, tempfile
-    src = '#include "cdgvae.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include "cdgvae.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(cdg_linear),sizeof(cdg_adam_args),sizeof(cdg_pendulum_config),sizeof(cdg_pendulum_io),' \
-          'sizeof(cdg_pendulum_fwd_io),sizeof(cdg_tabular_config),sizeof(cdg_tabular_io));return 0;}'
+          'sizeof(cdg_pendulum_fwd_io),sizeof(cdg_tabular_config),sizeof(cdg_tabular_io),sizeof(cdg_conv),sizeof(cdg_bnorm),' \
+          'sizeof(cdg_gen_block),sizeof(cdg_generator),sizeof(cdg_res_block),sizeof(cdg_celeba_config),sizeof(cdg_celeba_io));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
         open(c, "w").write(src)
@@ -40,7 +41,8 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     mine = [ctypes.sizeof(t) for t in (_lib.Linear, _lib.AdamArgs, _lib.PendulumConfig, _lib.PendulumIO,
-                                       _lib.PendulumFwdIO, _lib.TabularConfig, _lib.TabularIO)]
+                                       _lib.PendulumFwdIO, _lib.TabularConfig, _lib.TabularIO, _lib.Conv, _lib.BNorm, _lib.GenBlock,
+                                       _lib.GeneratorDesc, _lib.ResBlock, _lib.CelebaConfig, _lib.CelebaIO)]
     assert sizes == mine
 
 
@@ -184,3 +186,30 @@ def test_device_dataloader_reproduces_dataloader_order_and_rng_stream():
                 else:
                     assert torch.equal(r[0], m[0]) and torch.equal(r[1], m[1])
                 assert torch.equal(rn, mn)
+
+
+def test_celeba_host_model_matches_reference_layout(golden):
+    """celeba/module/model.py drop-in on the host: same-seed tensors, state_dict keys (generators unregistered), trainable
+    set, arena bookkeeping, and no CPU fallback."""
+    from cdgvae_b200.celeba.module.model import CDGVAE as CelebaCDGVAE
+    from oracle import celeba_oracle as corc
+    c = golden("celeba_linear")
+    cfg = dict(c["config"], pretrained=False)
+    x, y, n1, n2 = corc.synth_celeba(cfg["batch_size"], 1234, 4321)
+    masks = torch.split(x[..., 3:], 1, dim=-1)
+    torch.manual_seed(cfg["seed"])
+    model = CelebaCDGVAE(torch.tensor(c["B"]), masks, cfg, "cpu")
+    sd = model.state_dict()
+    assert not any(k.startswith("decoder") for k in sd) and len(sd) == 128       # SURVEY §A.3: plain list, 128 registered tensors
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == c["trainable"]
+    for k, g in c["init"].items():
+        t = sd[k] if k in sd else dict(model.decoder[int(k.split(".")[1])].state_dict())[k.split(".", 2)[2]]
+        exact_check(t, g, k)
+    assert model._n_params >= 12324 and model._frozen.numel() > 50_000_000
+    w = model.decoder[0].block1.conv_1.weight_orig
+    assert w.data_ptr() == model._frozen[model._foff["decoder.0.block1.conv_1.weight_orig"]:].data_ptr()   # views of the arena
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.bind_optimizer(opt)
+    assert model.adam_segments()[0][0] == 0
+    with pytest.raises(RuntimeError):
+        model(x)                                         # no CPU path
