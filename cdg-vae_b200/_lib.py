@@ -6,7 +6,7 @@ from . import build as _build
 
 MAX_NODE, MAX_DEC, MAX_FLOW, MAX_LAYERS, MAX_SPANS, MAX_SEG = 8, 8, 2, 4, 64, 32
 SCM = {"linear": 0, "nonlinear": 1}
-GEMM_MODES = {"auto": 0, "simt": 1, "tc3x": 2, "tc1x": 3}
+GEMM_MODES = {"auto": 0, "simt": 1, "tc3x": 2, "tc1x": 3, "bf3x": 4}
 TAB_KIND = {"loan": 0, "adult": 1, "covtype": 2, "tvae": 3}
 PROF_CATS = ["enc0_fwd", "dec2_fwd", "dec2_dgrad", "dec2_wgrad", "enc0_wgrad", "gemm_other", "latent", "recon", "misc"]
 

@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <map>
@@ -110,6 +111,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 // A operand from tensor memory (128 lanes = rows, one column per K element), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -165,6 +174,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -180,15 +194,19 @@ __device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
     return r * 64u + ((chunk ^ ((r >> 1) & 3u)) << 4);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int PASSES = 3>
 struct Cfg {
+    // PASSES == 2 is the bf16x3 arithmetic (see the BF3X notes at the converter): the raw fp32 tile is converted IN PLACE
+    // into a hi and a lo bf16 tile (a 128-byte fp32 row becomes two 64-byte bf16 rows), so a stage holds one copy of
+    // each operand and the ring is 4 deep at every tile width.
+    static constexpr bool BF3X = PASSES == 2;
     // (a 6-stage ring was tried for BN = 160 and changed nothing: the ring depth is not what limits the main loop)
     // narrow tiles (BN <= 64: the convolutions with 32 / 64 output channels) leave room for a 4-deep ring of 32-float blocks
-    static constexpr int STAGES = BK == 32 ? (BN <= 64 ? 4 : 2) : 4;
+    static constexpr int STAGES = BF3X ? 4 : (BK == 32 ? (BN <= 64 ? 4 : 2) : 4);
     static constexpr int ROW_BYTES = BK * 4;
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // hi + lo for both operands
+    static constexpr int STAGE_BYTES = BF3X ? (A_BYTES + B_BYTES) : 2 * (A_BYTES + B_BYTES);     // hi + lo for both operands
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int B_ROWS_PER_BOX = BN <= 256 ? BN : BN / 2;  // K-major TMA box rows (<= 256)
     static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4));   // MN-major chunk width (<= 128)
@@ -199,11 +217,12 @@ struct Cfg {
     // BK columns each per stage): the MMA then reads A from tensor memory, which removes A from the shared
     // memory data path -- the path ncu shows saturated (LSU + tensor wavefronts at 92 % of peak).
     static constexpr int A_COL0 = (NACC * BN + 31) / 32 * 32;
-    static constexpr bool A_TMEM = (A_COL0 + STAGES * 2 * BK <= 512);
-    static constexpr int TMEM_USED = (NACC * BN + 31) / 32 * 32 + ((((NACC * BN + 31) / 32 * 32) + STAGES * 2 * BK <= 512) ? STAGES * 2 * BK : 0);
+    static constexpr bool A_TMEM = !BF3X && (A_COL0 + STAGES * 2 * BK <= 512);
+    static constexpr int TMEM_USED = (NACC * BN + 31) / 32 * 32 + (A_TMEM ? STAGES * 2 * BK : 0);
     static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
+    static_assert(!BF3X || BK == 32, "bf16x3 tiles are built from 32-float K-blocks");
 };
 
 // ---- converter --------------------------------------------------------------------------------
@@ -315,6 +334,93 @@ __device__ __forceinline__ void convert_mnmajor(uint8_t* hi, uint8_t* lo, int ct
     }
 }
 
+// ---- bf16x3 (PASSES == 2) -------------------------------------------------------------------------
+// a = hi + lo with hi = bf16(a), lo = bf16(a - hi): 16 mantissa bits per operand.  Every K-block issues
+//   D += A_lo*B_hi;  D += A_hi*B_lo;  D += A_hi*B_hi        (tcgen05.mma.kind::f16 on bf16, fp32 accumulate in TMEM)
+// i.e. 3 bf16 MMAs (= 1.5 TF32 MMAs) per product instead of 3 TF32 MMAs, and half the operand bytes through the
+// shared-memory pipe.  Dropped term A_lo*B_lo ~ 2^-18; representation error 2^-17 per operand: ~1e-5 relative per GEMM.
+// Tiles: raw fp32 rows of 128 B (SWIZZLE_128B) become, in place, a hi tile (rows of 64 B, SWIZZLE_64B) in the first half
+// of the buffer and a lo tile in the second half.  All reads of a tile complete (named barrier) before any write.
+__device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);   // lower k in the low half
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// K-major raw tile [ROWS][32 floats]: unit u = (row, 8-float group g) -> one 16-byte bf16 chunk of hi and of lo
+template <int ROWS, int NT>
+__device__ __forceinline__ void bf3x_kmajor(uint8_t* buf, int ct, int bar_id) {
+    constexpr int UNITS = ROWS * 4;
+    constexpr int IT = (UNITS + NT - 1) / NT;
+    float v[IT][8];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int u = ct + it * NT;
+        if (u < UNITS) {
+            const uint32_t r = (uint32_t)(u >> 2), g = (uint32_t)(u & 3);
+            const float4 a = *reinterpret_cast<const float4*>(buf + sw_chunk<32>(r, 2 * g));
+            const float4 b = *reinterpret_cast<const float4*>(buf + sw_chunk<32>(r, 2 * g + 1));
+            v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+            v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
+    uint8_t* lo_tile = buf + ROWS * 64;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int u = ct + it * NT;
+        if (u < UNITS) {
+            const uint32_t r = (uint32_t)(u >> 2), g = (uint32_t)(u & 3);
+            uint4 hi, lo;
+            bf16_split8(v[it], hi, lo);
+            const uint32_t off = sw_chunk<16>(r, g);
+            *reinterpret_cast<uint4*>(buf + off) = hi;
+            *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+        }
+    }
+}
+
+// MN-major raw boxes [32 k-rows][CW mn] (chunk c at byte c*CW*128): thread j owns mn column j, i.e. K-major row j
+template <int ROWS, int CW, int NT>
+__device__ __forceinline__ void bf3x_mnmajor(uint8_t* buf, int ct, int bar_id) {
+    constexpr int IT = (ROWS + NT - 1) / NT;
+    float v[IT][32];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int j = ct + it * NT;
+        if (j < ROWS) {
+            const int c = j / CW, col = j - c * CW;
+            const float* raw = reinterpret_cast<const float*>(buf + (size_t)c * CW * 128);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[it][k] = raw[k * CW + col];
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
+    uint8_t* lo_tile = buf + ROWS * 64;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int j = ct + it * NT;
+        if (j < ROWS) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 hi, lo;
+                bf16_split8(&v[it][8 * g], hi, lo);
+                const uint32_t off = sw_chunk<16>((uint32_t)j, (uint32_t)g);
+                *reinterpret_cast<uint4*>(buf + off) = hi;
+                *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+            }
+        }
+    }
+}
+
 // Branch-free tanh for the fused reconstruction head: tanh(x) = 1 - 2 / (1 + e^{2x}).  Absolute error <= ~3e-7
 // (ex2.approx + rcp.approx), i.e. well inside the 1e-4 parity budget of xhat in [-1, 1]; tanhf()'s branchy
 // polynomial/exp split serialises the single epilogue warp per scheduler (measured: 66k cycles per 128x256 tile).
@@ -346,7 +452,8 @@ __device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t 
 template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-    using C_ = Cfg<BN, BK>;
+    using C_ = Cfg<BN, BK, PASSES>;
+    constexpr bool BF3X = C_::BF3X;
     constexpr int NACC = C_::NACC;
     constexpr int STAGES = C_::STAGES;
     constexpr int A_BYTES = C_::A_BYTES;
@@ -362,10 +469,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     auto stage_ptr = [&](int s) { return smem + (size_t)s * C_::STAGE_BYTES; };
+    // tf32 modes: [A hi | A lo | B hi | B lo], each a full fp32 tile.  bf16x3: [A | B], each raw fp32 tile converted in
+    // place into [hi bf16 | lo bf16] halves.
     auto a_hi = [&](int s) { return stage_ptr(s); };
-    auto a_lo = [&](int s) { return stage_ptr(s) + A_BYTES; };
-    auto b_hi = [&](int s) { return stage_ptr(s) + 2 * A_BYTES; };
-    auto b_lo = [&](int s) { return stage_ptr(s) + 2 * A_BYTES + C_::B_BYTES; };
+    auto a_lo = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES / 2 : A_BYTES); };
+    auto b_hi = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES : 2 * A_BYTES); };
+    auto b_lo = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES + C_::B_BYTES / 2 : 2 * A_BYTES + C_::B_BYTES); };
     // work item -> (m block, n block, first K-block, number of K-blocks)
     auto decode = [&](int64_t w, int& m_blk, int& n_blk, int& kb_beg, int& nkb) {
         const int sp = (int)(w % p.splits);
@@ -379,7 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[STAGES + s]), NUM_CONV_WARPS / CONV_GROUPS);
+            mbar_init(smem_u32(&bars[STAGES + s]), NUM_CONV_WARPS / (BF3X ? 1 : CONV_GROUPS));
             mbar_init(smem_u32(&bars[2 * STAGES + s]), 1);
         }
         for (int b = 0; b < NACC; ++b) {
@@ -429,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int64_t r = m0 / p.conv_W;
                         tma_load_4d(smem_u32(a_hi(s)), &tmA, full, c0, w0 + kw - pad, (int)(r % p.conv_H) + kh - pad, (int)(r / p.conv_H));
                     } else if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
-                    else tma_load_2d(smem_u32(a_lo(s)), &tmA, full, m_blk * BM, k0);
+                    else tma_load_2d(smem_u32(BF3X ? a_hi(s) : a_lo(s)), &tmA, full, m_blk * BM, k0);
                     if (!B_MN) {
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
@@ -437,7 +546,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_CW)
-                            tma_load_2d(smem_u32(b_lo(s) + r * ROWB), &tmB, full, n_blk * BN + r, k0);
+                            tma_load_2d(smem_u32((BF3X ? b_hi(s) : b_lo(s)) + r * ROWB), &tmB, full, n_blk * BN + r, k0);
                     }
                 }
             }
@@ -460,6 +569,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(smem_u32(&bars[STAGES + s]), ph);
                     tc_fence_after();
+                    if (BF3X) {
+                        // bf16 tiles: rows of 64 B (SWIZZLE_64B descriptors), UMMA K = 16 elements = 32 B
+                        constexpr uint32_t ib0 = make_idesc_bf16(BM, C_::N0);
+                        constexpr uint32_t ib1 = make_idesc_bf16(BM, C_::N1 > 0 ? C_::N1 : 16);
+                        const uint64_t dah = make_kmajor_desc<16>(smem_u32(a_hi(s))), dal = make_kmajor_desc<16>(smem_u32(a_lo(s)));
+                        const uint64_t dbh = make_kmajor_desc<16>(smem_u32(b_hi(s))), dbl = make_kmajor_desc<16>(smem_u32(b_lo(s)));
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint64_t da = pass == 0 ? dal : dah;
+                            const uint64_t db = pass == 1 ? dbl : dbh;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
+                                const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                                umma_bf16(tacc, da + koff, db + koff, ib0, acc);
+                                if (C_::N1 > 0) umma_bf16(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                            }
+                        }
+                    } else {
                     const uint64_t dah = make_kmajor_desc<BK>(smem_u32(a_hi(s))), dal = make_kmajor_desc<BK>(smem_u32(a_lo(s)));
                     const uint64_t dbh = make_kmajor_desc<BK>(smem_u32(b_hi(s))), dbl = make_kmajor_desc<BK>(smem_u32(b_lo(s)));
 #pragma unroll
@@ -483,6 +611,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
+                    }
                     umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
                 }
                 umma_commit(smem_u32(&acc_full[buf]));                  // accumulator of this work item complete
@@ -493,15 +622,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Two groups of four warps alternate ring stages: a stage's conversion is a latency chain (shared-memory read,
         // tcgen05.st + wait, proxy fence, arrive), so two stages in flight hide most of it.  Each group covers all four
         // TMEM lane quarters (warps 2-5 and 6-9: warp % 4 = 2,3,0,1).
-        constexpr int GT = 32 * NUM_CONV_WARPS / CONV_GROUPS;       // threads per group
-        const int grp = CONV_GROUPS == 1 ? 0 : (warp - 2) / (NUM_CONV_WARPS / CONV_GROUPS);
+        constexpr int NGRP = BF3X ? 1 : CONV_GROUPS;
+        constexpr int GT = 32 * NUM_CONV_WARPS / NGRP;              // threads per group
+        const int grp = NGRP == 1 ? 0 : (warp - 2) / (NUM_CONV_WARPS / NGRP);
         const int ct = (threadIdx.x - 64) - grp * GT;
         uint32_t it = 0;
         for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
             int m_blk, n_blk, kb_beg, nkb;
             decode(w, m_blk, n_blk, kb_beg, nkb);
             for (int i = 0; i < nkb; ++i, ++it) {
-                if (CONV_GROUPS == 2 && (int)(it & 1u) != grp) continue;
+                if (NGRP == 2 && (int)(it & 1u) != grp) continue;
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
@@ -510,9 +640,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
                     continue;
                 }
-                if (C_::A_TMEM) {
+                if (BF3X) {
+                    // all converter warps share a stage (the in-place conversion needs every read done before any write)
+                    constexpr int NTA = 32 * NUM_CONV_WARPS;
+                    const int cta = threadIdx.x - 64;
+                    if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1);
+                    else bf3x_mnmajor<BM, 128, NTA>(a_hi(s), cta, 1);
+                    if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2);
+                    else bf3x_mnmajor<BN, C_::B_CW, NTA>(b_hi(s), cta, 2);
+                } else if (C_::A_TMEM) {
                     const uint32_t ta = tmem_base + C_::A_COL0 + s * 2 * BK;
-                    if (CONV_GROUPS == 2) {
+                    if (NGRP == 2) {
                         convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), ta, warp, lane, 0);
                         convert_a_tmem<PASSES, BK, A_MN>(a_hi(s), a_lo(s), ta, warp, lane, 1);
                     } else {
@@ -522,7 +660,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!A_MN) convert_kmajor<PASSES, GT>(a_hi(s), a_lo(s), A_BYTES, ct, p.rawhi);
                     else convert_mnmajor<PASSES, BM, 128, BK, GT>(a_hi(s), a_lo(s), ct, 1 + grp);
                 }
-                if (!B_MN) convert_kmajor<PASSES, GT>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
+                if (BF3X) {
+                } else if (!B_MN) convert_kmajor<PASSES, GT>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
                 else convert_mnmajor<PASSES, BN, C_::B_CW, BK, GT>(b_hi(s), b_lo(s), ct, 3 + grp);
                 tc_fence_before();                                   // tcgen05.st (A ring) ordered before the arrive
                 fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
@@ -786,10 +925,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     auto kern = gemm_tc_kernel<BN, BK, PASSES, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
-        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK>::SMEM));
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK, PASSES>::SMEM));
         attr_done = true;
     }
-    kern<<<grid, THREADS, Cfg<BN, BK>::SMEM, s>>>(ta, tb, p);
+    kern<<<grid, THREADS, Cfg<BN, BK, PASSES>::SMEM, s>>>(ta, tb, p);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }
@@ -889,7 +1028,7 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     // narrow outputs (N <= 64) run the 64-wide tile with 32-float K-blocks: the main loop of this kernel has a fixed cost per
     // K-block (TMA -> convert -> MMA hand-offs), so halving the block count matters more than ring depth there
     const bool narrow = g0.N <= 64 && passes != 1 && g0.K >= 32 && (g0.conv_C == 0 || g0.conv_C % 32 == 0);
-    const int BK = (passes == 1 || narrow) ? 32 : default_bk();
+    const int BK = (passes == 1 || passes == 2 || narrow) ? 32 : default_bk();
     const int pr = plan_gemm(g0, BK, &pl);
     if (pr != CDG_OK) return pr;
     const GemmDesc& g = pl.g;
@@ -939,7 +1078,13 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
-    if (passes == 1) {
+    if (passes == 2) {
+        if (BN == 64) r = launch_layout<64, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 160) r = launch_layout<160, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        else r = launch_layout<304, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+    } else if (passes == 1) {
         if (BN == 64) r = launch_layout<64, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
         else if (BN == 160) r = launch_layout<160, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);

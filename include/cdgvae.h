@@ -35,7 +35,7 @@ extern "C" {
 
 enum { CDG_OK = 0, CDG_ERR_INVALID = 1, CDG_ERR_CUDA = 2, CDG_ERR_WORKSPACE = 3, CDG_ERR_UNSUPPORTED = 4 };
 enum { CDG_SCM_LINEAR = 0, CDG_SCM_PLANAR = 1 };
-enum { CDG_GEMM_AUTO = 0, CDG_GEMM_SIMT = 1, CDG_GEMM_TC3X = 2, CDG_GEMM_TC1X = 3 };
+enum { CDG_GEMM_AUTO = 0, CDG_GEMM_SIMT = 1, CDG_GEMM_TC3X = 2, CDG_GEMM_TC1X = 3, CDG_GEMM_BF3X = 4 };
 
 const char* cdg_last_error(void);
 int cdg_version(void);
