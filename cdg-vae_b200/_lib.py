@@ -117,7 +117,7 @@ EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
-           "cdg_conv2d_dgrad"]
+           "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit"]
 
 _lib = None
 
@@ -170,6 +170,9 @@ def lib():
                                      C.POINTER(Conv), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.cdg_conv2d_dgrad.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Conv),
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_split_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.cdg_gemm_bsplit.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     _lib = L
     return L
 

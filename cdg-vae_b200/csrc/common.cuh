@@ -133,7 +133,16 @@ struct GemmDesc {
     // convolution, K = conv_k^2 * conv_C in (kh, kw, c) order; the halo is zero-filled by TMA.  sa_m / sa_k are ignored.
     int conv_C = 0, conv_H = 0, conv_W = 0, conv_k = 0;
     int64_t conv_B = 0;
+    // Pre-split B operand (bf16x3 mode only): B(n,k) = b_hi16[n*ld_b16 + k] + b_lo16[n*ld_b16 + k] as bf16 pairs made once
+    // per step by launch_split_bf16 (weights); the kernel then streams ready-made tiles and converts only A.
+    const void* b_hi16 = nullptr;
+    const void* b_lo16 = nullptr;
+    int64_t ld_b16 = 0;
 };
+
+// W[rows, cols] (row stride ld) -> hi / lo bf16 copies; transpose != 0 writes them as [cols][rows] (row stride ld16 either way)
+int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
+                      cudaStream_t s);
 
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
 int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG_ERR_UNSUPPORTED otherwise

@@ -1,5 +1,6 @@
 // Memory-bound fused kernels of the training step: masked-sum/tanh/MSE reconstruction head
 // with its backward, fused Adam over the flat arena, and the per-step log row.
+#include <cuda_bf16.h>
 #include "latent.cuh"
 #include "elementwise.cuh"
 
@@ -151,6 +152,53 @@ int launch_gather_cols(const float* z, int d, float* zin, int f, int off, int ex
 int launch_scatter_add_cols(const float* gzin, float* gz, int d, int f, int off, int extra, int64_t B, cudaStream_t s) {
     const int blocks = (int)imin64((B * (f + 1) + 255) / 256, kNumSMs * 8);
     scatter_add_cols_kernel<<<blocks, 256, 0, s>>>(gzin, gz, d, f, off, extra, B);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+// ---- weight pre-split for the bf16x3 GEMM: W = bf16 hi + bf16 lo, optionally transposed ------------------------------
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ W, int64_t rows, int64_t cols, int64_t ld,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld16,
+                                                         int transpose) {
+    __shared__ float tile[32][33];
+    if (!transpose) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / cols, c = i - r * cols;
+            const float v = W[r * ld + c];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hi[r * ld16 + c] = h;
+            lo[r * ld16 + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+        return;
+    }
+    // transposed copy through a 32x32 shared-memory tile (coalesced on both sides)
+    const int64_t tr = (rows + 31) / 32, tc = (cols + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int64_t t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+        const int64_t r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int64_t r = r0 + j, c = c0 + tx;
+            tile[j][tx] = (r < rows && c < cols) ? W[r * ld + c] : 0.f;
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int64_t c = c0 + j, r = r0 + tx;               // output row = source column
+            if (c < cols && r < rows) {
+                const float v = tile[tx][j];
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                hi[c * ld16 + r] = h;
+                lo[c * ld16 + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+        }
+    }
+}
+int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
+                      cudaStream_t s) {
+    if (rows * cols == 0) return CDG_OK;
+    const int64_t work = transpose ? ((rows + 31) / 32) * ((cols + 31) / 32) : (rows * cols + 255) / 256;
+    split_bf16_kernel<<<(int)imin64(work, kNumSMs * 16), 256, 0, s>>>(W, rows, cols, ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld16,
+                                                                   transpose);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }

@@ -59,6 +59,7 @@ struct Params {
     int probe;                                  // timing experiments only (results invalid): 1 = no conversion, 2 = no TMA
     int rawhi;                                  // K-major operands: leave the raw tile as `hi` (tensor core truncates)
     int64_t work_total;                         // tiles_m * tiles_n * splits
+    int b_pre;                                  // bf16x3: B arrives pre-split (hi / lo bf16 tiles by TMA, no conversion)
     int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
 
@@ -451,7 +452,8 @@ __device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t 
 
 template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmB2, const Params p) {
     using C_ = Cfg<BN, BK, PASSES>;
     constexpr bool BF3X = C_::BF3X;
     constexpr int NACC = C_::NACC;
@@ -539,7 +541,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_4d(smem_u32(a_hi(s)), &tmA, full, c0, w0 + kw - pad, (int)(r % p.conv_H) + kh - pad, (int)(r / p.conv_H));
                     } else if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
                     else tma_load_2d(smem_u32(BF3X ? a_hi(s) : a_lo(s)), &tmA, full, m_blk * BM, k0);
-                    if (!B_MN) {
+                    if (BF3X && p.b_pre) {
+                        // ready-made bf16 tiles: rows of 64 B straight into the hi / lo halves
+#pragma unroll
+                        for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX) {
+                            tma_load_2d(smem_u32(b_hi(s) + r * 64), &tmB, full, k0, n_blk * BN + r);
+                            tma_load_2d(smem_u32(b_lo(s) + r * 64), &tmB2, full, k0, n_blk * BN + r);
+                        }
+                    } else if (!B_MN) {
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX)
                             tma_load_2d(smem_u32(b_hi(s) + r * ROWB), &tmB, full, k0, n_blk * BN + r);
@@ -646,7 +655,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int cta = threadIdx.x - 64;
                     if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1);
                     else bf3x_mnmajor<BM, 128, NTA>(a_hi(s), cta, 1);
-                    if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2);
+                    if (p.b_pre) {
+                    } else if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2);
                     else bf3x_mnmajor<BN, C_::B_CW, NTA>(b_hi(s), cta, 2);
                 } else if (C_::A_TMEM) {
                     const uint32_t ta = tmem_base + C_::A_COL0 + s * 2 * BK;
@@ -903,6 +913,27 @@ static int make_conv_map(const float* X, int64_t B, int H, int W, int C, int BK,
     g_maps[key] = *out;
     return CDG_OK;
 }
+// pre-split bf16 operand [rows][K] (row stride ld16 elements): box {32 bf16 = 64 B, box_rows}, SWIZZLE_64B
+static int make_map_bf16(const void* X, int64_t rows, int64_t K, int64_t ld16, int box_rows, CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
+    MapKey key{X, rows, K, ld16, -16, 32, box_rows, 3};
+    {
+        std::lock_guard<std::mutex> g(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return CDG_OK; }
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld16 * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r); return CDG_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *out;
+    return CDG_OK;
+}
 // spatial extents whose 128-pixel tiles are boxes: powers of two (W >= 128: multiples of 128)
 static bool conv_ok(const GemmDesc& g, int BK) {
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
@@ -921,25 +952,25 @@ static bool operand_ok(const float* X, int64_t s_r, int64_t s_k, int64_t rows, i
 }
 
 template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t s) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const Params& p, dim3 grid, cudaStream_t s) {
     auto kern = gemm_tc_kernel<BN, BK, PASSES, A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
         CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK, PASSES>::SMEM));
         attr_done = true;
     }
-    kern<<<grid, THREADS, Cfg<BN, BK, PASSES>::SMEM, s>>>(ta, tb, p);
+    kern<<<grid, THREADS, Cfg<BN, BK, PASSES>::SMEM, s>>>(ta, tb, tb2, p);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }
 
 template <int BN, int BK, int PASSES>
-static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid,
-                         cudaStream_t s) {
-    if (!a_mn && !b_mn) return launch<BN, BK, PASSES, false, false>(ta, tb, p, grid, s);
-    if (!a_mn && b_mn) return launch<BN, BK, PASSES, false, true>(ta, tb, p, grid, s);
-    if (a_mn && !b_mn) return launch<BN, BK, PASSES, true, false>(ta, tb, p, grid, s);
-    return launch<BN, BK, PASSES, true, true>(ta, tb, p, grid, s);
+static int launch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2,
+                         const Params& p, dim3 grid, cudaStream_t s) {
+    if (!a_mn && !b_mn) return launch<BN, BK, PASSES, false, false>(ta, tb, tb2, p, grid, s);
+    if (!a_mn && b_mn) return launch<BN, BK, PASSES, false, true>(ta, tb, tb2, p, grid, s);
+    if (a_mn && !b_mn) return launch<BN, BK, PASSES, true, false>(ta, tb, tb2, p, grid, s);
+    return launch<BN, BK, PASSES, true, true>(ta, tb, tb2, p, grid, s);
 }
 
 }  // namespace tc
@@ -962,7 +993,7 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     if (g.K < 16 || (g.M < 32 && g.N < 32) || g.M * g.N < 4096) return CDG_ERR_UNSUPPORTED;
     // put the long output dimension on M (128-row tiles) when the other fits one N tile
     if (g.conv_C > 0 && !conv_ok(g, BK)) return CDG_ERR_UNSUPPORTED;
-    if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON && g.conv_C == 0) {
+    if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON && g.conv_C == 0 && !g.b_hi16) {
         std::swap(g.A, g.B); std::swap(g.sa_m, g.sb_n); std::swap(g.sa_k, g.sb_k); std::swap(g.M, g.N);
         std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
         bias_on_m = 1;
@@ -971,7 +1002,10 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     bool a_mn, b_mn;
     if (g.conv_C > 0) a_mn = false;
     else if (!operand_ok(g.A, g.sa_m, g.sa_k, g.M, g.K, &a_mn)) return CDG_ERR_UNSUPPORTED;
-    if (!operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn)) return CDG_ERR_UNSUPPORTED;
+    if (g.b_hi16) {
+        if (BK != 32 || g.ld_b16 % 8 != 0 || (((uintptr_t)g.b_hi16 | (uintptr_t)g.b_lo16) & 15) != 0) return CDG_ERR_UNSUPPORTED;
+        b_mn = false;
+    } else if (!operand_ok(g.B, g.sb_n, g.sb_k, g.N, g.K, &b_mn)) return CDG_ERR_UNSUPPORTED;
     int BN;
     if (g.N <= 64 && BK == 32) BN = 64;
     else if (g.N <= 128) BN = 128;
@@ -1075,32 +1109,42 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     const int b_box = pl.b_mn ? (BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4))) : (BN <= 256 ? BN : BN / 2);
     if (g.conv_C > 0) CDG_TRY(make_conv_map(g.A, g.conv_B, g.conv_H, g.conv_W, g.conv_C, BK, &ta));
     else CDG_TRY(make_map(g.A, g.M, g.K, g.sa_m, g.sa_k, pl.a_mn, 128, BK, &ta));
-    CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
+    CUtensorMap tb2;
+    if (g.b_hi16 && passes == 2) {
+        const int pb = BN <= 256 ? BN : BN / 2;
+        CDG_TRY(make_map_bf16(g.b_hi16, g.N, g.K, g.ld_b16, pb, &tb));
+        CDG_TRY(make_map_bf16(g.b_lo16, g.N, g.K, g.ld_b16, pb, &tb2));
+        p.b_pre = 1;
+    } else {
+        CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
+        tb2 = tb;
+        p.b_pre = 0;
+    }
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
     if (passes == 2) {
-        if (BN == 64) r = launch_layout<64, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 128) r = launch_layout<128, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 160) r = launch_layout<160, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 64) r = launch_layout<64, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 160) r = launch_layout<160, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else r = launch_layout<304, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
     } else if (passes == 1) {
-        if (BN == 64) r = launch_layout<64, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 160) r = launch_layout<160, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 64) r = launch_layout<64, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 160) r = launch_layout<160, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else r = launch_layout<304, 32, 1>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
     } else if (BK == 32) {
-        if (BN == 64) r = launch_layout<64, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 128) r = launch_layout<128, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 160) r = launch_layout<160, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 64) r = launch_layout<64, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 128) r = launch_layout<128, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 160) r = launch_layout<160, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else r = launch_layout<304, 32, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
     } else {
-        if (BN == 128) r = launch_layout<128, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 160) r = launch_layout<160, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else if (BN == 256) r = launch_layout<256, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
-        else r = launch_layout<304, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, p, grid, s);
+        if (BN == 128) r = launch_layout<128, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 160) r = launch_layout<160, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else if (BN == 256) r = launch_layout<256, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
+        else r = launch_layout<304, 16, 3>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
     }
     CDG_TRY(r);
     if (p.atomic && g0.epi != EPI_NONE)

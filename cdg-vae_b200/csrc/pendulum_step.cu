@@ -16,21 +16,29 @@ struct cdg_pendulum_plan {
     cdg_pendulum_config c;
     int lat_off[CDG_MAX_DEC];   // first latent column of decoder k
     cdg::Profiler prof;
+    // bf16 (hi, lo) copies of the big Linear weights, made once per step for the bf16x3 GEMM: element
+    // offsets into a bf16 pool in the workspace, per layer (enc j -> j, dec k,j -> 3 + 3k + j); -1 = layer not split
+    static constexpr int kLayers = 3 + 3 * CDG_MAX_DEC;
+    int64_t f_hi[kLayers], f_lo[kLayers], t_hi[kLayers], t_lo[kLayers];   // forward [out][pad8(in)], transposed [in][pad8(out)]
+    int64_t split_elems = 0;
 };
 
 namespace cdg {
 
 static inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }
+static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
+// batches from which the step pre-splits its weights (below, the extra ~0.1 ms per step is not repaid)
+constexpr int64_t kSplitMinBatch = 2048;
 
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
-        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, total;
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, total;
     int64_t sep[CDG_MAX_DEC];      // general masks: full-width output of every decoder
     int64_t zin[CDG_MAX_DEC], gzin; // DR variant: gathered decoder inputs [B, f+1] and their gradient
     int64_t gemm_ws_floats;
 };
 
-static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL) {
+static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, int64_t split_elems = 0) {
     PendWs w;
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o += pad64(n); return r; };
@@ -51,6 +59,7 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL) {
     w.g_h2l = take(BL * H); w.g_h1l = take(BL * H);
     w.gemm_ws_floats = 1 << 16;
     w.gemm_ws = take(w.gemm_ws_floats);
+    w.wsplit = take(B >= kSplitMinBatch ? (split_elems + 1) / 2 : 0);
     w.total = o;
     return w;
 }
@@ -65,7 +74,67 @@ struct Ctx {
     int mode;
     Profiler* prof = nullptr;
     void mark(int cat) const { if (prof) prof->mark(cat, s); }
+    bool split = false;         // weights pre-split into bf16 (hi, lo) for this call
+    // layer index of L in the plan's split tables, or -1
+    int layer_of(const cdg_linear& L) const {
+        const cdg_pendulum_config& cf = p->c;
+        for (int j = 0; j < 3; ++j) if (cf.enc[j].w == L.w) return j;
+        for (int k = 0; k < cf.n_dec; ++k)
+            for (int j = 0; j < 3; ++j) if (cf.dec[k][j].w == L.w) return 3 + 3 * k + j;
+        return -1;
+    }
+    const uint16_t* pool() const { return reinterpret_cast<const uint16_t*>(W + w.wsplit); }
 };
+
+// point a forward GEMM (B = W[row_lo:, :], K = in) at the pre-split copy of L; false when L has none
+static bool use_split_fwd(const Ctx& c, const cdg_linear& L, int64_t row_lo, GemmDesc& g) {
+    if (!c.split) return false;
+    const int id = c.layer_of(L);
+    if (id < 0 || c.p->f_hi[id] < 0) return false;
+    const int64_t ld = pad8(L.in);
+    g.b_hi16 = c.pool() + c.p->f_hi[id] + row_lo * ld;
+    g.b_lo16 = c.pool() + c.p->f_lo[id] + row_lo * ld;
+    g.ld_b16 = ld;
+    return true;
+}
+// input-gradient GEMM (B(n,k) = W[row_lo + k][n], K = rows): the transposed copy [in][pad8(out)], columns from row_lo
+static bool use_split_dgrad(const Ctx& c, const cdg_linear& L, int64_t row_lo, GemmDesc& g) {
+    if (!c.split || row_lo % 8 != 0) return false;
+    const int id = c.layer_of(L);
+    if (id < 0 || c.p->t_hi[id] < 0) return false;
+    g.b_hi16 = c.pool() + c.p->t_hi[id] + row_lo;
+    g.b_lo16 = c.pool() + c.p->t_lo[id] + row_lo;
+    g.ld_b16 = pad8(L.out);
+    return true;
+}
+// the bf16x3 kernel with ready-made weight tiles; anything it cannot take goes the usual way
+static int gemm_weights(const Ctx& c, GemmDesc& g, bool have_split) {
+    if (have_split) {
+        const int r = gemm_tc(g, 2, nullptr, 0, c.s);
+        if (r != CDG_ERR_UNSUPPORTED) return r;
+        g.b_hi16 = g.b_lo16 = nullptr;
+    }
+    return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+}
+
+// once per call: bf16 (hi, lo) copies of every big weight, in both orientations
+static int split_weights(Ctx& c, int64_t B) {
+    c.split = false;
+    if (B < kSplitMinBatch || c.p->split_elems == 0 || (c.mode != CDG_GEMM_AUTO && c.mode != CDG_GEMM_BF3X)) return CDG_OK;
+    const cdg_pendulum_config& cf = c.p->c;
+    uint16_t* pool = reinterpret_cast<uint16_t*>(c.W + c.w.wsplit);
+    auto one = [&](const cdg_linear& L, int id) -> int {
+        if (c.p->f_hi[id] < 0) return CDG_OK;
+        CDG_TRY(launch_split_bf16(c.P + L.w, L.out, L.in, L.in, pool + c.p->f_hi[id], pool + c.p->f_lo[id], pad8(L.in), 0, c.s));
+        CDG_TRY(launch_split_bf16(c.P + L.w, L.out, L.in, L.in, pool + c.p->t_hi[id], pool + c.p->t_lo[id], pad8(L.out), 1, c.s));
+        return CDG_OK;
+    };
+    for (int j = 0; j < 3; ++j) CDG_TRY(one(cf.enc[j], j));
+    for (int k = 0; k < cf.n_dec; ++k)
+        for (int j = 0; j < 3; ++j) CDG_TRY(one(cf.dec[k][j], 3 + 3 * k + j));
+    c.split = true;
+    return CDG_OK;
+}
 
 // Y[M,N] = act(X[M,K] W[N,K]^T + b)   (nn.Linear forward)
 static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
@@ -76,7 +145,7 @@ static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linea
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = L.in; g.sb_k = 1;
     g.C = Y; g.ldc = ldy; g.M = M; g.N = n_rows; g.K = L.in;
     g.epi = act ? EPI_BIAS_ACT : EPI_BIAS; g.act = CDG_ACT_ELU; g.bias = c.P + L.b + row_lo;
-    return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+    return gemm_weights(c, g, use_split_fwd(c, L, row_lo, g));
 }
 // dW[rows,K] += dY[M,rows]^T X[M,K];  db[rows] += colsum(dY)
 static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float* X, int64_t ldx, const cdg_linear& L,
@@ -100,7 +169,7 @@ static int linear_dgrad(const Ctx& c, const float* dY, int64_t ldy, const cdg_li
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = 1; g.sb_k = L.in;
     g.C = dX; g.ldc = lddx; g.M = M; g.N = L.in; g.K = n_rows;
     if (Hout) { g.epi = EPI_MUL_DACT; g.act = CDG_ACT_ELU; g.aux = Hout; g.ld_aux = ldh; }
-    return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+    return gemm_weights(c, g, use_split_dgrad(c, L, row_lo, g));
 }
 
 static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
@@ -177,9 +246,18 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
         if (cf.col_hi[k] - cf.col_lo[k] > 0) {
             c.mark(PROF_DEC2_FWD);
-            const GemmDesc g = dec_out_desc(c, k, B, pre, x, xhat, acc);
-            if (x) CDG_TRY(gemm_tc(g, c.mode == CDG_GEMM_TC1X ? 1 : 3, nullptr, 0, c.s));
-            else CDG_TRY(gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s));
+            GemmDesc g = dec_out_desc(c, k, B, pre, x, xhat, acc);
+            const bool sp = use_split_fwd(c, cf.dec[k][2], cf.col_lo[k], g);
+            if (x) {
+                int r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
+                if (r == CDG_ERR_UNSUPPORTED) {
+                    g.b_hi16 = g.b_lo16 = nullptr;
+                    r = gemm_tc(g, c.mode == CDG_GEMM_TC1X ? 1 : (c.mode == CDG_GEMM_BF3X ? 2 : 3), nullptr, 0, c.s);
+                }
+                CDG_TRY(r);
+            } else {
+                CDG_TRY(gemm_weights(c, g, sp));
+            }
         }
     }
     return CDG_OK;
@@ -255,6 +333,22 @@ extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_
     p->c = c;
     int off = 0;
     for (int k = 0; k < c.n_dec; ++k) { p->lat_off[k] = off; off += c.factor[k]; }
+    // bf16 split pool: layers whose contraction and output extents can both feed tensor-core tiles
+    int64_t e = 0;
+    auto plan_layer = [&](const cdg_linear& L, int id) {
+        p->f_hi[id] = p->f_lo[id] = p->t_hi[id] = p->t_lo[id] = -1;
+        if (L.in < 16 || L.out < 16) return;
+        const int64_t nf = (int64_t)L.out * pad8(L.in), nt = (int64_t)L.in * pad8(L.out);
+        p->f_hi[id] = e; e += pad64(nf);
+        p->f_lo[id] = e; e += pad64(nf);
+        p->t_hi[id] = e; e += pad64(nt);
+        p->t_lo[id] = e; e += pad64(nt);
+    };
+    for (int i = 0; i < cdg_pendulum_plan::kLayers; ++i) p->f_hi[i] = p->f_lo[i] = p->t_hi[i] = p->t_lo[i] = -1;
+    for (int j = 0; j < 3; ++j) plan_layer(c.enc[j], j);
+    for (int k = 0; k < c.n_dec; ++k)
+        for (int j = 0; j < 3; ++j) plan_layer(c.dec[k][j], 3 + 3 * k + j);
+    p->split_elems = e;
     *out = p;
     return CDG_OK;
 }
@@ -288,7 +382,7 @@ extern "C" int cdg_pendulum_profile_read(cdg_pendulum_plan* p, double* out_ms) {
 
 extern "C" int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l) {
     if (!p || batch < 0 || batch_l < 0) return -1;
-    return pend_layout(p->c, batch, batch_l).total * 4;
+    return pend_layout(p->c, batch, batch_l, p->split_elems).total * 4;
 }
 
 extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pendulum_io* io, void* stream) {
@@ -303,7 +397,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     c.p = p; c.P = io->params; c.G = io->grads; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
     c.mode = cf.gemm_mode;
     c.prof = p->prof.enabled ? &p->prof : nullptr;
-    c.w = pend_layout(cf, B, BL);
+    c.w = pend_layout(cf, B, BL, p->split_elems);
     if (c.w.total * 4 > io->workspace_bytes) {
         set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
         return CDG_ERR_WORKSPACE;
@@ -314,6 +408,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     cudaStream_t s = c.s;
     c.mark(PROF_MISC);
 
+    CDG_TRY(split_weights(c, B));
     // optimizer.zero_grad() (train.py:168) + loss accumulators
     CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * cf.n_params, s));
     CDG_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_LEN, s));
@@ -411,7 +506,7 @@ extern "C" int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd
     Ctx c;
     c.p = p; c.P = io->params; c.G = nullptr; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
     c.mode = cf.gemm_mode;
-    c.w = pend_layout(cf, B, 0);
+    c.w = pend_layout(cf, B, 0, p->split_elems);
     if (c.w.total * 4 > io->workspace_bytes) {
         set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
         return CDG_ERR_WORKSPACE;
@@ -469,4 +564,20 @@ extern "C" int cdg_gemm(int mode, const float* A, int64_t sa_m, int64_t sa_k, co
     g.A = A; g.sa_m = sa_m; g.sa_k = sa_k; g.B = B; g.sb_n = sb_n; g.sb_k = sb_k;
     g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.accumulate = accumulate;
     return gemm_dispatch(mode, g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// cdg_gemm with the B operand (weights) pre-split into bf16 (hi, lo) by cdg_split_bf16: the bf16x3 fast path
+extern "C" int cdg_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16,
+                              int transpose, void* stream) {
+    CDG_REQUIRE(W && hi && lo && ld16 % 8 == 0, "cdg_split_bf16: bad argument");
+    return launch_split_bf16(W, rows, cols, ld, hi, lo, ld16, transpose, (cudaStream_t)stream);
+}
+extern "C" int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const void* b_hi, const void* b_lo, int64_t ld16,
+                               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
+    CDG_REQUIRE(A && b_hi && b_lo && C, "cdg_gemm_bsplit: null pointer");
+    GemmDesc g;
+    g.A = A; g.sa_m = sa_m; g.sa_k = sa_k; g.B = nullptr; g.sb_n = ld16; g.sb_k = 1;
+    g.b_hi16 = b_hi; g.b_lo16 = b_lo; g.ld_b16 = ld16;
+    g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+    return gemm_tc(g, 2, nullptr, 0, (cudaStream_t)stream);
 }

@@ -302,6 +302,13 @@ int cdg_gemm(int mode, const float* A, int64_t sa_m, int64_t sa_k, const float* 
              float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
              void* workspace, int64_t workspace_bytes, void* stream);
 
+/* bf16x3 fast path for weight operands: W = bf16 hi + bf16 lo made once per step (optionally transposed, row stride ld16
+ * elements, a multiple of 8), then C[M,N] = sum_k A(m,k) * (b_hi[n*ld16+k] + b_lo[n*ld16+k]) on the tcgen05 kernel. */
+int cdg_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
+                   void* stream);
+int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const void* b_hi, const void* b_lo, int64_t ld16, float* C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
