@@ -138,6 +138,11 @@ struct GemmDesc {
     const void* b_hi16 = nullptr;
     const void* b_lo16 = nullptr;
     int64_t ld_b16 = 0;
+    // Same for A, usable only where the planner swaps the operands (N > 304 >= M: the first-layer weight gradient, whose
+    // narrow operand is dY): A(m,k) = a_hi16[m*ld_a16 + k] + a_lo16[...].
+    const void* a_hi16 = nullptr;
+    const void* a_lo16 = nullptr;
+    int64_t ld_a16 = 0;
 };
 
 // W[rows, cols] (row stride ld) -> hi / lo bf16 copies; transpose != 0 writes them as [cols][rows] (row stride ld16 either way)

@@ -996,8 +996,10 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     if (g.N > 304 && g.M <= 304 && g.epi != EPI_RECON && g.conv_C == 0 && !g.b_hi16) {
         std::swap(g.A, g.B); std::swap(g.sa_m, g.sb_n); std::swap(g.sa_k, g.sb_k); std::swap(g.M, g.N);
         std::swap(sc_m, sc_n); std::swap(aux_sm, aux_sn);
+        std::swap(g.a_hi16, g.b_hi16); std::swap(g.a_lo16, g.b_lo16); std::swap(g.ld_a16, g.ld_b16);
         bias_on_m = 1;
     }
+    if (g.a_hi16) return CDG_ERR_UNSUPPORTED;       // a pre-split A is only usable once swapped into the B slot
     if (g.N < 16 && g.conv_C == 0) return CDG_ERR_UNSUPPORTED;   // (conv mode: a 3-channel toRGB still beats im2col + rowdot)
     bool a_mn, b_mn;
     if (g.conv_C > 0) a_mn = false;

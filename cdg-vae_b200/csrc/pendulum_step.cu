@@ -32,7 +32,8 @@ constexpr int64_t kSplitMinBatch = 2048;
 
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
-        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, total;
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, total;
+    int64_t asplit_half;           // elements of one (hi or lo) transposed activation copy
     int64_t sep[CDG_MAX_DEC];      // general masks: full-width output of every decoder
     int64_t zin[CDG_MAX_DEC], gzin; // DR variant: gathered decoder inputs [B, f+1] and their gradient
     int64_t gemm_ws_floats;
@@ -60,6 +61,9 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, i
     w.gemm_ws_floats = 1 << 16;
     w.gemm_ws = take(w.gemm_ws_floats);
     w.wsplit = take(B >= kSplitMinBatch ? (split_elems + 1) / 2 : 0);
+    // wgrad: the narrow [batch, <= 304] operand, split + transposed per call (hi then lo)
+    w.asplit_half = pad64(304 * pad8(B > BL ? B : BL));
+    w.asplit = take(B >= kSplitMinBatch && split_elems > 0 ? w.asplit_half : 0);
     w.total = o;
     return w;
 }
@@ -156,7 +160,26 @@ static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float*
     g.B = X; g.sb_n = 1; g.sb_k = ldx;
     g.C = c.G + L.w + row_lo * L.in; g.ldc = L.in; g.M = n_rows; g.N = L.in; g.K = M;
     g.epi = EPI_NONE; g.accumulate = 1;
-    CDG_TRY(gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s));
+    // bf16x3 with the narrow operand ([batch, <= 304]: an activation, or dY for the first layer whose operands the planner
+    // swaps) split and transposed beforehand, so that only the wide streamed operand is converted inside the GEMM
+    int r = CDG_ERR_UNSUPPORTED;
+    if (c.split && M >= kSplitMinBatch && n_rows >= 16 && L.in >= 16) {
+        uint16_t* hi = reinterpret_cast<uint16_t*>(c.W + c.w.asplit);
+        uint16_t* lo = hi + c.w.asplit_half;
+        const int64_t ld16 = pad8(M);
+        if (L.in <= 304) {
+            CDG_TRY(launch_split_bf16(X, M, L.in, ldx, hi, lo, ld16, 1, c.s));
+            g.b_hi16 = hi; g.b_lo16 = lo; g.ld_b16 = ld16;
+            r = gemm_tc(g, 2, nullptr, 0, c.s);
+        } else if (n_rows <= 304) {
+            CDG_TRY(launch_split_bf16(dY, M, n_rows, ldy, hi, lo, ld16, 1, c.s));
+            g.a_hi16 = hi; g.a_lo16 = lo; g.ld_a16 = ld16;
+            r = gemm_tc(g, 2, nullptr, 0, c.s);
+        }
+        g.b_hi16 = g.b_lo16 = g.a_hi16 = g.a_lo16 = nullptr;
+    }
+    if (r == CDG_ERR_UNSUPPORTED) r = gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+    CDG_TRY(r);
     c.mark(PROF_MISC);
     return launch_colsum(dY, ldy, M, n_rows, c.G + L.b + row_lo, c.s);
 }

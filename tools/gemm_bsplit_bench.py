@@ -28,8 +28,12 @@ def main():
     # (name, A [M,K], W, transpose W?, N, K)   C = A @ Weff^T with Weff[n,k]
     cases = [("enc0_fwd   x @ W0^T", x, w0, 0, H, P), ("dec2_fwd   a2 @ W2^T", h, w2, 0, 5952, H),
              ("dec2_dgrad g @ W2", gp, w2, 1, H, 5952), ("enc1_fwd   h @ W1^T", h, w2[:H].contiguous(), 0, H, H)]
+    # weight-gradient contractions: A = the wide streamed operand, batch-major (A(m,k) = A[k, m]); B = the [B,300] operand,
+    # split + transposed once.  (name, A [K,M], W=[K,N] source of B, transpose=1, N, K, a_batch_major)
+    cases += [("dec2_wgrad g^T @ a2", gp, h, 1, H, Bt), ("enc0_wgrad x^T @ gh", x, h, 1, H, Bt)]
     for name, A, W, tr, N, K in cases:
-        M = A.shape[0]
+        bm = name.startswith(("dec2_wgrad", "enc0_wgrad"))
+        M = A.shape[1] if bm else A.shape[0]
         ld16 = pad8(K)
         hi = torch.zeros(N, ld16, dtype=torch.bfloat16, device="cuda")
         lo = torch.zeros_like(hi)
@@ -37,14 +41,15 @@ def main():
         out = torch.zeros(M, N, device="cuda")
         rows = torch.arange(0, M, max(1, M // 64), device="cuda")[:64]
         Weff = (W.t() if tr else W).double()
-        ref = A[rows].double() @ Weff.t()
+        ref = (A[:, rows].t() if bm else A[rows]).double() @ Weff.t()
+        sa = (1, A.shape[1]) if bm else (A.shape[1], 1)
 
         def run_split():
-            _lib.check(L.cdg_gemm_bsplit(A.data_ptr(), A.shape[1], 1, hi.data_ptr(), lo.data_ptr(), ld16, out.data_ptr(), N, M, N, K, s))
+            _lib.check(L.cdg_gemm_bsplit(A.data_ptr(), sa[0], sa[1], hi.data_ptr(), lo.data_ptr(), ld16, out.data_ptr(), N, M, N, K, s))
 
         def run_mode(mode):
             sb = (1, W.shape[1]) if tr else (W.shape[1], 1)
-            _lib.check(L.cdg_gemm(_lib.GEMM_MODES[mode], A.data_ptr(), A.shape[1], 1, W.data_ptr(), sb[0], sb[1], out.data_ptr(), N,
+            _lib.check(L.cdg_gemm(_lib.GEMM_MODES[mode], A.data_ptr(), sa[0], sa[1], W.data_ptr(), sb[0], sb[1], out.data_ptr(), N,
                                   M, N, K, 0, ws.data_ptr(), ws.numel(), s))
 
         for label, fn in (("tc3x", lambda: run_mode("tc3x")), ("bf3x", lambda: run_mode("bf3x")), ("bf3x+presplit", run_split)):
