@@ -27,9 +27,10 @@ MACS_L = 3_778_800 * 2 + 92_400   # labeled sample: encoder fwd + wgrad + dgrad 
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_enc0_fwd_tc3x.txt): encoder first Linear forward,
-# x[32768,12288] @ W0[300,12288]^T.  Algorithmic bytes of that launch: x once + W0 once + h1 written once.
-NCU_TRAFFIC = {"bytes": 1.791965e9 + 39.7696e6, "launch": "gemm_tc_kernel<304,16,3,0,0> enc0 forward, M=32768 N=300 K=12288",
+# `ncu --set full` capture (profiles/r01_ncu_enc0_fwd_bf3x_presplit.txt): encoder first Linear forward,
+# x[32768,12288] @ W0[300,12288]^T.  Algorithmic bytes of that launch: x once + W0 once (as bf16 hi + lo) + h1 written once.
+NCU_TRAFFIC = {"bytes": 1.826604e9 + 46.850048e6,
+               "launch": "gemm_tc_kernel<304,32,2,0,0> (bf16x3, pre-split weights) enc0 forward, M=32768 N=300 K=12288",
                "algorithmic": 32768 * 12288 * 4 + 300 * 12288 * 4 + 32768 * 300 * 4}
 
 
@@ -175,7 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 17, help="unlabeled samples per GPU per step")
-    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc3x", "tc1x"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc3x", "tc1x", "bf3x"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -293,10 +294,11 @@ def main():
                          "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                          "traffic": NCU_TRAFFIC["bytes"], "traffic_launch": NCU_TRAFFIC["launch"],
                          "traffic_algorithmic": NCU_TRAFFIC["algorithmic"],
-                         "frac_of_fp32_faithful_ceiling": ach / (tf_sus / 6.0),
+                         "frac_of_fp32_faithful_ceiling": ach / (tf_sus / (3.0 if args.gemm in ("auto", "bf3x") else 6.0)),
                          "peak_source": f"bf16 dense sustained, {src} (MEASURED_PEAKS.json)",
                          "algorithmic_flops_per_step": flops / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,
-                         "note": "fp32-faithful arithmetic: 3xTF32 costs 6 bf16-equivalent passes, so frac <= 1/6 in that mode",
+                         "note": "fp32-faithful arithmetic (parity 1e-4): every product is 3 bf16 MMAs on hi/lo splits (bf16x3; "
+                                 "gemm=tc3x: 3 TF32 MMAs = 6 bf16-equivalents), so frac <= 1/3 (1/6) by construction",
                          "breakdown_ms_per_step": {k: v / args.steps for k, v in prof.items()}},
             "cpu_baseline": cpu,
             "e2e": e2e,

@@ -43,7 +43,12 @@ constexpr int NUM_CONV_WARPS = 8;
 #define CDG_TC_CONV_GROUPS 2
 #endif
 constexpr int CONV_GROUPS = CDG_TC_CONV_GROUPS;   // 1: all eight converter warps share every stage; 2: two groups alternate stages
-constexpr int NUM_EPI_WARPS = 4;
+#ifndef CDG_TC_EPI_WARPS
+#define CDG_TC_EPI_WARPS 4
+#endif
+// 4 epilogue warps (one per TMEM lane quarter).  8 (two per quarter, each taking half of the tile's columns) were measured
+// on the short-K fused-head GEMM (dec2 forward, K = 300): 7.4 vs 6.8 ms per step -- the epilogue is not what paces it
+constexpr int NUM_EPI_WARPS = CDG_TC_EPI_WARPS;
 constexpr int THREADS = 32 * (2 + NUM_CONV_WARPS + NUM_EPI_WARPS);
 
 struct Params {
@@ -682,6 +687,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                                      // TMEM lane quarter this warp may access
+        // column range of this warp: the whole tile (4 epilogue warps) or one half (8)
+        constexpr int CSPLIT = ((BN / 2 + 15) / 16) * 16;
+        const int ehalf = NUM_EPI_WARPS == 8 ? (warp - (2 + NUM_CONV_WARPS)) >> 2 : 0;
+        const int c_beg = ehalf == 0 ? 0 : CSPLIT;
+        const int c_end = (NUM_EPI_WARPS == 8 && ehalf == 0) ? CSPLIT : BN;
         uint32_t j = 0;
         float rloss = 0.f;
         for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x, ++j) {
@@ -703,7 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float4 r0[4], r1[4], r2[4];                                // chunks c0, c0+16, c0+32 in flight
             auto fetch = [&](int c0, float4* dst) {
                 const int64_t n0 = (int64_t)n_blk * BN + c0;
-                if (side && c0 < BN && n0 + 16 <= p.N) {
+                if (side && c0 < c_end && n0 + 16 <= p.N) {
                     if (p.vec8) {
                         ld_nc_v8(side + c0, dst[0], dst[1]);
                         ld_nc_v8(side + c0 + 8, dst[2], dst[3]);
@@ -713,9 +723,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             };
-            fetch(0, r0); fetch(16, r1); fetch(32, r2);
+            fetch(c_beg, r0); fetch(c_beg + 16, r1); fetch(c_beg + 32, r2);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = c_beg; c0 < c_end; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 float4 cur[4];
