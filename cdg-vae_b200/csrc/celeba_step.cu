@@ -75,7 +75,7 @@ struct WMat {
 };
 // weights as the B operand.  gemm_mode "bf3x": the bf16x3 kernel with ready-made weight tiles (18.0 vs 19.2 ms per step at
 // batch 16).  It is NOT the default here: this step amplifies GEMM rounding by 1e3 .. 1e4 (tools/celeba_grad_noise.py), and
-// bf16x3's 4-8e-6 per GEMM lands the fc gradient at 1.8e-2 of the fp64 oracle where 3xTF32 (and the reference's own fp32)
+// bf16x3's 4-8e-6 per GEMM lands the fc gradient at 1.8e-2 of an fp64 evaluation where 3xTF32 (and the reference's own fp32)
 // stay within 1e-2 -- so "auto" keeps the 3xTF32 arithmetic for the CelebA convolutions.
 static int gemm_w(Cx& cx, GemmDesc& g, const WMat& wm) {
     if (wm.hi && cx.mode == CDG_GEMM_BF3X) {
