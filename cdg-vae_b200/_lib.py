@@ -37,7 +37,8 @@ class PendulumIO(C.Structure):
                 ("workspace_bytes", C.c_int64), ("x", C.c_void_p), ("y", C.c_void_p), ("ld_y", C.c_int32),
                 ("noise", C.c_void_p), ("batch", C.c_int64), ("x_l", C.c_void_p), ("y_l", C.c_void_p),
                 ("ld_y_l", C.c_int32), ("batch_l", C.c_int64), ("logs", C.c_void_p), ("xhat", C.c_void_p),
-                ("masks", C.c_void_p)]
+                ("masks", C.c_void_p), ("d_params", C.c_void_p), ("d_grads", C.c_void_p), ("d_net", Linear * 3),
+                ("d_n_params", C.c_int64), ("perm", C.c_void_p), ("gamma", C.c_float)]
 
 
 class PendulumFwdIO(C.Structure):
@@ -113,7 +114,7 @@ class CelebaIO(C.Structure):
 # every symbol include/cdgvae.h declares
 EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
-           "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_forward_backward",
+           "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
@@ -143,6 +144,8 @@ def lib():
     L.cdg_pendulum_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cdg_pendulum_workspace_bytes.restype = C.c_int64
     L.cdg_pendulum_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.cdg_pendulum_workspace_bytes_infomax.restype = C.c_int64
+    L.cdg_pendulum_workspace_bytes_infomax.argtypes = [C.c_void_p, C.c_int64]
     L.cdg_pendulum_create.argtypes = [C.POINTER(PendulumConfig), C.POINTER(C.c_void_p)]
     L.cdg_pendulum_destroy.argtypes = [C.c_void_p]
     L.cdg_pendulum_destroy.restype = None

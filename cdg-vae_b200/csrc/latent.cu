@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(LatentArgs a) {
         for (int j = 0; j < CDG_MAX_NODE; ++j)
             gu[j] = j < d ? flow_bwd(ft, a.scm, a.flow_num, j, a.u_in[b * d + j], a.g_z[b * d + j], fg) : 0.f;
         matvec_AT(ft, d, gu, ge);
+        if (a.g_eps) {
+#pragma unroll
+            for (int i = 0; i < CDG_MAX_NODE; ++i)
+                if (i < d) ge[i] += a.g_eps[b * d + i];
+        }
 #pragma unroll
         for (int i = 0; i < CDG_MAX_NODE; ++i) {
             if (i < d) {

@@ -21,6 +21,7 @@ struct LatentArgs {
     const float* u_in;            // [batch, d] saved orig_latent (bwd)
     const float* g_z;             // [batch, d]
     const float* g_align;         // [batch, 2d] or null
+    const float* g_eps;           // [batch, d] or null: extra d loss / d epsilon (InfoMax discriminator path)
     float* eps_out; float* u_out; float* z_out;
     float* g_out;                 // [batch, 2d]
     double* acc;                  // loss accumulators (may be null)

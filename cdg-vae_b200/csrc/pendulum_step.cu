@@ -34,18 +34,20 @@ struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
         g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, total;
     int64_t asplit_half;           // elements of one (hi or lo) transposed activation copy
+    // InfoMax discriminator (allocated only when requested)
+    int64_t dx, dh1j, dh1m, dh2j, dh2m, dj, dm, dgj, dgm, dg2, dg1j, dg1m, deps_perm, dtj, dtm, dgeps;
     int64_t sep[CDG_MAX_DEC];      // general masks: full-width output of every decoder
     int64_t zin[CDG_MAX_DEC], gzin; // DR variant: gathered decoder inputs [B, f+1] and their gradient
     int64_t gemm_ws_floats;
 };
 
-static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, int64_t split_elems = 0) {
+static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, int64_t split_elems = 0, bool infomax = false) {
     PendWs w;
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o += pad64(n); return r; };
     const int64_t H = c.hidden, d = c.node, P = c.input_dim;
     const int64_t Bal = BL > 0 ? BL : B;
-    w.acc = take(2 * ACC_LEN + 2);
+    w.acc = take(2 * ACC_LEN + 8);
     w.h1 = take(B * H); w.h2 = take(B * H); w.ml = take(B * 2 * d);
     w.eps = take(B * d); w.u = take(B * d); w.z = take(B * d);
     w.zal = take(Bal * d); w.g_align = take(Bal * 2 * d);
@@ -64,6 +66,11 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, i
     // wgrad: the narrow [batch, <= 304] operand, split + transposed per call (hi then lo)
     w.asplit_half = pad64(304 * pad8(B > BL ? B : BL));
     w.asplit = take(B >= kSplitMinBatch && split_elems > 0 ? w.asplit_half : 0);
+    const int64_t Bi = infomax ? B : 0;
+    w.dx = take(Bi * H); w.dh1j = take(Bi * H); w.dh1m = take(Bi * H); w.dh2j = take(Bi * H); w.dh2m = take(Bi * H);
+    w.dj = take(Bi); w.dm = take(Bi); w.dgj = take(Bi); w.dgm = take(Bi);
+    w.dg2 = take(Bi * H); w.dg1j = take(Bi * H); w.dg1m = take(Bi * H);
+    w.deps_perm = take(Bi * d); w.dtj = take(Bi * d); w.dtm = take(Bi * d); w.dgeps = take(Bi * d);
     w.total = o;
     return w;
 }
@@ -405,7 +412,169 @@ extern "C" int cdg_pendulum_profile_read(cdg_pendulum_plan* p, double* out_ms) {
 
 extern "C" int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l) {
     if (!p || batch < 0 || batch_l < 0) return -1;
-    return pend_layout(p->c, batch, batch_l, p->split_elems).total * 4;
+    return pend_layout(p->c, batch, batch_l, p->split_elems, false).total * 4;
+}
+
+namespace cdg {
+
+// ---- InfoMax discriminator block (modules/model.py:191-206, modules/train.py:113-142) ------------------------------
+enum { ACC_MI_J = ACC_LEN, ACC_MI_M = ACC_LEN + 1 };
+
+// h1 = ELU(hx + z @ Wz^T + b): the x part of the first Linear is shared by the joint and the marginal pass
+__global__ void __launch_bounds__(256) disc_l1_kernel(const float* __restrict__ hx, const float* __restrict__ z, int d,
+                                                      const float* __restrict__ Wz, int64_t ldw, const float* __restrict__ b,
+                                                      float* __restrict__ out, int64_t B, int H) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * H; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / H;
+        const int n = (int)(i - r * H);
+        float s = hx[i] + b[n];
+        for (int k = 0; k < d; ++k) s = fmaf(z[r * d + k], Wz[n * ldw + k], s);
+        out[i] = s > 0.f ? s : expf(s) - 1.f;
+    }
+}
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ perm, float* __restrict__ dst, int64_t B,
+                                   int d) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * d; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[perm[i / d] * d + (i % d)];
+}
+// MI = -(mean dj - mean exp(dm - 1));  g_dj = -c / B,  g_dm = c * exp(dm - 1) / B  with c = gamma + 1 (train.py:139-140)
+__global__ void __launch_bounds__(256) disc_mi_kernel(const float* __restrict__ dj, const float* __restrict__ dm, float* __restrict__ gj,
+                                                      float* __restrict__ gm, int64_t B, float c, double* acc) {
+    __shared__ double red[32];
+    double sj = 0.0, sm = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const float e = expf(dm[i] - 1.f);
+        sj += (double)dj[i];
+        sm += (double)e;
+        gj[i] = -c / (float)B;
+        gm[i] = c * e / (float)B;
+    }
+    double t = block_sum<double>(sj, red);
+    if (threadIdx.x == 0) atomicAdd(acc + ACC_MI_J, t);
+    t = block_sum<double>(sm, red);
+    if (threadIdx.x == 0) atomicAdd(acc + ACC_MI_M, t);
+}
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+// g_eps[b] = tj[b];  g_eps[perm[i]] += tm[i]   (perm is a permutation: no write conflicts across threads of pass 2)
+__global__ void scatter_perm_kernel(const float* __restrict__ tj, const float* __restrict__ tm, const int64_t* __restrict__ perm,
+                                    float* __restrict__ out, int64_t B, int d, int pass) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * d; i += (int64_t)gridDim.x * blockDim.x) {
+        if (pass == 0) out[i] = tj[i];
+        else out[perm[i / d] * d + (i % d)] += tm[i];
+    }
+}
+__global__ void infomax_logs_kernel(double* acc, float* logs, int d, float B, float beta, float lambda_, float gamma) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float recon = (float)(acc[ACC_RECON] / (double)B), kl = (float)(acc[ACC_KL] / (double)B);
+        const float al = (float)(acc[ACC_ALIGN] / (double)B);
+        const float mi = -((float)(acc[ACC_MI_J] / (double)B) - (float)(acc[ACC_MI_M] / (double)B));
+        float loss = recon + beta * kl;                                  // train.py:131-133
+        loss += lambda_ * al;
+        loss += gamma * mi;
+        logs[0] = loss; logs[1] = recon; logs[2] = kl; logs[3] = al; logs[4] = mi;
+        for (int i = 0; i < d; ++i) logs[5 + i] = (float)(acc[ACC_VAR + i] / (double)B);
+        for (int i = 0; i < ACC_LEN + 2; ++i) acc[i] = 0.0;
+    }
+}
+
+static int ew_grid(int64_t n) { return (int)imin64((n + 255) / 256, kNumSMs * 16); }
+
+// Forward and backward of the discriminator on (x, eps) and (x, eps[perm]); leaves d MI-part / d eps in w.dgeps.
+static int infomax_block(const Ctx& c, const cdg_pendulum_io* io, int64_t B, double* acc) {
+    const cdg_pendulum_config& cf = c.p->c;
+    const int64_t H = cf.hidden, d = cf.node, P = cf.input_dim;
+    const cdg_linear* N = io->d_net;
+    CDG_REQUIRE(N[0].in == P + d && N[0].out == H && N[1].in == H && N[1].out == H && N[2].in == H && N[2].out == 1,
+                "discriminator shape mismatch");
+    CDG_REQUIRE(io->d_grads && io->perm, "InfoMax: d_grads / perm missing");
+    const float* DP = io->d_params;
+    float* DG = io->d_grads;
+    float* W = c.W;
+    cudaStream_t s = c.s;
+    const int64_t ldw = P + d;
+    const float* eps = W + c.w.eps;
+    float *hx = W + c.w.dx, *h1j = W + c.w.dh1j, *h1m = W + c.w.dh1m, *h2j = W + c.w.dh2j, *h2m = W + c.w.dh2m;
+    float *dj = W + c.w.dj, *dm = W + c.w.dm, *gj = W + c.w.dgj, *gm = W + c.w.dgm;
+    float *g2 = W + c.w.dg2, *g1j = W + c.w.dg1j, *g1m = W + c.w.dg1m, *epsp = W + c.w.deps_perm;
+    auto gemm = [&](GemmDesc& g) { return gemm_dispatch(c.mode == CDG_GEMM_BF3X ? CDG_GEMM_AUTO : c.mode, g, W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, s); };
+    CDG_CHECK_CUDA(cudaMemsetAsync(DG, 0, sizeof(float) * io->d_n_params, s));          // optimizer_D.zero_grad()
+    c.mark(PROF_GEMM_OTHER);
+    // ---- forward ----
+    {   // hx = x @ W1[:, :P]^T
+        GemmDesc g;
+        g.A = io->x; g.sa_m = P; g.sa_k = 1; g.B = DP + N[0].w; g.sb_n = ldw; g.sb_k = 1;
+        g.C = hx; g.ldc = H; g.M = B; g.N = H; g.K = P;
+        CDG_TRY(gemm(g));
+    }
+    gather_rows_kernel<<<ew_grid(B * d), 256, 0, s>>>(eps, io->perm, epsp, B, (int)d);
+    CDG_CHECK_LAUNCH();
+    disc_l1_kernel<<<ew_grid(B * H), 256, 0, s>>>(hx, eps, (int)d, DP + N[0].w + P, ldw, DP + N[0].b, h1j, B, (int)H);
+    CDG_CHECK_LAUNCH();
+    disc_l1_kernel<<<ew_grid(B * H), 256, 0, s>>>(hx, epsp, (int)d, DP + N[0].w + P, ldw, DP + N[0].b, h1m, B, (int)H);
+    CDG_CHECK_LAUNCH();
+    auto lin = [&](const float* X, int64_t K, const cdg_linear& L, float* Y, bool act) {
+        GemmDesc g;
+        g.A = X; g.sa_m = K; g.sa_k = 1; g.B = DP + L.w; g.sb_n = L.in; g.sb_k = 1;
+        g.C = Y; g.ldc = L.out; g.M = B; g.N = L.out; g.K = L.in;
+        g.epi = act ? EPI_BIAS_ACT : EPI_BIAS; g.act = CDG_ACT_ELU; g.bias = DP + L.b;
+        return gemm(g);
+    };
+    CDG_TRY(lin(h1j, H, N[1], h2j, true));
+    CDG_TRY(lin(h1m, H, N[1], h2m, true));
+    CDG_TRY(lin(h2j, H, N[2], dj, false));
+    CDG_TRY(lin(h2m, H, N[2], dm, false));
+    disc_mi_kernel<<<ew_grid(B), 256, 0, s>>>(dj, dm, gj, gm, B, io->gamma + 1.f, acc);
+    CDG_CHECK_LAUNCH();
+    // ---- backward ----
+    auto wgrad = [&](const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t w_off, int64_t ldc, int64_t rows, int64_t cols) {
+        GemmDesc g;                                                     // dW[rows, cols] += dY[B, rows]^T X[B, cols]
+        g.A = dY; g.sa_m = 1; g.sa_k = ldy; g.B = X; g.sb_n = 1; g.sb_k = ldx;
+        g.C = DG + w_off; g.ldc = ldc; g.M = rows; g.N = cols; g.K = B; g.accumulate = 1;
+        return gemm(g);
+    };
+    auto dgrad = [&](const float* dY, int64_t ldy, const float* Wm, int64_t ldwm, int64_t rows, int64_t cols, float* dX, const float* Hout) {
+        GemmDesc g;                                                     // dX[B, cols] = (dY[B, rows] W[rows, cols]) * ELU'(Hout)
+        g.A = dY; g.sa_m = ldy; g.sa_k = 1; g.B = Wm; g.sb_n = 1; g.sb_k = ldwm;
+        g.C = dX; g.ldc = cols; g.M = B; g.N = cols; g.K = rows;
+        if (Hout) { g.epi = EPI_MUL_DACT; g.act = CDG_ACT_ELU; g.aux = Hout; g.ld_aux = cols; }
+        return gemm(g);
+    };
+    // layer 3 (300 -> 1), joint then marginal; each pass continues down to layer 1's input gradient
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* gd = pass == 0 ? gj : gm;
+        const float* h2 = pass == 0 ? h2j : h2m;
+        const float* h1 = pass == 0 ? h1j : h1m;
+        float* g1 = pass == 0 ? g1j : g1m;
+        CDG_TRY(wgrad(gd, 1, h2, H, N[2].w, H, 1, H));
+        CDG_TRY(launch_colsum(gd, 1, B, 1, DG + N[2].b, s));
+        CDG_TRY(dgrad(gd, 1, DP + N[2].w, H, 1, H, g2, h2));
+        CDG_TRY(wgrad(g2, H, h1, H, N[1].w, H, H, H));
+        CDG_TRY(launch_colsum(g2, H, B, H, DG + N[1].b, s));
+        CDG_TRY(dgrad(g2, H, DP + N[1].w, H, H, H, g1, h1));
+        // layer 1, latent part: dWz += g1^T z; t = g1 @ Wz
+        CDG_TRY(wgrad(g1, H, pass == 0 ? eps : epsp, d, N[0].w + P, ldw, H, d));
+        CDG_TRY(dgrad(g1, H, DP + N[0].w + P, ldw, H, d, W + (pass == 0 ? c.w.dtj : c.w.dtm), nullptr));
+    }
+    // layer 1, image part: dWx += (g1j + g1m)^T x; db1 = colsum(g1j + g1m)
+    add2_kernel<<<ew_grid(B * H), 256, 0, s>>>(g1j, g1m, g2, B * H);
+    CDG_CHECK_LAUNCH();
+    CDG_TRY(wgrad(g2, H, io->x, P, N[0].w, ldw, H, P));
+    CDG_TRY(launch_colsum(g2, H, B, H, DG + N[0].b, s));
+    for (int pass = 0; pass < 2; ++pass) {
+        scatter_perm_kernel<<<ew_grid(B * d), 256, 0, s>>>(W + c.w.dtj, W + c.w.dtm, io->perm, W + c.w.dgeps, B, (int)d, pass);
+        CDG_CHECK_LAUNCH();
+    }
+    return CDG_OK;
+}
+
+}  // namespace cdg
+using namespace cdg;
+
+extern "C" int64_t cdg_pendulum_workspace_bytes_infomax(const cdg_pendulum_plan* p, int64_t batch) {
+    if (!p || batch < 0) return -1;
+    return pend_layout(p->c, batch, 0, p->split_elems, true).total * 4;
 }
 
 extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pendulum_io* io, void* stream) {
@@ -420,7 +589,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     c.p = p; c.P = io->params; c.G = io->grads; c.W = (float*)io->workspace; c.s = (cudaStream_t)stream;
     c.mode = cf.gemm_mode;
     c.prof = p->prof.enabled ? &p->prof : nullptr;
-    c.w = pend_layout(cf, B, BL, p->split_elems);
+    c.w = pend_layout(cf, B, BL, p->split_elems, io->d_params != nullptr);
     if (c.w.total * 4 > io->workspace_bytes) {
         set_error("workspace too small: need %lld bytes, got %lld", (long long)c.w.total * 4, (long long)io->workspace_bytes);
         return CDG_ERR_WORKSPACE;
@@ -434,7 +603,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     CDG_TRY(split_weights(c, B));
     // optimizer.zero_grad() (train.py:168) + loss accumulators
     CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * cf.n_params, s));
-    CDG_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_LEN, s));
+    CDG_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * (ACC_LEN + 2), s));
     if (!covers_all(cf)) CDG_CHECK_CUDA(cudaMemsetAsync(W + c.w.pre, 0, sizeof(float) * B * Pd, s));
 
     // ---- forward ----
@@ -474,6 +643,12 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         CDG_TRY(launch_recon(W + c.w.pre, io->x, io->xhat, B, Pd, acc, 1, s));
     }
 
+    const bool infomax = io->d_params != nullptr;
+    if (infomax) {
+        CDG_REQUIRE(!semi, "InfoMax has no semi-supervised variant");
+        CDG_TRY(infomax_block(c, io, B, acc));
+    }
+
     // ---- backward ----
     float* ga2 = W + c.w.ga2;
     float* ga1 = W + c.w.ga1;
@@ -508,6 +683,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     fill_latent(cf, lb);
     lb.batch = B; lb.params = io->params; lb.grads = io->grads; lb.ml = W + c.w.ml; lb.noise = io->noise;
     lb.u_in = W + c.w.u; lb.g_z = g_z; lb.g_align = semi ? nullptr : W + c.w.g_align; lb.g_out = W + c.w.g_ml;
+    lb.g_eps = infomax ? W + c.w.dgeps : nullptr;
     c.mark(PROF_LATENT);
     CDG_TRY(launch_latent_bwd(lb, s));
     CDG_TRY(encoder_bwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.g_ml, W + c.w.g_h2, W + c.w.g_h1));
@@ -515,7 +691,12 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         CDG_TRY(encoder_bwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.g_align, W + c.w.g_h2l, W + c.w.g_h1l));
 
     c.mark(PROF_MISC);
-    CDG_TRY(launch_finalize_logs(acc, io->logs, (int)d, (float)B, (float)B, (float)(semi ? BL : B), cf.beta, cf.lambda_, s));
+    if (infomax) {
+        infomax_logs_kernel<<<1, 32, 0, s>>>(acc, io->logs, (int)d, (float)B, cf.beta, cf.lambda_, io->gamma);
+        CDG_CHECK_LAUNCH();
+    } else {
+        CDG_TRY(launch_finalize_logs(acc, io->logs, (int)d, (float)B, (float)B, (float)(semi ? BL : B), cf.beta, cf.lambda_, s));
+    }
     c.mark(-1);
     return CDG_OK;
 }

@@ -232,7 +232,8 @@ class CDGVAE(ArenaModule):
         return torch.randn(batch, self.config["node"])              # CPU draw, as model.py:276
 
     # -- training entry (used by modules/train.py) -------------------------------------------------
-    def forward_backward(self, x, y, noise, logs_row, x_l=None, y_l=None, xhat=None):
+    def forward_backward(self, x, y, noise, logs_row, x_l=None, y_l=None, xhat=None, infomax=None):
+        """`infomax` = (discriminator, perm, gamma) runs the InfoMax discriminator inside the same step (train.py:113-142)."""
         dev = self.arena_device
         plan = self._get_plan()
         x = _f32c(x, dev).reshape(x.shape[0], -1)
@@ -250,7 +251,17 @@ class CDGVAE(ArenaModule):
             y = _f32c(y, dev)
             io.y, io.ld_y = _ptr(y), y.shape[1]
             keep.append(y)
-        nbytes = _lib.lib().cdg_pendulum_workspace_bytes(plan, Bn, 0 if x_l is None else x_l.shape[0])
+        if infomax is not None:
+            disc, perm, gamma = infomax
+            perm = perm.to(device=dev, dtype=torch.int64).contiguous()
+            io.d_params, io.d_grads, io.d_n_params = _ptr(disc._arena), _ptr(disc._grads), disc._n_params
+            for j, idx in enumerate((0, 2, 4)):
+                io.d_net[j] = disc._lin(f"net.{idx}")
+            io.perm, io.gamma = _ptr(perm), float(gamma)
+            keep.append(perm)
+            nbytes = _lib.lib().cdg_pendulum_workspace_bytes_infomax(plan, Bn)
+        else:
+            nbytes = _lib.lib().cdg_pendulum_workspace_bytes(plan, Bn, 0 if x_l is None else x_l.shape[0])
         ws = self._get_workspace(nbytes)
         io.workspace, io.workspace_bytes = _ptr(ws), ws.numel()
         io.x, io.noise, io.batch = _ptr(x), _ptr(noise), Bn
@@ -407,3 +418,21 @@ class VAE(CDGVAE):
                               want=("mean", "logvar", "epsilon", "orig_latent", "latent", "align_latent", "xhat"))
         return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
                 self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]), o["xhat"].view(-1, s, s, 3))
+
+
+class Discriminator(ArenaModule):
+    """modules/model.py:191-206: the InfoMax critic on (x, z), Linear(P + node, 300)-ELU-Linear(300, 300)-ELU-Linear(300, 1).
+    Inside train_InfoMax it is evaluated by the fused step (cdg_pendulum_forward_backward with d_params); `forward` here is
+    the stand-alone evaluation on the parameter views."""
+
+    def __init__(self, config, device="cpu"):
+        super().__init__()
+        self.config = config
+        P = 3 * config["image_size"] * config["image_size"]
+        self.net = nn.Sequential(nn.Linear(P + config["node"], 300), nn.ELU(), nn.Linear(300, 300), nn.ELU(),
+                                 nn.Linear(300, 1)).to(device)
+        self._build_arena()
+
+    def forward(self, x, z):
+        x = x.view(-1, 3 * self.config["image_size"] * self.config["image_size"])
+        return self.net(torch.cat((x, z), dim=1))

@@ -108,6 +108,42 @@ def train_VAE(dataloader, model, config, optimizer, device):
     return train_CDGVAE(dataloader, model, config, optimizer, device)
 
 
+def train_InfoMax(dataloader, model, discriminator, config, optimizer, optimizer_D, device):
+    """modules/train.py:71-148: the VAE step plus the mutual-information critic; logs gain 'MutualInfo'.  Both backward
+    passes of the reference (`loss.backward(retain_graph=True); MI.backward()`) and both optimizer steps happen here."""
+    _sync_config(model, config)
+    model.bind_optimizer(optimizer)
+    discriminator.bind_optimizer(optimizer_D)
+    keys = ["loss", "recon", "KL", "alignment", "MutualInfo"] + [f"posterior_variance{i + 1}" for i in range(config["node"])]
+    s = config["image_size"] if "image_size" in config else model.config["image_size"]
+    perm_fn = getattr(model, "perm_fn", None)
+    xhat, n = None, 0
+    for (x_batch, y_batch), last in _lookahead(dataloader):
+        rows = model._log_rows(n + 1, len(keys))
+        noise = model._noise(x_batch.shape[0])
+        perm = perm_fn(x_batch.shape[0]) if perm_fn else torch.randperm(x_batch.shape[0])      # train.py:75 (CPU draw)
+        if last:
+            xhat = torch.empty(x_batch.shape[0], 3 * s * s, device=model.arena_device)
+        model.forward_backward(x_batch, y_batch, noise, rows[n], xhat=xhat if last else None,
+                               infomax=(discriminator, perm, config["gamma"]))
+        scale = model.exchange_gradients()
+        discriminator.exchange_gradients()
+        model.adam_step(grad_scale=scale)
+        discriminator.adam_step(grad_scale=scale)
+        n += 1
+    logs = {k: [] for k in keys}
+    if n:
+        rows_ = model._logs[:n]
+        if _dist.world() > 1:
+            rows_ = _dist.allreduce_mean_(rows_.clone())
+        host = rows_.cpu()
+        for j, k in enumerate(keys):
+            logs[k] = host[:, j].tolist()
+    model._grad_views()
+    discriminator._grad_views()
+    return logs, (None if xhat is None else xhat.view(-1, s, s, 3))
+
+
 def _resident_loader(model, dataset, batch_size):
     """The reference builds `DataLoader(dataset, batch_size, shuffle=True)` on every call (train.py:222-223) and pays
     per-item float64->float32 conversion + collate + a pageable H2D copy per batch.  Datasets that expose their arrays

@@ -102,6 +102,8 @@ int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_plan** out)
 void cdg_pendulum_destroy(cdg_pendulum_plan* p);
 /* Workspace the caller must provide for a step on `batch` (+ `batch_l` labeled) samples. */
 int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l);
+/* ... for a step that also runs the InfoMax discriminator (io->d_params != NULL). */
+int64_t cdg_pendulum_workspace_bytes_infomax(const cdg_pendulum_plan* p, int64_t batch);
 
 typedef struct {
     const float* params;     /* parameter arena                                               */
@@ -120,6 +122,16 @@ typedef struct {
     float* logs;             /* [4 + d]: loss, recon, KL, alignment, posterior_variance1..d   */
     float* xhat;             /* optional [batch, P] reconstruction output (train.py:209), or NULL */
     const float* masks;      /* [K, P] decoder masks on the device; required when general_mask = 1 */
+    /* InfoMax baseline (modules/model.py:191-206 Discriminator; modules/train.py:71-148 train_InfoMax), when d_params != NULL:
+     * a discriminator Linear(P+d,300)-ELU-Linear(300,300)-ELU-Linear(300,1) on (x, epsilon) and on (x, epsilon[perm]);
+     * MI = -(mean D_joint - mean exp(D_marginal - 1)); loss += gamma * MI; gradients of loss + MI (train.py:139-140) land
+     * in `grads` (model) and `d_grads` (discriminator); logs become [loss, recon, KL, alignment, MutualInfo, variances]. */
+    const float* d_params;   /* discriminator arena                                            */
+    float* d_grads;
+    cdg_linear d_net[3];     /* net.{0,2,4} offsets in that arena                              */
+    int64_t d_n_params;
+    const int64_t* perm;     /* [batch] row permutation (torch.randperm, train.py:75)          */
+    float gamma;
 } cdg_pendulum_io;
 
 /* zero_grad + forward + losses + backward of one batch: train.py:168-202 (:235-278 when x_l != NULL).

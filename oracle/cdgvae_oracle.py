@@ -353,6 +353,59 @@ def train_step(params: Dict[str, Tensor], adam: Dict[str, dict], spec: Spec, A: 
 
 
 # --------------------------------------------------------------------------------------
+# InfoMax baseline (main.py --model InfoMax): VAE + a discriminator on (x, epsilon)
+# --------------------------------------------------------------------------------------
+def init_discriminator(config: dict, hidden: int = 300) -> Dict[str, Tensor]:
+    """Discriminator.__init__, modules/model.py:191-201: Linear(P + node, 300)-ELU-Linear(300, 300)-ELU-Linear(300, 1),
+    created right after the VAE under the same RNG stream (main.py:155-157); nn.Linear supplies the init law."""
+    import torch.nn as nn
+    dims = [3 * config["image_size"] ** 2 + config["node"], hidden, hidden, 1]
+    sd = {}
+    for j, (i, o) in zip((0, 2, 4), zip(dims[:-1], dims[1:])):
+        lin = nn.Linear(i, o)
+        sd[f"net.{j}.weight"], sd[f"net.{j}.bias"] = lin.weight.detach().clone(), lin.bias.detach().clone()
+    return sd
+
+
+def discriminator(dparams, x: Tensor, z: Tensor) -> Tensor:
+    """Discriminator.forward, modules/model.py:203-206."""
+    h = torch.cat((x.reshape(x.shape[0], -1), z), dim=1)
+    return mlp(dparams, "net", [0, 2, 4], h, "elu")
+
+
+def infomax_train_step(params, dparams, adam, adam_d, spec: Spec, A: Tensor, x: Tensor, y: Tensor, noise: Tensor, perm: Tensor,
+                       gamma: float, lr_d: float):
+    """One batch of train_InfoMax, modules/train.py:71-148.  `loss.backward(retain_graph=True); MI.backward()` accumulates
+    d loss + d MI into every .grad (train.py:139-140), i.e. the gradient of recon + beta KL + lambda align + (gamma + 1) MI;
+    both optimizers then step (train.py:141-142)."""
+    leaves = {k: v.detach().requires_grad_(True) for k, v in params.items()}
+    dleaves = {k: v.detach().requires_grad_(True) for k, v in dparams.items()}
+    out = forward(leaves, spec, A, x, noise)
+    recon = recon_term(leaves, spec, out["xhat"], x)
+    kl = kl_term(out["mean"], out["logvar"], spec.node)
+    align = align_term(out["align_latent"], y[:, : spec.node])
+    d_joint = discriminator(dleaves, x, out["epsilon"])
+    d_marg = discriminator(dleaves, x, out["epsilon"][perm])            # permute_dims, train.py:73-77
+    mi = -(d_joint.mean() - torch.exp(d_marg - 1).mean())
+    loss = recon + spec.beta * kl + spec.lam * align + gamma * mi
+    names, dnames = list(leaves), list(dleaves)
+    gl = torch.autograd.grad(loss + mi, [leaves[n] for n in names] + [dleaves[n] for n in dnames])
+    grads = dict(zip(names, gl[: len(names)]))
+    dgrads = dict(zip(dnames, gl[len(names):]))
+    spec_d = Spec(**{**spec.__dict__, "lr": lr_d})
+    with torch.no_grad():
+        for n in names:
+            adam_update(params[n], grads[n], adam[n], spec)
+        for n in dnames:
+            adam_update(dparams[n], dgrads[n], adam_d[n], spec_d)
+    logs = {"loss": loss, "recon": recon, "KL": kl, "alignment": align, "MutualInfo": mi}
+    var_ = out["logvar"].exp().mean(0)
+    for i in range(spec.node):
+        logs[f"posterior_variance{i + 1}"] = var_[i]
+    return {k: float(v.detach()) for k, v in logs.items()}, grads, dgrads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic inputs of SURVEY.md §8(d) (shared by goldens, tests, bench and smoke)
 # --------------------------------------------------------------------------------------
 def pendulum_B(node: int = 4) -> Tensor:

@@ -233,6 +233,61 @@ def dr_case(name, scm, image_size, bands, batch, nsteps):
     return case
 
 
+def infomax_case(name, image_size, batch, nsteps):
+    """main.py --model InfoMax: VAE + Discriminator, train_InfoMax (modules/train.py:71-148).  torch.randperm is replaced
+    for the duration of the reference call so that permute_dims uses a pre-generated permutation."""
+    config = dict(node=4, scm="linear", flow_num=1, inverse_loop=100, image_size=image_size, batch_size=batch, lr=1e-3,
+                  lr_D=1e-4, beta=0.1, gamma=1.0, cuda=False, seed=1)
+    config["lambda"] = 5.0
+    Bm = orc.pendulum_B(4)
+    torch.manual_seed(config["seed"])
+    model = pm.VAE(Bm, config, "cpu")
+    disc = pm.Discriminator(config, "cpu")
+    model.train(); disc.train()
+    opt = torch.optim.Adam(model.parameters(), lr=config["lr"])
+    opt_d = torch.optim.Adam(disc.parameters(), lr=config["lr_D"])
+    spec = orc.vae_spec(config)
+    A = orc.i_b_inv(Bm)
+    torch.manual_seed(config["seed"])
+    params = orc.init_params(spec, config["seed"])
+    dparams = orc.init_discriminator(config)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, params[k]), k
+    for k, v in disc.state_dict().items():
+        assert torch.equal(v, dparams[k]), k
+    adam, adam_d = orc.new_adam_state(params), orc.new_adam_state(dparams)
+    case = {"name": name, "family": "infomax", "config": {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
+            "I_B_inv": A.tolist(), "init": summarize_dict(params), "init_d": summarize_dict(dparams), "steps": []}
+    worst = 0.0
+    for s in range(nsteps):
+        x, y, noise = orc.synth_pendulum(batch, image_size, 4, seed=1234 + s, noise_seed=4321 + s)
+        perm = torch.randperm(batch, generator=torch.Generator().manual_seed(99 + s))
+        orig_perm = torch.randperm
+        torch.randperm = lambda n, **kw: perm.clone()
+        try:
+            with NoiseInjector([noise]):
+                logs, xhat = pt.train_InfoMax([(x, y)], model, disc, config, opt, opt_d, "cpu")
+        finally:
+            torch.randperm = orig_perm
+        entry = {"perm": perm.tolist(), "logs": {k: float(v[0]) for k, v in logs.items()}}
+        ol, og, odg, _ = orc.infomax_train_step(params, dparams, adam, adam_d, spec, A, x, y, noise, perm, config["gamma"], config["lr_D"])
+        for k, v in entry["logs"].items():
+            d = abs(ol[k] - v) / (abs(v) + 1e-12)
+            worst = max(worst, d)
+            assert d < (2e-6 if s == 0 else 1e-4), (name, s, k, ol[k], v)
+        for n, p in model.named_parameters():
+            assert rel(og[n], p.grad) < (1e-5 if s == 0 else 1e-3), (name, s, n)
+        for n, p in disc.named_parameters():
+            assert rel(odg[n], p.grad) < (1e-5 if s == 0 else 1e-3), (name, s, "D", n)
+        if s == 0:
+            entry["grads"] = summarize_dict({n: p.grad for n, p in model.named_parameters()})
+            entry["grads_d"] = summarize_dict({n: p.grad for n, p in disc.named_parameters()})
+        entry["params_d"] = summarize_dict(disc.state_dict())
+        case["steps"].append(entry)
+    print(f"{name}: {nsteps} steps, oracle-vs-reference worst log rel diff {worst:.2e}")
+    return case
+
+
 def tabular_case(dataset, batch, nsteps):
     config = dict(dataset=dataset, scm="linear", flow_num=1, inverse_loop=100, batch_size=batch, lr=0.01,
                   beta=0.01, cuda=False, seed=1)
@@ -294,6 +349,12 @@ def tvae_case(kind, batch, nsteps):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "infomax":
+        c = infomax_case("infomax_small", 8, 16, 3)
+        with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
+            json.dump(c, f)
+        print("wrote", c["name"])
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "dr":
         c = dr_case("dr_small_linear", "linear", 8, (3, 6), 16, 4)
         with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
