@@ -143,11 +143,15 @@ struct GemmDesc {
     const void* a_hi16 = nullptr;
     const void* a_lo16 = nullptr;
     int64_t ld_a16 = 0;
+    // Tensor-core kernel, no operand swap: the LAST column n = N-1 of the result goes to extra_col[m] instead of C[m, N-1].
+    // A weight-gradient GEMM whose pre-split B carries a row of ones there yields the bias gradient (the column sum of dY)
+    // for free, instead of a separate pass over dY.
+    float* extra_col = nullptr;
 };
 
 // W[rows, cols] (row stride ld) -> hi / lo bf16 copies; transpose != 0 writes them as [cols][rows] (row stride ld16 either way)
 int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
-                      cudaStream_t s);
+                      cudaStream_t s, int ones_row = 0);   // ones_row (transposed only): append output row `cols` = 1.0
 
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
 int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG_ERR_UNSUPPORTED otherwise

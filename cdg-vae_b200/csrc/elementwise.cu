@@ -159,7 +159,7 @@ int launch_scatter_add_cols(const float* gzin, float* gz, int d, int f, int off,
 // ---- weight pre-split for the bf16x3 GEMM: W = bf16 hi + bf16 lo, optionally transposed ------------------------------
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ W, int64_t rows, int64_t cols, int64_t ld,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld16,
-                                                         int transpose) {
+                                                         int transpose, int ones_row) {
     __shared__ float tile[32][33];
     if (!transpose) {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += (int64_t)gridDim.x * blockDim.x) {
@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
         }
         return;
     }
+    if (ones_row)       // output row `cols`: the constant 1 (hi = 1, lo = 0) over the `rows` contraction entries
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+            hi[cols * ld16 + i] = __float2bfloat16_rn(1.f);
+            lo[cols * ld16 + i] = __float2bfloat16_rn(0.f);
+        }
     // transposed copy through a 32x32 shared-memory tile (coalesced on both sides)
     const int64_t tr = (rows + 31) / 32, tc = (cols + 31) / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -194,11 +199,11 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     }
 }
 int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
-                      cudaStream_t s) {
+                      cudaStream_t s, int ones_row) {
     if (rows * cols == 0) return CDG_OK;
     const int64_t work = transpose ? ((rows + 31) / 32) * ((cols + 31) / 32) : (rows * cols + 255) / 256;
     split_bf16_kernel<<<(int)imin64(work, kNumSMs * 16), 256, 0, s>>>(W, rows, cols, ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld16,
-                                                                   transpose);
+                                                                   transpose, transpose ? ones_row : 0);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }

@@ -64,6 +64,7 @@ struct Params {
     int probe;                                  // timing experiments only (results invalid): 1 = no conversion, 2 = no TMA
     int rawhi;                                  // K-major operands: leave the raw tile as `hi` (tensor core truncates)
     int64_t work_total;                         // tiles_m * tiles_n * splits
+    float* extra;                               // column N-1 of the result goes to extra[m] (bias gradient via a ones row)
     int b_pre;                                  // bf16x3: B arrives pre-split (hi / lo bf16 tiles by TMA, no conversion)
     int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
@@ -734,7 +735,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 fetch(c0 + 48, r2);
                 const int64_t n0 = (int64_t)n_blk * BN + c0;
                 if (!row_ok || n0 >= p.N) continue;
-                if (p.vec && !p.atomic && n0 + 16 <= p.N) {
+                if (p.vec && !p.atomic && n0 + 16 <= p.N && !(p.extra && n0 + 16 >= p.N)) {
                     float* crow = p.C + m * p.sc_m + n0;
                     if (p.epi == EPI_RECON) {
                         float* xh = p.rxhat ? p.rxhat + m * p.sc_m + n0 : nullptr;
@@ -810,6 +811,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int64_t n = n0 + e;
                         if (n < p.N) {
                             float* cptr = p.C + m * p.sc_m + n * p.sc_n;
+                            if (p.extra && n == p.N - 1) cptr = p.extra + m;
                             if (p.atomic) {
                                 atomicAdd(cptr, v[e]);
                             } else if (p.epi == EPI_RECON) {
@@ -1010,6 +1012,7 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
         bias_on_m = 1;
     }
     if (g.a_hi16) return CDG_ERR_UNSUPPORTED;       // a pre-split A is only usable once swapped into the B slot
+    if (g.extra_col && (bias_on_m || g.epi != EPI_NONE)) return CDG_ERR_UNSUPPORTED;   // plain (accumulating) results only
     if (g.N < 16 && g.conv_C == 0) return CDG_ERR_UNSUPPORTED;   // (conv mode: a 3-channel toRGB still beats im2col + rowdot)
     bool a_mn, b_mn;
     if (g.conv_C > 0) a_mn = false;
@@ -1087,6 +1090,7 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     p.rx = g.recon_x; p.rx_ld = g.ld_x; p.rxhat = g.recon_xhat; p.racc = g.recon_acc; p.inv_batch = g.inv_batch;
     p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per;
     p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
+    p.extra = g.extra_col;
     p.conv_cb = g.conv_C > 0 ? g.conv_C / BK : 0; p.conv_W = g.conv_W; p.conv_H = g.conv_H; p.conv_k = g.conv_k;
     {
         static int rawhi = -1;

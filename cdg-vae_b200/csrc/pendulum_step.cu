@@ -174,10 +174,14 @@ static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float*
         uint16_t* hi = reinterpret_cast<uint16_t*>(c.W + c.w.asplit);
         uint16_t* lo = hi + c.w.asplit_half;
         const int64_t ld16 = pad8(M);
-        if (L.in <= 304) {
-            CDG_TRY(launch_split_bf16(X, M, L.in, ldx, hi, lo, ld16, 1, c.s));
+        if (L.in < 304) {
+            // B = X^T with a row of ones appended: column L.in of the product is colsum(dY) = the bias gradient
+            CDG_TRY(launch_split_bf16(X, M, L.in, ldx, hi, lo, ld16, 1, c.s, 1));
             g.b_hi16 = hi; g.b_lo16 = lo; g.ld_b16 = ld16;
+            g.N = L.in + 1; g.extra_col = c.G + L.b + row_lo;
             r = gemm_tc(g, 2, nullptr, 0, c.s);
+            g.N = L.in; g.extra_col = nullptr;
+            if (r == CDG_OK) return CDG_OK;                 // bias gradient included
         } else if (n_rows <= 304) {
             CDG_TRY(launch_split_bf16(dY, M, n_rows, ldy, hi, lo, ld16, 1, c.s));
             g.a_hi16 = hi; g.a_lo16 = lo; g.ld_a16 = ld16;
