@@ -546,3 +546,36 @@ def test_bf16x3_presplit_path_matches_oracle(scm, semi):
         assert rel(p.grad, og[n]) < RTOL, (n, rel(p.grad, og[n]))
     if flows_m:
         assert rel(torch.cat(flows_m), torch.cat(flows_o)) < RTOL
+
+
+def test_cuda_graph_replay_of_presplit_path_matches_eager():
+    """Batches of 2,048 .. 4,096 rows are both graph-replayed (engine.GRAPH_MAX_ROWS) and on the bf16x3 pre-split path:
+    weight splits, transposed operand splits and the TMA-map construction must all be capturable."""
+    from cdgvae_b200.modules.model import CDGVAE
+    from cdgvae_b200.modules import train as T
+    B = 2048
+    cfg = dict(node=4, scm="nonlinear", flow_num=1, inverse_loop=100, factor=[1, 1, 2], image_size=16, batch_size=B,
+               lr=1e-3, beta=0.1, seed=1)
+    cfg["lambda"] = 5.0
+    data, noises = [], []
+    for i in range(4):
+        x, y, nz = orc.synth_pendulum(B, 16, 4, 700 + i, 800 + i)
+        data.append((x.cuda(), y.cuda()))
+        noises.append(nz.cuda())
+    res = []
+    for graphs in (False, True):
+        torch.manual_seed(1)
+        model = CDGVAE(orc.pendulum_B(4), orc.pendulum_masks(16, (5, 11)), cfg, "cpu").to("cuda")
+        opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+        model.use_graphs = graphs
+        q = list(noises)
+        model.noise_fn = lambda n, d: q.pop(0)
+        logs, xhat = T.train_CDGVAE(data, model, cfg, opt, "cuda")
+        if graphs:
+            assert any(isinstance(v, tuple) for v in model._graphs.values()), "no graph was captured"
+        res.append((logs, xhat.clone(), model._arena.clone()))
+    for k in res[0][0]:
+        for a, b in zip(res[0][0][k], res[1][0][k]):
+            assert abs(a - b) <= 5e-5 * abs(a) + 1e-7, (k, a, b)
+    assert rel(res[0][1], res[1][1]) < 1e-4
+    assert rel(res[0][2], res[1][2]) < 1e-4
