@@ -198,6 +198,8 @@ static int prep_conv(Cx& cx, const cdg_conv& cv, bool need_wd, PConv* p) {
         p->d16.lo = cx.ws.take<uint16_t>((int64_t)cv.cin * p->d16.ld);
     }
     if (cx.dry) return CDG_OK;
+    const bool want16 = cx.mode == CDG_GEMM_BF3X;            // the bf16 (hi, lo) copies only feed the opt-in bf16x3 path
+    if (!want16) { p->f16 = Split16(); p->d16 = Split16(); }
     CDG_TRY(launch_weight_prep(cx.frozen + cv.w, cv.cout, cv.cin, cv.k, p->inv_sigma, p->wf, p->Kpf, p->wd, p->Kpd, cx.s, p->f16,
                                need_wd ? p->d16 : Split16()));
     return CDG_OK;

@@ -145,9 +145,34 @@ int launch_lin0_prep(const float* w, const float* b, int C, int HW, int zd, cons
 }
 
 // ---- spectral normalisation ------------------------------------------------------------------------------
-// t = W^T u : block (32 columns x 8 row lanes)
+// t = W^T u.  Wide layers (cols >= 32): block = 32 columns x 8 row lanes.  Narrow layers (the generators' first Linear:
+// 8192 rows x 2..6 columns): one block, every thread strides over rows with one partial sum per column.
 __global__ void __launch_bounds__(256) sn_wt_u_kernel(SnBatch sb) {
     const SnLayer L = sb.l[blockIdx.y];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (L.cols <= 8) {
+        if (blockIdx.x != 0) return;
+        __shared__ float red8[32];
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < L.rows; i += 256) {
+            const float u = L.u[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < L.cols) acc[j] = fmaf(L.w[(int64_t)i * L.cols + j], u, acc[j]);
+        }
+        for (int j = 0; j < L.cols; ++j) {
+            float v = warp_sum(acc[j]);
+            __syncthreads();
+            if ((tid & 31) == 0) red8[tid >> 5] = v;
+            __syncthreads();
+            if (tid == 0) {
+                float s = 0.f;
+                for (int w = 0; w < 8; ++w) s += red8[w];
+                L.t[j] = s;
+            }
+        }
+        return;
+    }
     const int j = blockIdx.x * 32 + threadIdx.x;
     if (blockIdx.x * 32 >= L.cols) return;
     __shared__ float red[8][33];

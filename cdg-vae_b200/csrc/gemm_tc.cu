@@ -995,6 +995,11 @@ struct Plan {
     bool a_mn, b_mn;
 };
 
+static bool no160() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CDG_TC_NO160"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
 // shape / layout analysis shared by gemm_tc and gemm_tc_can
 static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     using namespace tc;
@@ -1026,7 +1031,7 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     else if (g.N <= 128) BN = 128;
     else if (g.N <= 160) BN = 160;
     else if (g.N <= 256) BN = 256;
-    else if (g.N <= 304) BN = (g.K <= 1024 && g.M >= 128 * 64) ? 160 : 304;   // short K: two 160-wide tiles with
+    else if (g.N <= 304) BN = (g.K <= 1024 && g.M >= 128 * 64 && !no160()) ? 160 : 304;   // short K: two 160-wide tiles with
     else BN = 256;                                                            // double-buffered accumulators
     const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
     if (tn > (1 << 30) || tm > (1 << 30)) return CDG_ERR_UNSUPPORTED;
