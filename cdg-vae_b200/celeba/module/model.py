@@ -221,6 +221,10 @@ class CDGVAE(ArenaModule):
 
     def _run(self, x=None, y=None, noise=None, backward=False, deterministic=False, encoder_passes=2, encode_only=False,
              latent_in=None, epsilon2_in=None, logs_row=None, want_xhat=False, want_sep=False, want_latents=False):
+        if latent_in is None and not self.encoder.training:
+            # the reference only ever runs this model in training mode (celeba/main.py:118); eval-mode BatchNorm in the
+            # encoder (running statistics instead of batch statistics) is not implemented in the kernels
+            raise NotImplementedError("the CelebA encoder is evaluated with batch statistics (model.train()); eval mode is not built")
         dev = self.arena_device
         plan = self._get_plan()
         d, S = self.config["node"], self.IMAGE_SIZE
