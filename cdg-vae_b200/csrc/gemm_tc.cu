@@ -38,6 +38,10 @@ namespace tc {
 constexpr int BM = 128;
 // K-block = one swizzle row: 32 floats (SWIZZLE_128B, 2-stage ring) or 16 floats (SWIZZLE_64B, 4-stage ring).
 // The ring holds the same bytes either way; the finer blocks keep more TMA loads in flight per byte.
+#ifndef CDG_TC_BF3X_A_TMEM
+#define CDG_TC_BF3X_A_TMEM 1
+#endif
+#define CDG_TC_A_TMEM_BF16_OK(bf3x) (!(bf3x) || CDG_TC_BF3X_A_TMEM)
 constexpr int NUM_CONV_WARPS = 8;
 #ifndef CDG_TC_CONV_GROUPS
 #define CDG_TC_CONV_GROUPS 2
@@ -65,6 +69,7 @@ struct Params {
     int rawhi;                                  // K-major operands: leave the raw tile as `hi` (tensor core truncates)
     int64_t work_total;                         // tiles_m * tiles_n * splits
     float* extra;                               // column N-1 of the result goes to extra[m] (bias gradient via a ones row)
+    int a16swap;                                // experiment switch: order of the two bf16 in a packed TMEM column
     int b_pre;                                  // bf16x3: B arrives pre-split (hi / lo bf16 tiles by TMA, no conversion)
     int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
@@ -133,6 +138,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
@@ -224,8 +237,11 @@ struct Cfg {
     // BK columns each per stage): the MMA then reads A from tensor memory, which removes A from the shared
     // memory data path -- the path ncu shows saturated (LSU + tensor wavefronts at 92 % of peak).
     static constexpr int A_COL0 = (NACC * BN + 31) / 32 * 32;
-    static constexpr bool A_TMEM = !BF3X && (A_COL0 + STAGES * 2 * BK <= 512);
-    static constexpr int TMEM_USED = (NACC * BN + 31) / 32 * 32 + (A_TMEM ? STAGES * 2 * BK : 0);
+    // bf16x3: hi and lo of the A tile as packed bf16 pairs, BK/2 columns each per stage (the converter then writes no shared
+    // memory at all and the UMMA reads only B from it: ncu showed the L1/shared pipe at 68-75 % with A in shared memory)
+    static constexpr int A_STAGE_COLS = BF3X ? BK : 2 * BK;
+    static constexpr bool A_TMEM = (A_COL0 + STAGES * A_STAGE_COLS <= 512) && CDG_TC_A_TMEM_BF16_OK(BF3X);
+    static constexpr int TMEM_USED = (NACC * BN + 31) / 32 * 32 + (A_TMEM ? STAGES * A_STAGE_COLS : 0);
     static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
@@ -360,6 +376,42 @@ __device__ __forceinline__ void bf16_split8(const float* v, uint4& hi, uint4& lo
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// A tile -> tensor memory as packed bf16 pairs (hi: columns [0, 16), lo: [16, 32) of the stage's slot).  Converter warp w owns
+// TMEM lane quarter w % 4 (one row per lane); the two warps of a quarter take 16 of the 32 K entries each.  Source: K-major
+// raw tile (SWIZZLE_128B) or MN-major raw box ([32 k][128 m]).  No shared-memory writes, no barrier.
+template <bool MN>
+__device__ __forceinline__ void bf3x_a_tmem(const uint8_t* raw, uint32_t tmem_slot, int warp, int lane, int swap_halves) {
+    const int q = warp & 3, khalf = (warp - 2) >> 2;
+    const uint32_t row = (uint32_t)(q * 32 + lane);
+    float v[16];
+    if (!MN) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(raw + sw_chunk<32>(row, (uint32_t)(khalf * 4 + c)));
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        }
+    } else {
+        const float* r = reinterpret_cast<const float*>(raw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = r[(khalf * 16 + j) * BM + row];
+    }
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+        const uint32_t a0 = __bfloat16_as_ushort(h0), a1 = __bfloat16_as_ushort(h1);
+        const uint32_t b0 = __bfloat16_as_ushort(l0), b1 = __bfloat16_as_ushort(l1);
+        h[i] = swap_halves ? (a1 | (a0 << 16)) : (a0 | (a1 << 16));
+        l[i] = swap_halves ? (b1 | (b0 << 16)) : (b0 | (b1 << 16));
+    }
+    const uint32_t base = tmem_slot + ((uint32_t)(q * 32) << 16) + (uint32_t)(khalf * 8);
+    tmem_st8(base, h);
+    tmem_st8(base + 16, l);
+    tmem_st_wait();
 }
 
 // K-major raw tile [ROWS][32 floats]: unit u = (row, 8-float group g) -> one 16-byte bf16 chunk of hi and of lo
@@ -598,8 +650,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int k = 0; k < 2; ++k) {
                                 const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
                                 const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                                umma_bf16(tacc, da + koff, db + koff, ib0, acc);
-                                if (C_::N1 > 0) umma_bf16(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                                if (C_::A_TMEM) {
+                                    const uint32_t ta = tmem_base + C_::A_COL0 + s * C_::A_STAGE_COLS + (pass == 0 ? 16 : 0) + k * 8;
+                                    umma_bf16_ts(tacc, ta, db + koff, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16_ts(tacc + C_::N0, ta, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                                } else {
+                                    umma_bf16(tacc, da + koff, db + koff, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                                }
                             }
                         }
                     } else {
@@ -659,7 +717,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // all converter warps share a stage (the in-place conversion needs every read done before any write)
                     constexpr int NTA = 32 * NUM_CONV_WARPS;
                     const int cta = threadIdx.x - 64;
-                    if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1);
+                    if (C_::A_TMEM) bf3x_a_tmem<A_MN>(a_hi(s), tmem_base + C_::A_COL0 + s * C_::A_STAGE_COLS, warp, lane, p.a16swap);
+                    else if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1);
                     else bf3x_mnmajor<BM, 128, NTA>(a_hi(s), cta, 1);
                     if (p.b_pre) {
                     } else if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2);
@@ -1096,6 +1155,11 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per;
     p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
     p.extra = g.extra_col;
+    {
+        static int sw = -1;
+        if (sw < 0) { const char* e = getenv("CDG_TC_A16SWAP"); sw = (e && atoi(e) != 0) ? 1 : 0; }
+        p.a16swap = sw;
+    }
     p.conv_cb = g.conv_C > 0 ? g.conv_C / BK : 0; p.conv_W = g.conv_W; p.conv_H = g.conv_H; p.conv_k = g.conv_k;
     {
         static int rawhi = -1;
