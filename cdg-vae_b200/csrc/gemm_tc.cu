@@ -71,6 +71,7 @@ struct Params {
     float* extra;                               // column N-1 of the result goes to extra[m] (bias gradient via a ones row)
     int a16swap;                                // experiment switch: order of the two bf16 in a packed TMEM column
     int b_pre;                                  // bf16x3: B arrives pre-split (hi / lo bf16 tiles by TMA, no conversion)
+    int sw32;                                   // bf16x3: bf16 tiles as two K = 16 sub-tiles of 32-byte rows (SWIZZLE_32B)
     int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
 
@@ -148,6 +149,51 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
 }
+// ---- CTA pairs (cta_group::2): one MMA of M = 256 spans both CTAs of a 2-CTA cluster; each CTA supplies its own 128 rows
+// of A (from its tensor memory or shared memory) and HALF of the B rows (from its shared memory), and receives its 128 rows
+// of the accumulator in its own tensor memory.  Only CTA rank 0 issues MMAs and commits (multicast to both CTAs' barriers).
+__device__ __forceinline__ void umma_bf16_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3) : "memory");
+}
+// one lane of a converged warp (the compiler then knows a single thread issues the tcgen05 instructions inside the branch and
+// feeds their uniform-register operands without a per-lane "waterfall" loop around every MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA rank 0 of the cluster
+__device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(bar));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");   // (.release.cluster costs a MEMBAR.ALL.GPU per arrive)
+}
+
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
@@ -189,6 +235,16 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
     d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;        // layout type SWIZZLE_128B (2) / SWIZZLE_64B (4)
     return d;
 }
+// bf16 K = 16 sub-tile: rows of 32 B (SWIZZLE_32B), 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_kmajor_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                         // layout type SWIZZLE_32B
+    return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -214,7 +270,11 @@ __device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
     return r * 64u + ((chunk ^ ((r >> 1) & 3u)) << 4);
 }
 
-template <int BN, int BK, int PASSES = 3>
+// Staged reconstruction epilogue (STG): every epilogue warp owns EPI_NIN target buffers and EPI_NOUT output buffers of
+// 32 rows x 32 floats (SWIZZLE_128B) moved by TMA, paid for with one ring stage.
+constexpr int EPI_NIN = 3, EPI_NOUT = 2, EPI_CHUNK_BYTES = 32 * 128;
+
+template <int BN, int BK, int PASSES = 3, bool STG = false, bool CTA2 = false>
 struct Cfg {
     // PASSES == 2 is the bf16x3 arithmetic (see the BF3X notes at the converter): the raw fp32 tile is converted IN PLACE
     // into a hi and a lo bf16 tile (a 128-byte fp32 row becomes two 64-byte bf16 rows), so a stage holds one copy of
@@ -222,12 +282,15 @@ struct Cfg {
     static constexpr bool BF3X = PASSES == 2;
     // (a 6-stage ring was tried for BN = 160 and changed nothing: the ring depth is not what limits the main loop)
     // narrow tiles (BN <= 64: the convolutions with 32 / 64 output channels) leave room for a 4-deep ring of 32-float blocks
-    static constexpr int STAGES = BF3X ? 4 : (BK == 32 ? (BN <= 64 ? 4 : 2) : 4);
+    static constexpr int STAGES = CTA2 ? 6 : BF3X ? (STG ? 3 : 4) : (BK == 32 ? (BN <= 64 ? 4 : 2) : 4);
+    static constexpr int EPI_BYTES = STG ? NUM_EPI_WARPS * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES : 0;
     static constexpr int ROW_BYTES = BK * 4;
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = BF3X ? (A_BYTES + B_BYTES) : 2 * (A_BYTES + B_BYTES);     // hi + lo for both operands
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int B_CTA_BYTES = CTA2 ? B_BYTES / 2 : B_BYTES;   // CTA pairs: each CTA stages half of the B rows
+    static constexpr int STAGE_BYTES = BF3X ? (A_BYTES + B_CTA_BYTES) : 2 * (A_BYTES + B_BYTES);  // hi + lo for both operands
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(!STG || (BF3X && BN % 32 == 0 && NUM_EPI_WARPS == 4), "staged epilogue: bf16x3 tiles, one warp per lane quarter");
     static constexpr int B_ROWS_PER_BOX = BN <= 256 ? BN : BN / 2;  // K-major TMA box rows (<= 256)
     static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4));   // MN-major chunk width (<= 128)
     static constexpr int N0 = BN <= 256 ? BN : 160;                 // first MMA's N
@@ -246,6 +309,8 @@ struct Cfg {
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
     static_assert(!BF3X || BK == 32, "bf16x3 tiles are built from 32-float K-blocks");
+    static_assert(!CTA2 || (BF3X && !STG), "CTA pairs: bf16x3 tiles");
+    static_assert(!CTA2 || (N0 % 16 == 0 && N1 % 16 == 0), "UMMA N is a multiple of 16 at M = 256; half-B boxes are whole 8-row groups");
 };
 
 // ---- converter --------------------------------------------------------------------------------
@@ -414,9 +479,20 @@ __device__ __forceinline__ void bf3x_a_tmem(const uint8_t* raw, uint32_t tmem_sl
     tmem_st_wait();
 }
 
+// Byte offset of the 16-byte chunk g (8 bf16: k = 8g .. 8g+7) of row r inside a bf16 tile of ROWS rows x 32 k.
+//   sw32 == 0: rows of 64 B, SWIZZLE_64B.  An MMA (K = 16) then reads half of every row: the 32-byte pieces of rows r and
+//              r + 2 fall on the same banks (the swizzle only permutes chunks inside the half), so every operand read costs
+//              two shared-memory wavefronts per useful one.
+//   sw32 != 0: two K = 16 sub-tiles of 32-byte rows, SWIZZLE_32B (address bit 4 ^= bit 7): 8 rows = 256 contiguous bytes.
+template <int ROWS>
+__device__ __forceinline__ uint32_t bf16_tile_off(uint32_t r, uint32_t g, int sw32) {
+    if (sw32) return (g >> 1) * (uint32_t)(ROWS * 32) + r * 32u + (((g & 1u) ^ ((r >> 2) & 1u)) << 4);
+    return sw_chunk<16>(r, g);
+}
+
 // K-major raw tile [ROWS][32 floats]: unit u = (row, 8-float group g) -> one 16-byte bf16 chunk of hi and of lo
 template <int ROWS, int NT>
-__device__ __forceinline__ void bf3x_kmajor(uint8_t* buf, int ct, int bar_id) {
+__device__ __forceinline__ void bf3x_kmajor(uint8_t* buf, int ct, int bar_id, int sw32) {
     constexpr int UNITS = ROWS * 4;
     constexpr int IT = (UNITS + NT - 1) / NT;
     float v[IT][8];
@@ -440,7 +516,7 @@ __device__ __forceinline__ void bf3x_kmajor(uint8_t* buf, int ct, int bar_id) {
             const uint32_t r = (uint32_t)(u >> 2), g = (uint32_t)(u & 3);
             uint4 hi, lo;
             bf16_split8(v[it], hi, lo);
-            const uint32_t off = sw_chunk<16>(r, g);
+            const uint32_t off = bf16_tile_off<ROWS>(r, g, sw32);
             *reinterpret_cast<uint4*>(buf + off) = hi;
             *reinterpret_cast<uint4*>(lo_tile + off) = lo;
         }
@@ -449,7 +525,7 @@ __device__ __forceinline__ void bf3x_kmajor(uint8_t* buf, int ct, int bar_id) {
 
 // MN-major raw boxes [32 k-rows][CW mn] (chunk c at byte c*CW*128): thread j owns mn column j, i.e. K-major row j
 template <int ROWS, int CW, int NT>
-__device__ __forceinline__ void bf3x_mnmajor(uint8_t* buf, int ct, int bar_id) {
+__device__ __forceinline__ void bf3x_mnmajor(uint8_t* buf, int ct, int bar_id, int sw32) {
     constexpr int IT = (ROWS + NT - 1) / NT;
     float v[IT][32];
 #pragma unroll
@@ -472,7 +548,7 @@ __device__ __forceinline__ void bf3x_mnmajor(uint8_t* buf, int ct, int bar_id) {
             for (int g = 0; g < 4; ++g) {
                 uint4 hi, lo;
                 bf16_split8(&v[it][8 * g], hi, lo);
-                const uint32_t off = sw_chunk<16>((uint32_t)j, (uint32_t)g);
+                const uint32_t off = bf16_tile_off<ROWS>((uint32_t)j, (uint32_t)g, sw32);
                 *reinterpret_cast<uint4*>(buf + off) = hi;
                 *reinterpret_cast<uint4*>(lo_tile + off) = lo;
             }
@@ -508,11 +584,16 @@ __device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t 
     return val;
 }
 
-template <int BN, int BK, int PASSES, bool A_MN, bool B_MN>
+template <int BN, int BK, int PASSES, bool A_MN, bool B_MN, bool STG = false, bool CTA2 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmB2, const Params p) {
-    using C_ = Cfg<BN, BK, PASSES>;
+               const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmX,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmXh, const Params p) {
+    using C_ = Cfg<BN, BK, PASSES, STG, CTA2>;
+    // CTA pairs: cluster c = blockIdx.x / 2 owns work items c, c + #clusters, ...; a work item covers TWO 128-row blocks
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const int64_t w_first = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+    const int64_t w_step = CTA2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
     constexpr bool BF3X = C_::BF3X;
     constexpr int NACC = C_::NACC;
     constexpr int STAGES = C_::STAGES;
@@ -520,11 +601,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int ROWB = C_::ROW_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
-    // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, then NACC acc-full, NACC acc-empty
+    uint8_t* epi_base = smem + STAGES * C_::STAGE_BYTES;             // staged-epilogue buffers (1024-byte aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C_::EPI_BYTES);
+    // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, then NACC acc-full, NACC acc-empty,
+    // then (staged epilogue) EPI_NIN "target chunk landed" barriers per epilogue warp
     uint64_t* acc_full = bars + 3 * STAGES;
     uint64_t* acc_empty = acc_full + NACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+    uint64_t* in_full = acc_empty + NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + (STG ? NUM_EPI_WARPS * EPI_NIN : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -534,13 +618,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto a_hi = [&](int s) { return stage_ptr(s); };
     auto a_lo = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES / 2 : A_BYTES); };
     auto b_hi = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES : 2 * A_BYTES); };
-    auto b_lo = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES + C_::B_BYTES / 2 : 2 * A_BYTES + C_::B_BYTES); };
+    auto b_lo = [&](int s) { return stage_ptr(s) + (BF3X ? A_BYTES + C_::B_CTA_BYTES / 2 : 2 * A_BYTES + C_::B_BYTES); };
     // work item -> (m block, n block, first K-block, number of K-blocks)
     auto decode = [&](int64_t w, int& m_blk, int& n_blk, int& kb_beg, int& nkb) {
         const int sp = (int)(w % p.splits);
         const int64_t t = w / p.splits;
         n_blk = (int)(t % p.tiles_n);
         m_blk = (int)(t / p.tiles_n);
+        if (CTA2) m_blk = 2 * m_blk + (int)rank;
         kb_beg = sp * p.kb_per_split;
         nkb = min(p.kb_total, kb_beg + p.kb_per_split) - kb_beg;
     };
@@ -548,31 +633,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[STAGES + s]), NUM_CONV_WARPS / (BF3X ? 1 : CONV_GROUPS));
+            mbar_init(smem_u32(&bars[STAGES + s]), (CTA2 ? 2 : 1) * NUM_CONV_WARPS / (BF3X ? 1 : CONV_GROUPS));
             mbar_init(smem_u32(&bars[2 * STAGES + s]), 1);
         }
         for (int b = 0; b < NACC; ++b) {
             mbar_init(smem_u32(&acc_full[b]), 1);
-            mbar_init(smem_u32(&acc_empty[b]), 32 * NUM_EPI_WARPS);
+            mbar_init(smem_u32(&acc_empty[b]), (CTA2 ? 2 : 1) * 32 * NUM_EPI_WARPS);
         }
+        if (STG)
+            for (int b = 0; b < NUM_EPI_WARPS * EPI_NIN; ++b) mbar_init(smem_u32(&in_full[b]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C_::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C_::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C_::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        // (whole warp in the loops, one elected lane issues: see the MMA issuer)
+        {
+            if (elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+            }
             uint32_t it = 0;
-            for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+            for (int64_t w = w_first; w < p.work_total; w += w_step) {
                 int m_blk, n_blk, kb_beg, nkb;
                 decode(w, m_blk, n_blk, kb_beg, nkb);
                 for (int i = 0; i < nkb; ++i, ++it) {
@@ -580,8 +676,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(smem_u32(&bars[2 * STAGES + s]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bars[s]);
-                    if (p.probe == 2) { mbar_arrive(full); continue; }
-                    mbar_expect_tx(full, A_BYTES + C_::B_BYTES);
+                    if (!elect_one()) continue;
+                    if (p.probe & 2) { mbar_arrive(full); continue; }
+                    mbar_expect_tx(full, A_BYTES + C_::B_CTA_BYTES);
                     const int k0 = (kb_beg + i) * BK;
                     // the streamed operand comes from HBM: pull the tile needed PF K-blocks from now into L2
                     constexpr int PF = 2 * STAGES;
@@ -599,12 +696,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_4d(smem_u32(a_hi(s)), &tmA, full, c0, w0 + kw - pad, (int)(r % p.conv_H) + kh - pad, (int)(r / p.conv_H));
                     } else if (!A_MN) tma_load_2d(smem_u32(a_hi(s)), &tmA, full, k0, m_blk * BM);
                     else tma_load_2d(smem_u32(BF3X ? a_hi(s) : a_lo(s)), &tmA, full, m_blk * BM, k0);
-                    if (BF3X && p.b_pre) {
+                    if (CTA2) {
+                        // this CTA's half of each MMA's B rows (pre-split bf16, rows of 64 B): [N0/2 rows | N1/2 rows]
+                        constexpr int H0 = C_::N0 / 2, H1 = C_::N1 / 2;
+                        tma_load_2d(smem_u32(b_hi(s)), &tmB, full, k0, n_blk * BN + (int)rank * H0);
+                        tma_load_2d(smem_u32(b_lo(s)), &tmB2, full, k0, n_blk * BN + (int)rank * H0);
+                        if (H1 > 0) {
+                            tma_load_2d(smem_u32(b_hi(s) + H0 * 64), &tmX, full, k0, n_blk * BN + C_::N0 + (int)rank * H1);
+                            tma_load_2d(smem_u32(b_lo(s) + H0 * 64), &tmC, full, k0, n_blk * BN + C_::N0 + (int)rank * H1);
+                        }
+                    } else if (BF3X && p.b_pre) {
                         // ready-made bf16 tiles: rows of 64 B straight into the hi / lo halves
 #pragma unroll
                         for (int r = 0; r < BN; r += C_::B_ROWS_PER_BOX) {
-                            tma_load_2d(smem_u32(b_hi(s) + r * 64), &tmB, full, k0, n_blk * BN + r);
-                            tma_load_2d(smem_u32(b_lo(s) + r * 64), &tmB2, full, k0, n_blk * BN + r);
+                            if (p.sw32) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    tma_load_2d(smem_u32(b_hi(s) + h * BN * 32 + r * 32), &tmB, full, k0 + 16 * h, n_blk * BN + r);
+                                    tma_load_2d(smem_u32(b_lo(s) + h * BN * 32 + r * 32), &tmB2, full, k0 + 16 * h, n_blk * BN + r);
+                                }
+                            } else {
+                                tma_load_2d(smem_u32(b_hi(s) + r * 64), &tmB, full, k0, n_blk * BN + r);
+                                tma_load_2d(smem_u32(b_lo(s) + r * 64), &tmB2, full, k0, n_blk * BN + r);
+                            }
                         }
                     } else if (!B_MN) {
 #pragma unroll
@@ -620,11 +734,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp walks the loops (warp-uniform control flow and operands); one elected lane issues the MMAs.
+        // With `if (lane == 0)` around everything the compiler kept descriptors in per-thread registers and wrapped EVERY
+        // tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~150 issue cycles per MMA, i.e. the tensor pipe idled
+        // more than half of the time (pure-MMA probe: 45 % of its rate; tools/mma_rate.cu).
+        if (rank == 0) {
+            const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
             constexpr uint32_t idesc0 = make_idesc(BM, C_::N0);
             constexpr uint32_t idesc1 = make_idesc(BM, C_::N1 > 0 ? C_::N1 : 16);
             uint32_t it = 0, j = 0;
-            for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x, ++j) {
+            for (int64_t w = w_first; w < p.work_total; w += w_step, ++j) {
                 int m_blk, n_blk, kb_beg, nkb;
                 decode(w, m_blk, n_blk, kb_beg, nkb);
                 const uint32_t buf = j % NACC;
@@ -636,12 +755,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(smem_u32(&bars[STAGES + s]), ph);
                     tc_fence_after();
+                    if (elect_one()) {
                     if (BF3X) {
                         // bf16 tiles: rows of 64 B (SWIZZLE_64B descriptors), UMMA K = 16 elements = 32 B
-                        constexpr uint32_t ib0 = make_idesc_bf16(BM, C_::N0);
-                        constexpr uint32_t ib1 = make_idesc_bf16(BM, C_::N1 > 0 ? C_::N1 : 16);
-                        const uint64_t dah = make_kmajor_desc<16>(smem_u32(a_hi(s))), dal = make_kmajor_desc<16>(smem_u32(a_lo(s)));
-                        const uint64_t dbh = make_kmajor_desc<16>(smem_u32(b_hi(s))), dbl = make_kmajor_desc<16>(smem_u32(b_lo(s)));
+                        constexpr uint32_t ib0 = make_idesc_bf16(CTA2 ? 2 * BM : BM, C_::N0);
+                        constexpr uint32_t ib1 = make_idesc_bf16(CTA2 ? 2 * BM : BM, C_::N1 > 0 ? C_::N1 : 16);
+                        const bool s32 = p.sw32 != 0;
+                        const uint64_t dah = s32 ? make_kmajor_desc_sw32(smem_u32(a_hi(s))) : make_kmajor_desc<16>(smem_u32(a_hi(s)));
+                        const uint64_t dal = s32 ? make_kmajor_desc_sw32(smem_u32(a_lo(s))) : make_kmajor_desc<16>(smem_u32(a_lo(s)));
+                        const uint64_t dbh = s32 ? make_kmajor_desc_sw32(smem_u32(b_hi(s))) : make_kmajor_desc<16>(smem_u32(b_hi(s)));
+                        const uint64_t dbl = s32 ? make_kmajor_desc_sw32(smem_u32(b_lo(s))) : make_kmajor_desc<16>(smem_u32(b_lo(s)));
+                        // descriptor steps (16-byte units): second K = 16 half of a tile, second MMA's rows (N0 ..)
+                        const uint64_t ak1 = (uint64_t)((s32 ? BM * 32 : 32) >> 4), bk1 = (uint64_t)((s32 ? BN * 32 : 32) >> 4);
+                        const uint64_t bn1 = (uint64_t)(((CTA2 ? C_::N0 / 2 : C_::N0) * (s32 ? 32 : 64)) >> 4);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint64_t da = pass == 0 ? dal : dah;
@@ -649,14 +775,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
                                 const uint32_t acc = (i > 0 || pass > 0 || k > 0) ? 1u : 0u;
-                                const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                                if (C_::A_TMEM) {
+                                const uint64_t dbk = db + k * bk1;
+                                if (CTA2 && C_::A_TMEM) {
                                     const uint32_t ta = tmem_base + C_::A_COL0 + s * C_::A_STAGE_COLS + (pass == 0 ? 16 : 0) + k * 8;
-                                    umma_bf16_ts(tacc, ta, db + koff, ib0, acc);
-                                    if (C_::N1 > 0) umma_bf16_ts(tacc + C_::N0, ta, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                                    umma_bf16_ts2(tacc, ta, dbk, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16_ts2(tacc + C_::N0, ta, dbk + bn1, ib1, acc);
+                                } else if (CTA2) {
+                                    umma_bf16_ss2(tacc, da + k * ak1, dbk, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16_ss2(tacc + C_::N0, da + k * ak1, dbk + bn1, ib1, acc);
+                                } else if (C_::A_TMEM) {
+                                    const uint32_t ta = tmem_base + C_::A_COL0 + s * C_::A_STAGE_COLS + (pass == 0 ? 16 : 0) + k * 8;
+                                    umma_bf16_ts(tacc, ta, dbk, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16_ts(tacc + C_::N0, ta, dbk + bn1, ib1, acc);
                                 } else {
-                                    umma_bf16(tacc, da + koff, db + koff, ib0, acc);
-                                    if (C_::N1 > 0) umma_bf16(tacc + C_::N0, da + koff, db + koff + (uint64_t)((C_::N0 * 64) >> 4), ib1, acc);
+                                    umma_bf16(tacc, da + k * ak1, dbk, ib0, acc);
+                                    if (C_::N1 > 0) umma_bf16(tacc + C_::N0, da + k * ak1, dbk + bn1, ib1, acc);
                                 }
                             }
                         }
@@ -685,9 +818,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     }
-                    umma_commit(smem_u32(&bars[2 * STAGES + s]));      // frees the stage when these MMAs retire
+                    if (CTA2) umma_commit2(smem_u32(&bars[2 * STAGES + s]));
+                    else umma_commit(smem_u32(&bars[2 * STAGES + s]));  // frees the stage when these MMAs retire
+                    if (i == nkb - 1) {
+                        if (CTA2) umma_commit2(smem_u32(&acc_full[buf]));
+                        else umma_commit(smem_u32(&acc_full[buf]));     // accumulator of this work item complete
+                    }
+                    }
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&acc_full[buf]));                  // accumulator of this work item complete
             }
         }
     } else if (warp < 2 + NUM_CONV_WARPS) {
@@ -700,7 +839,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grp = NGRP == 1 ? 0 : (warp - 2) / (NUM_CONV_WARPS / NGRP);
         const int ct = (threadIdx.x - 64) - grp * GT;
         uint32_t it = 0;
-        for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        for (int64_t w = w_first; w < p.work_total; w += w_step) {
             int m_blk, n_blk, kb_beg, nkb;
             decode(w, m_blk, n_blk, kb_beg, nkb);
             for (int i = 0; i < nkb; ++i, ++it) {
@@ -708,9 +847,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
-                if (p.probe == 1) {
+                if (p.probe & 1) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+                    if (lane == 0) {
+                        if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&bars[STAGES + s]));
+                        else mbar_arrive(smem_u32(&bars[STAGES + s]));
+                    }
                     continue;
                 }
                 if (BF3X) {
@@ -718,11 +860,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     constexpr int NTA = 32 * NUM_CONV_WARPS;
                     const int cta = threadIdx.x - 64;
                     if (C_::A_TMEM) bf3x_a_tmem<A_MN>(a_hi(s), tmem_base + C_::A_COL0 + s * C_::A_STAGE_COLS, warp, lane, p.a16swap);
-                    else if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1);
-                    else bf3x_mnmajor<BM, 128, NTA>(a_hi(s), cta, 1);
+                    else if (!A_MN) bf3x_kmajor<BM, NTA>(a_hi(s), cta, 1, p.sw32);
+                    else bf3x_mnmajor<BM, 128, NTA>(a_hi(s), cta, 1, p.sw32);
                     if (p.b_pre) {
-                    } else if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2);
-                    else bf3x_mnmajor<BN, C_::B_CW, NTA>(b_hi(s), cta, 2);
+                    } else if (!B_MN) bf3x_kmajor<BN, NTA>(b_hi(s), cta, 2, p.sw32);
+                    else bf3x_mnmajor<BN, C_::B_CW, NTA>(b_hi(s), cta, 2, p.sw32);
                 } else if (C_::A_TMEM) {
                     const uint32_t ta = tmem_base + C_::A_COL0 + s * 2 * BK;
                     if (NGRP == 2) {
@@ -741,12 +883,135 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_before();                                   // tcgen05.st (A ring) ordered before the arrive
                 fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+                if (lane == 0) {
+                    // CTA pairs: the MMA thread of rank 0 waits for both CTAs' tiles (landed by TMA and converted)
+                    if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&bars[STAGES + s]));
+                    else mbar_arrive(smem_u32(&bars[STAGES + s]));
+                }
             }
         }
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                                      // TMEM lane quarter this warp may access
+        if constexpr (STG) {
+            // ---- staged reconstruction head --------------------------------------------------------------------------
+            // The row-per-thread epilogue reads the target and writes the gradient as 32-byte pieces of 32 different rows
+            // per instruction (measured: 2x the HBM time of those bytes).  Here every warp streams its 32 rows x 32 columns
+            // chunks through shared memory with TMA: target chunks arrive EPI_NIN deep (running ahead across tiles),
+            // gradient (and xhat) chunks leave through EPI_NOUT buffers as bulk stores; the threads only touch shared
+            // memory (swizzled, conflict-free) and tensor memory.
+            constexpr int CPT = BN / 32;                             // chunks per tile
+            const int ew = warp - (2 + NUM_CONV_WARPS);
+            uint8_t* ebuf = epi_base + (size_t)ew * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES;
+            uint64_t* infull = in_full + ew * EPI_NIN;
+            auto nvalid = [&](int n_blk) {
+                const int64_t nv = (p.N - (int64_t)n_blk * BN + 31) / 32;
+                return nv < CPT ? (int)nv : CPT;
+            };
+            // producer side (lane 0): the next target chunk in this CTA's (tile, chunk) order
+            int64_t pw = blockIdx.x;
+            int pc = 0;
+            uint32_t pcount = 0;
+            auto issue_next = [&]() {
+                if (pw >= p.work_total) return;
+                int m_blk, n_blk, kb_beg, nkb;
+                decode(pw, m_blk, n_blk, kb_beg, nkb);
+                const uint32_t b = pcount % EPI_NIN;
+                const uint32_t bar = smem_u32(&infull[b]);
+                mbar_expect_tx(bar, EPI_CHUNK_BYTES);
+                tma_load_2d(smem_u32(ebuf + b * EPI_CHUNK_BYTES), &tmX, bar, n_blk * BN + pc * 32, m_blk * BM + q * 32);
+                ++pcount;
+                if (++pc >= nvalid(n_blk)) { pc = 0; pw += gridDim.x; }
+            };
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+#pragma unroll
+                for (int i = 0; i < EPI_NIN; ++i) issue_next();
+            }
+            uint32_t j = 0, ccount = 0, ocount = 0;
+            float rloss = 0.f;
+            auto put_chunk = [&](const CUtensorMap* tm, const float* o, int col0, int row0) {
+                uint8_t* xo = ebuf + (size_t)(EPI_NIN + (ocount % EPI_NOUT)) * EPI_CHUNK_BYTES;
+                ++ocount;
+                // the bulk store that used this buffer EPI_NOUT chunks ago has read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(EPI_NOUT - 1) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<float4*>(xo + sw_chunk<32>((uint32_t)lane, (uint32_t)ch)) =
+                        make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                     reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(xo)), "r"(col0), "r"(row0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            };
+            for (int64_t w = w_first; w < p.work_total; w += w_step, ++j) {
+                int m_blk, n_blk, kb_beg, nkb;
+                decode(w, m_blk, n_blk, kb_beg, nkb);
+                const uint32_t buf = j % NACC;
+                mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
+                tc_fence_after();
+                const int row0 = m_blk * BM + q * 32;
+                const bool row_ok = (int64_t)row0 + lane < p.M;
+                const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+                const int nv = nvalid(n_blk);
+#pragma unroll 1
+                for (int c = 0; c < nv; ++c) {
+                    float v[32], xs[32];
+                    tmem_ld16(trow + (uint32_t)(c * 32), v);
+                    tmem_ld16(trow + (uint32_t)(c * 32 + 16), v + 16);
+                    if (c == nv - 1) {                               // accumulator drained: the MMA warp may reuse the buffer
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&acc_empty[buf]));
+                    }
+                    const uint32_t b = ccount % EPI_NIN;
+                    mbar_wait(smem_u32(&infull[b]), (ccount / EPI_NIN) & 1u);
+                    ++ccount;
+                    const uint8_t* xin = ebuf + b * EPI_CHUNK_BYTES;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 t = *reinterpret_cast<const float4*>(xin + sw_chunk<32>((uint32_t)lane, (uint32_t)ch));
+                        xs[4 * ch] = t.x; xs[4 * ch + 1] = t.y; xs[4 * ch + 2] = t.z; xs[4 * ch + 3] = t.w;
+                    }
+                    __syncwarp();
+                    if (lane == 0) issue_next();                     // refill the buffer just read
+                    const int col0 = n_blk * BN + c * 32;
+                    const bool full = (int64_t)col0 + 32 <= p.N;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        float bb[4];
+                        if (full) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.bias + col0 + 4 * g);
+                            bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) bb[e] = (int64_t)col0 + 4 * g + e < p.N ? p.bias[col0 + 4 * g + e] : 0.f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = 4 * g + e;
+                            const float t = tanh_fast(v[i] + bb[e]);
+                            const float df = t - xs[i];
+                            const bool ok = row_ok && (full || (int64_t)col0 + i < p.N);
+                            rloss += ok ? 0.5f * df * df : 0.f;
+                            xs[i] = df * (1.f - t * t) * p.inv_batch;
+                            v[i] = t;
+                        }
+                    }
+                    put_chunk(&tmC, xs, col0, row0);
+                    if (p.rxhat) put_chunk(&tmXh, v, col0, row0);
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (p.racc) {
+                const float s = warp_sum(rloss);
+                if (lane == 0) atomicAdd(p.racc, (double)s);
+            }
+        } else {
         // column range of this warp: the whole tile (4 epilogue warps) or one half (8)
         constexpr int CSPLIT = ((BN / 2 + 15) / 16) * 16;
         const int ehalf = NUM_EPI_WARPS == 8 ? (warp - (2 + NUM_CONV_WARPS)) >> 2 : 0;
@@ -754,7 +1019,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c_end = (NUM_EPI_WARPS == 8 && ehalf == 0) ? CSPLIT : BN;
         uint32_t j = 0;
         float rloss = 0.f;
-        for (int64_t w = blockIdx.x; w < p.work_total; w += gridDim.x, ++j) {
+        for (int64_t w = w_first; w < p.work_total; w += w_step, ++j) {
             int m_blk, n_blk, kb_beg, nkb;
             decode(w, m_blk, n_blk, kb_beg, nkb);
             const uint32_t buf = j % NACC;
@@ -887,18 +1152,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(&acc_empty[buf]));                  // TMEM buffer may be overwritten
+            if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&acc_empty[buf]));
+            else mbar_arrive(smem_u32(&acc_empty[buf]));             // TMEM buffer may be overwritten
         }
         if (p.epi == EPI_RECON && p.racc) {
             const float s = warp_sum(rloss);
             if (lane == 0) atomicAdd(p.racc, (double)s);
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();      // both CTAs are done with each other's shared / tensor memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
+        if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
     }
 }
 
@@ -985,19 +1254,19 @@ static int make_conv_map(const float* X, int64_t B, int H, int W, int C, int BK,
     return CDG_OK;
 }
 // pre-split bf16 operand [rows][K] (row stride ld16 elements): box {32 bf16 = 64 B, box_rows}, SWIZZLE_64B
-static int make_map_bf16(const void* X, int64_t rows, int64_t K, int64_t ld16, int box_rows, CUtensorMap* out) {
+static int make_map_bf16(const void* X, int64_t rows, int64_t K, int64_t ld16, int box_rows, int sw32, CUtensorMap* out) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
-    MapKey key{X, rows, K, ld16, -16, 32, box_rows, 3};
+    MapKey key{X, rows, K, ld16, -16, sw32 ? 16 : 32, box_rows, 3};
     {
         std::lock_guard<std::mutex> g(g_maps_mu);
         auto it = g_maps.find(key);
         if (it != g_maps.end()) { *out = it->second; return CDG_OK; }
     }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld16 * 2};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {sw32 ? 16u : 32u, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r); return CDG_ERR_CUDA; }
     std::lock_guard<std::mutex> g(g_maps_mu);
@@ -1030,7 +1299,48 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
         CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK, PASSES>::SMEM));
         attr_done = true;
     }
-    kern<<<grid, THREADS, Cfg<BN, BK, PASSES>::SMEM, s>>>(ta, tb, tb2, p);
+    kern<<<grid, THREADS, Cfg<BN, BK, PASSES>::SMEM, s>>>(ta, tb, tb2, ta, ta, ta, p);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+// CTA-pair launch: clusters of 2, pre-split bf16 B (tb / tb2: first MMA's half rows, tb3 / tb4: second MMA's), A converted in the loop
+template <int BN, bool A_MN>
+static int launch_cta2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const CUtensorMap& tb3,
+                       const CUtensorMap& tb4, const Params& p, unsigned clusters, cudaStream_t s) {
+    auto kern = gemm_tc_kernel<BN, 32, 2, A_MN, false, false, true>;
+    using C_ = Cfg<BN, 32, 2, false, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C_::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CDG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tb2, tb3, tb4, ta, p));
+    ++g_launches;
+    return CDG_OK;
+}
+
+// the fused reconstruction head with the staged (TMA in / TMA out) epilogue: 256-wide bf16x3 tile, K-major operands
+static int launch_recon_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const CUtensorMap& tx,
+                               const CUtensorMap& tc_, const CUtensorMap& txh, const Params& p, dim3 grid, cudaStream_t s) {
+    auto kern = gemm_tc_kernel<256, 32, 2, false, false, true>;
+    using C_ = Cfg<256, 32, 2, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+        attr_done = true;
+    }
+    kern<<<grid, THREADS, C_::SMEM, s>>>(ta, tb, tb2, tx, tc_, txh, p);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }
@@ -1159,6 +1469,9 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
         static int sw = -1;
         if (sw < 0) { const char* e = getenv("CDG_TC_A16SWAP"); sw = (e && atoi(e) != 0) ? 1 : 0; }
         p.a16swap = sw;
+        static int sw32 = -1;
+        if (sw32 < 0) { const char* e = getenv("CDG_TC_SW32"); sw32 = (e && atoi(e) != 0) ? 1 : 0; }
+        p.sw32 = sw32;
     }
     p.conv_cb = g.conv_C > 0 ? g.conv_C / BK : 0; p.conv_W = g.conv_W; p.conv_H = g.conv_H; p.conv_k = g.conv_k;
     {
@@ -1197,8 +1510,8 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     CUtensorMap tb2;
     if (g.b_hi16 && passes == 2) {
         const int pb = BN <= 256 ? BN : BN / 2;
-        CDG_TRY(make_map_bf16(g.b_hi16, g.N, g.K, g.ld_b16, pb, &tb));
-        CDG_TRY(make_map_bf16(g.b_lo16, g.N, g.K, g.ld_b16, pb, &tb2));
+        CDG_TRY(make_map_bf16(g.b_hi16, g.N, g.K, g.ld_b16, pb, p.sw32, &tb));
+        CDG_TRY(make_map_bf16(g.b_lo16, g.N, g.K, g.ld_b16, pb, p.sw32, &tb2));
         p.b_pre = 1;
     } else {
         CDG_TRY(make_map(g.B, g.N, g.K, g.sb_n, g.sb_k, pl.b_mn, b_box, BK, &tb));
@@ -1207,7 +1520,37 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     }
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
-    if (passes == 2) {
+    static int no_stg = -1;
+    // measured on B200: 7.8 vs 7.1 ms per step for the decoder-output GEMMs -> off unless CDG_TC_STG=1
+    if (no_stg < 0) { const char* e = getenv("CDG_TC_STG"); no_stg = (e && atoi(e) != 0) ? 0 : 1; }
+    static int cta2 = -1;
+    if (cta2 < 0) { const char* e = getenv("CDG_TC_CTA2"); cta2 = (e && atoi(e) == 0) ? 0 : 1; }
+    if (passes == 2 && p.b_pre && cta2 && (BN == 304 || BN == 256 || BN == 160) && g.M >= 1024 && g.conv_C == 0) {
+        // CTA pairs: a work item is two 128-row blocks; each CTA stages half of the B rows of each MMA
+        const int N0 = BN <= 256 ? BN : 160, N1 = BN - N0;
+        CDG_TRY(make_map_bf16(g.b_hi16, g.N, g.K, g.ld_b16, N0 / 2, 0, &tb));
+        CDG_TRY(make_map_bf16(g.b_lo16, g.N, g.K, g.ld_b16, N0 / 2, 0, &tb2));
+        CUtensorMap tb3 = tb, tb4 = tb2;
+        if (N1 > 0) {
+            CDG_TRY(make_map_bf16(g.b_hi16, g.N, g.K, g.ld_b16, N1 / 2, 0, &tb3));
+            CDG_TRY(make_map_bf16(g.b_lo16, g.N, g.K, g.ld_b16, N1 / 2, 0, &tb4));
+        }
+        p.sw32 = 0;
+        p.work_total = ((pl.tm + 1) / 2) * pl.tn * splits;
+        const unsigned clusters = (unsigned)imin64(p.work_total, kNumSMs / 2);
+        if (BN == 304) r = pl.a_mn ? launch_cta2<304, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<304, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
+        else if (BN == 256) r = pl.a_mn ? launch_cta2<256, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<256, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
+        else r = pl.a_mn ? launch_cta2<160, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<160, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
+    } else if (passes == 2 && BN == 256 && g.epi == EPI_RECON && p.vec && !pl.a_mn && !pl.b_mn && !no_stg && g.M < (1ll << 31) &&
+        g.N < (1ll << 31)) {
+        // staged epilogue: target / gradient / xhat as [M rows][N columns] maps with 32 x 32 boxes (SWIZZLE_128B)
+        CUtensorMap tx, tcm, txh;
+        CDG_TRY(make_map(g.recon_x, g.M, g.N, g.ld_x, 1, false, 32, 32, &tx));
+        CDG_TRY(make_map(g.C, g.M, g.N, pl.sc_m, 1, false, 32, 32, &tcm));
+        if (g.recon_xhat) CDG_TRY(make_map(g.recon_xhat, g.M, g.N, pl.sc_m, 1, false, 32, 32, &txh));
+        else txh = tcm;
+        r = launch_recon_staged(ta, tb, tb2, tx, tcm, txh, p, grid, s);
+    } else if (passes == 2) {
         if (BN == 64) r = launch_layout<64, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
         else if (BN == 128) r = launch_layout<128, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
         else if (BN == 160) r = launch_layout<160, 32, 2>(pl.a_mn, pl.b_mn, ta, tb, tb2, p, grid, s);
