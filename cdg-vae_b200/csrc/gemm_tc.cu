@@ -224,6 +224,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, do other work, then wait (the wait names the registers so that no use can move above it)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
 template <int BK>
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
@@ -272,7 +286,7 @@ __device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
 
 // Staged reconstruction epilogue (STG): every epilogue warp owns EPI_NIN target buffers and EPI_NOUT output buffers of
 // 32 rows x 32 floats (SWIZZLE_128B) moved by TMA, paid for with one ring stage.
-constexpr int EPI_NIN = 3, EPI_NOUT = 2, EPI_CHUNK_BYTES = 32 * 128;
+constexpr int EPI_NOUT = 2, EPI_CHUNK_BYTES = 32 * 128;
 
 template <int BN, int BK, int PASSES = 3, bool STG = false, bool CTA2 = false>
 struct Cfg {
@@ -282,14 +296,17 @@ struct Cfg {
     static constexpr bool BF3X = PASSES == 2;
     // (a 6-stage ring was tried for BN = 160 and changed nothing: the ring depth is not what limits the main loop)
     // narrow tiles (BN <= 64: the convolutions with 32 / 64 output channels) leave room for a 4-deep ring of 32-float blocks
-    static constexpr int STAGES = CTA2 ? 6 : BF3X ? (STG ? 3 : 4) : (BK == 32 ? (BN <= 64 ? 4 : 2) : 4);
+    static constexpr int STAGES = CTA2 ? (STG ? 4 : 6) : BF3X ? (STG ? 3 : 4) : (BK == 32 ? (BN <= 64 ? 4 : 2) : 4);
+    static constexpr int EPI_NIN = CTA2 ? 4 : 3;
     static constexpr int EPI_BYTES = STG ? NUM_EPI_WARPS * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES : 0;
     static constexpr int ROW_BYTES = BK * 4;
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int B_CTA_BYTES = CTA2 ? B_BYTES / 2 : B_BYTES;   // CTA pairs: each CTA stages half of the B rows
     static constexpr int STAGE_BYTES = BF3X ? (A_BYTES + B_CTA_BYTES) : 2 * (A_BYTES + B_BYTES);  // hi + lo for both operands
-    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BIAS_LD = 320;                               // epilogue's bias tile (two tiles in flight)
+    static constexpr int BIAS_BYTES = STG ? 0 : 2 * BIAS_LD * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 384 /*barriers*/ + BIAS_BYTES;
     static_assert(!STG || (BF3X && BN % 32 == 0 && NUM_EPI_WARPS == 4), "staged epilogue: bf16x3 tiles, one warp per lane quarter");
     static constexpr int B_ROWS_PER_BOX = BN <= 256 ? BN : BN / 2;  // K-major TMA box rows (<= 256)
     static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4));   // MN-major chunk width (<= 128)
@@ -309,7 +326,7 @@ struct Cfg {
     static_assert(BN % 16 == 0 && N0 % 16 == 0 && N1 % 16 == 0, "UMMA N must be a multiple of 16 at M = 128");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
     static_assert(!BF3X || BK == 32, "bf16x3 tiles are built from 32-float K-blocks");
-    static_assert(!CTA2 || (BF3X && !STG), "CTA pairs: bf16x3 tiles");
+    static_assert(!CTA2 || BF3X, "CTA pairs: bf16x3 tiles");
     static_assert(!CTA2 || (N0 % 16 == 0 && N1 % 16 == 0), "UMMA N is a multiple of 16 at M = 256; half-B boxes are whole 8-row groups");
 };
 
@@ -590,6 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmX,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmXh, const Params p) {
     using C_ = Cfg<BN, BK, PASSES, STG, CTA2>;
+    constexpr int EPI_NIN = C_::EPI_NIN;
     // CTA pairs: cluster c = blockIdx.x / 2 owns work items c, c + #clusters, ...; a work item covers TWO 128-row blocks
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
     const int64_t w_first = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
@@ -605,6 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C_::EPI_BYTES);
     // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, then NACC acc-full, NACC acc-empty,
     // then (staged epilogue) EPI_NIN "target chunk landed" barriers per epilogue warp
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
     uint64_t* acc_full = bars + 3 * STAGES;
     uint64_t* acc_empty = acc_full + NACC;
     uint64_t* in_full = acc_empty + NACC;
@@ -909,7 +928,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 return nv < CPT ? (int)nv : CPT;
             };
             // producer side (lane 0): the next target chunk in this CTA's (tile, chunk) order
-            int64_t pw = blockIdx.x;
+            int64_t pw = w_first;
             int pc = 0;
             uint32_t pcount = 0;
             auto issue_next = [&]() {
@@ -921,7 +940,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(bar, EPI_CHUNK_BYTES);
                 tma_load_2d(smem_u32(ebuf + b * EPI_CHUNK_BYTES), &tmX, bar, n_blk * BN + pc * 32, m_blk * BM + q * 32);
                 ++pcount;
-                if (++pc >= nvalid(n_blk)) { pc = 0; pw += gridDim.x; }
+                if (++pc >= nvalid(n_blk)) { pc = 0; pw += w_step; }
             };
             if (lane == 0) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
@@ -966,7 +985,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld16(trow + (uint32_t)(c * 32 + 16), v + 16);
                     if (c == nv - 1) {                               // accumulator drained: the MMA warp may reuse the buffer
                         tc_fence_before();
-                        mbar_arrive(smem_u32(&acc_empty[buf]));
+                        if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&acc_empty[buf]));
+                        else mbar_arrive(smem_u32(&acc_empty[buf]));
                     }
                     const uint32_t b = ccount % EPI_NIN;
                     mbar_wait(smem_u32(&infull[b]), (ccount / EPI_NIN) & 1u);
@@ -1023,8 +1043,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int m_blk, n_blk, kb_beg, nkb;
             decode(w, m_blk, n_blk, kb_beg, nkb);
             const uint32_t buf = j % NACC;
-            mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
-            tc_fence_after();
             const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
             const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
             const bool row_ok = m < p.M;
@@ -1048,11 +1066,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             };
+            // everything that does not need the accumulator goes BEFORE the wait for it: the first target chunks and the
+            // tile's bias values (staged in shared memory: per-chunk global loads of the bias were an exposed L1/L2 latency
+            // in front of every tanh, ncu source view: 28 % of the epilogue warps' samples)
             fetch(c_beg, r0); fetch(c_beg + 16, r1); fetch(c_beg + 32, r2);
+            const float* bs = bias_s + (j & 1u) * C_::BIAS_LD;
+            const bool bias_tile = !STG && !p.bias_on_m && (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT || p.epi == EPI_RECON);
+            if (bias_tile) {
+                const int et = threadIdx.x - 32 * (2 + NUM_CONV_WARPS);
+                for (int c = et; c < BN; c += 32 * NUM_EPI_WARPS) {
+                    const int64_t n = (int64_t)n_blk * BN + c;
+                    bias_s[(j & 1u) * C_::BIAS_LD + c] = n < p.N ? p.bias[n] : 0.f;
+                }
+                asm volatile("bar.sync 5, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+            }
+            mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
+            tc_fence_after();
+            uint32_t vraw[16];
+            tmem_ld16_issue(trow + (uint32_t)c_beg, vraw);           // accumulator chunks are read one ahead of their use
 #pragma unroll 1
             for (int c0 = c_beg; c0 < c_end; c0 += 16) {
                 float v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);
+                tmem_ld16_wait(vraw);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vraw[i]);
+                if (c0 + 16 < c_end) tmem_ld16_issue(trow + (uint32_t)(c0 + 16), vraw);
                 float4 cur[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) { cur[g] = r0[g]; r0[g] = r1[g]; r1[g] = r2[g]; }
@@ -1061,72 +1099,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!row_ok || n0 >= p.N) continue;
                 if (p.vec && !p.atomic && n0 + 16 <= p.N && !(p.extra && n0 + 16 >= p.N)) {
                     float* crow = p.C + m * p.sc_m + n0;
+                    // results leave in halves of 8 columns (one 256-bit store each): keeps two float4 of outputs live, not four
                     if (p.epi == EPI_RECON) {
                         float* xh = p.rxhat ? p.rxhat + m * p.sc_m + n0 : nullptr;
-                        float4 og[4], tg[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * g);
-                            const float4 xx = cur[g];
-                            float t[4] = {tanh_fast(v[4 * g] + bb.x), tanh_fast(v[4 * g + 1] + bb.y), tanh_fast(v[4 * g + 2] + bb.z),
-                                          tanh_fast(v[4 * g + 3] + bb.w)};
-                            const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
-                            float o[4];
+                        for (int h = 0; h < 2; ++h) {
+                            float4 og[2], tg[2];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float df = t[e] - xs[e];
-                                rloss += 0.5f * df * df;
-                                o[e] = df * (1.f - t[e] * t[e]) * p.inv_batch;
+                            for (int gg = 0; gg < 2; ++gg) {
+                                const int g = 2 * h + gg;
+                                const float4 bb = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+                                const float4 xx = cur[g];
+                                float t[4] = {tanh_fast(v[4 * g] + bb.x), tanh_fast(v[4 * g + 1] + bb.y), tanh_fast(v[4 * g + 2] + bb.z),
+                                              tanh_fast(v[4 * g + 3] + bb.w)};
+                                const float xs[4] = {xx.x, xx.y, xx.z, xx.w};
+                                float o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float df = t[e] - xs[e];
+                                    rloss += 0.5f * df * df;
+                                    o[e] = df * (1.f - t[e] * t[e]) * p.inv_batch;
+                                }
+                                og[gg] = make_float4(o[0], o[1], o[2], o[3]);
+                                tg[gg] = make_float4(t[0], t[1], t[2], t[3]);
                             }
-                            og[g] = make_float4(o[0], o[1], o[2], o[3]);
-                            tg[g] = make_float4(t[0], t[1], t[2], t[3]);
-                        }
-                        if (p.vec8) {
-                            st_v8(crow, og[0], og[1]);
-                            st_v8(crow + 8, og[2], og[3]);
-                            if (xh) { st_v8(xh, tg[0], tg[1]); st_v8(xh + 8, tg[2], tg[3]); }
-                        } else {
+                            if (p.vec8) {
+                                st_v8(crow + 8 * h, og[0], og[1]);
+                                if (xh) st_v8(xh + 8 * h, tg[0], tg[1]);
+                            } else {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                *reinterpret_cast<float4*>(crow + 4 * g) = og[g];
-                                if (xh) *reinterpret_cast<float4*>(xh + 4 * g) = tg[g];
+                                for (int gg = 0; gg < 2; ++gg) {
+                                    *reinterpret_cast<float4*>(crow + 8 * h + 4 * gg) = og[gg];
+                                    if (xh) *reinterpret_cast<float4*>(xh + 8 * h + 4 * gg) = tg[gg];
+                                }
                             }
                         }
                     } else {
-                        float4 og[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float o[4] = {v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]};
-                            if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) {
-                                if (p.bias_on_m) {
-                                    const float bm = p.bias[m];
-                                    o[0] += bm; o[1] += bm; o[2] += bm; o[3] += bm;
-                                } else {
-                                    const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * g);
-                                    o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+                        for (int h = 0; h < 2; ++h) {
+                            float4 og[2];
+#pragma unroll
+                            for (int gg = 0; gg < 2; ++gg) {
+                                const int g = 2 * h + gg;
+                                float o[4] = {v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]};
+                                if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_ACT) {
+                                    if (p.bias_on_m) {
+                                        const float bm = p.bias[m];
+                                        o[0] += bm; o[1] += bm; o[2] += bm; o[3] += bm;
+                                    } else {
+                                        const float4 bb = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+                                        o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+                                    }
                                 }
-                            }
-                            if (p.epi == EPI_BIAS_ACT) {
+                                if (p.epi == EPI_BIAS_ACT) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) o[e] = act_fwd(o[e], p.act);
+                                    for (int e = 0; e < 4; ++e) o[e] = act_fwd(o[e], p.act);
+                                }
+                                if (p.epi == EPI_MUL_DACT) {
+                                    const float4 hh = cur[g];
+                                    o[0] *= act_bwd_from_out(hh.x, p.act); o[1] *= act_bwd_from_out(hh.y, p.act);
+                                    o[2] *= act_bwd_from_out(hh.z, p.act); o[3] *= act_bwd_from_out(hh.w, p.act);
+                                }
+                                if (p.accumulate) {
+                                    const float4 cc = *reinterpret_cast<const float4*>(crow + 4 * g);
+                                    o[0] += cc.x; o[1] += cc.y; o[2] += cc.z; o[3] += cc.w;
+                                }
+                                og[gg] = make_float4(o[0], o[1], o[2], o[3]);
                             }
-                            if (p.epi == EPI_MUL_DACT) {
-                                const float4 hh = cur[g];
-                                o[0] *= act_bwd_from_out(hh.x, p.act); o[1] *= act_bwd_from_out(hh.y, p.act);
-                                o[2] *= act_bwd_from_out(hh.z, p.act); o[3] *= act_bwd_from_out(hh.w, p.act);
-                            }
-                            if (p.accumulate) {
-                                const float4 cc = *reinterpret_cast<const float4*>(crow + 4 * g);
-                                o[0] += cc.x; o[1] += cc.y; o[2] += cc.z; o[3] += cc.w;
-                            }
-                            og[g] = make_float4(o[0], o[1], o[2], o[3]);
-                        }
-                        if (p.vec8) {
-                            st_v8(crow, og[0], og[1]);
-                            st_v8(crow + 8, og[2], og[3]);
-                        } else {
+                            if (p.vec8) {
+                                st_v8(crow + 8 * h, og[0], og[1]);
+                            } else {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(crow + 4 * g) = og[g];
+                                for (int gg = 0; gg < 2; ++gg) *reinterpret_cast<float4*>(crow + 8 * h + 4 * gg) = og[gg];
+                            }
                         }
                     }
                 } else {
@@ -1305,11 +1350,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 }
 
 // CTA-pair launch: clusters of 2, pre-split bf16 B (tb / tb2: first MMA's half rows, tb3 / tb4: second MMA's), A converted in the loop
-template <int BN, bool A_MN>
+template <int BN, bool A_MN, bool STG = false>
 static int launch_cta2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const CUtensorMap& tb3,
-                       const CUtensorMap& tb4, const Params& p, unsigned clusters, cudaStream_t s) {
-    auto kern = gemm_tc_kernel<BN, 32, 2, A_MN, false, false, true>;
-    using C_ = Cfg<BN, 32, 2, false, true>;
+                       const CUtensorMap& tb4, const Params& p, unsigned clusters, cudaStream_t s, const CUtensorMap* txh = nullptr) {
+    auto kern = gemm_tc_kernel<BN, 32, 2, A_MN, false, STG, true>;
+    using C_ = Cfg<BN, 32, 2, STG, true>;
     static bool attr_done = false;
     if (!attr_done) {
         CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
@@ -1325,7 +1370,7 @@ static int launch_cta2(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CDG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tb2, tb3, tb4, ta, p));
+    CDG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tb2, tb3, tb4, txh ? *txh : ta, p));
     ++g_launches;
     return CDG_OK;
 }
@@ -1538,7 +1583,15 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
         p.sw32 = 0;
         p.work_total = ((pl.tm + 1) / 2) * pl.tn * splits;
         const unsigned clusters = (unsigned)imin64(p.work_total, kNumSMs / 2);
-        if (BN == 304) r = pl.a_mn ? launch_cta2<304, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<304, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
+        if (BN == 256 && g.epi == EPI_RECON && p.vec && !pl.a_mn && !no_stg && g.M < (1ll << 31) && g.N < (1ll << 31)) {
+            // fused reconstruction head with the staged epilogue (N1 = 0: the tmX / tmC slots carry the target / gradient maps)
+            CUtensorMap tx, tcm, txh;
+            CDG_TRY(make_map(g.recon_x, g.M, g.N, g.ld_x, 1, false, 32, 32, &tx));
+            CDG_TRY(make_map(g.C, g.M, g.N, pl.sc_m, 1, false, 32, 32, &tcm));
+            if (g.recon_xhat) CDG_TRY(make_map(g.recon_xhat, g.M, g.N, pl.sc_m, 1, false, 32, 32, &txh));
+            else txh = tcm;
+            r = launch_cta2<256, false, true>(ta, tb, tb2, tx, tcm, p, clusters, s, &txh);
+        } else if (BN == 304) r = pl.a_mn ? launch_cta2<304, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<304, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
         else if (BN == 256) r = pl.a_mn ? launch_cta2<256, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<256, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
         else r = pl.a_mn ? launch_cta2<160, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<160, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
     } else if (passes == 2 && BN == 256 && g.epi == EPI_RECON && p.vec && !pl.a_mn && !pl.b_mn && !no_stg && g.M < (1ll << 31) &&
