@@ -29,8 +29,8 @@ MACS_L = 3_778_800 * 2 + 92_400   # labeled sample: encoder fwd + wgrad + dgrad 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
 # `ncu --set full` capture (profiles/r01_ncu_enc0_fwd_bf3x_presplit.txt): encoder first Linear forward,
 # x[32768,12288] @ W0[300,12288]^T.  Algorithmic bytes of that launch: x once + W0 once (as bf16 hi + lo) + h1 written once.
-NCU_TRAFFIC = {"bytes": 1.826604e9 + 46.850048e6,
-               "launch": "gemm_tc_kernel<304,32,2,0,0> (bf16x3, pre-split weights) enc0 forward, M=32768 N=300 K=12288",
+NCU_TRAFFIC = {"bytes": 1.899331e9 + 47.327488e6,   # profiles/r01_ncu_gemm_cta2_final.txt, launch 0
+               "launch": "gemm_tc_kernel<304,32,2,0,0,0,1> (bf16x3, pre-split weights, CTA pairs) enc0 forward, M=32768 N=300 K=12288",
                "algorithmic": 32768 * 12288 * 4 + 300 * 12288 * 4 + 32768 * 300 * 4}
 
 

@@ -321,6 +321,59 @@ int cdg_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void*
 int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const void* b_hi, const void* b_lo, int64_t ld16, float* C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CDG-TVAE data transform, APPLY side: the step on either side of train_TVAE.
+ * Fitting (BayesianGaussianMixture, category discovery) stays on the host; its result arrives here as tables.
+ *
+ * cdg_tvae_transform replaces DataTransformer.transform (tabular/modules/data_transformer.py:163-182) =
+ *   per continuous column ClusterBasedNormalizer._transform (tabular/modules/numerical.py:407-445: GMM
+ *   responsibilities, +1e-6, renormalise, component drawn by inverse-cdf from ONE uniform per cell, value
+ *   (x - mean_c) / (4 std_c) clipped to +-0.99) laid out by _transform_continuous (data_transformer.py:111-125:
+ *   scalar, then one-hot of the component), per discrete column the one-hot of _transform_discrete (:127-129).
+ * cdg_tvae_inverse_transform replaces DataTransformer.inverse_transform (data_transformer.py:184-227) =
+ *   argmax of the component block, optional N(value, sigmas[start]) draw (:138-140), clip to +-1 and
+ *   value * 4 std_c + mean_c (numerical.py:447-457), rounding of integer-typed columns (numerical.py:175-177);
+ *   discrete columns: argmax -> category value.
+ * cdg_gumbel_argmax replaces the Cover_Type draw of tabular/inference_tvae.py:232-235, :250-253:
+ *   argmax_j( log_softmax(logits)_j + log(-log(U_j + 1e-20) + 1e-20) ), fp32, first maximum wins.
+ *
+ * All randomness is INJECTED (the reference draws it from NumPy's / torch's global generators on the host):
+ *   uniforms[cc * rows + r] / normals[cc * rows + r] for the cc-th CONTINUOUS column and row r, i.e. the order in
+ *   which the reference's column-by-column loop consumes its stream.  raw tables are float64 row-major (NumPy's
+ *   dtype in the reference), transformed tables fp32 row-major (what the training step reads).
+ * Per-cell arithmetic is fp64 so that component indices and values agree with the reference bit for bit.
+ * ---------------------------------------------------------------------------------------- */
+#define CDG_MAX_TCOL 16     /* raw columns of a table                         */
+#define CDG_MAX_TCOMP 10    /* GMM components (DataTransformer max_clusters)  */
+#define CDG_MAX_TCAT 16     /* categories of a discrete column                */
+enum { CDG_TCOL_CONTINUOUS = 0, CDG_TCOL_DISCRETE = 1 };
+typedef struct {
+    int32_t kind;                       /* CDG_TCOL_*                                                             */
+    int32_t out_start;                  /* first column of this raw column's block in the transformed table       */
+    int32_t n_all;                      /* continuous: components the mixture was fitted with (<= CDG_MAX_TCOMP)  */
+    int32_t n_valid;                    /* continuous: components kept (weight > threshold); discrete: categories */
+    int32_t valid_idx[CDG_MAX_TCOMP];   /* continuous: mixture index of the j-th kept component                   */
+    int32_t round_int;                  /* inverse: raw dtype is integer -> round half to even                    */
+    /* continuous: log( weight_k N(x; .) ) = log_a[k] - 0.5 * prec[k] * (x - mean[k])^2 for ALL n_all components
+     * (for sklearn's BayesianGaussianMixture: precisions_cholesky_^2 * degrees_of_freedom_ and the digamma terms of
+     * _estimate_log_weights / _estimate_log_prob folded into log_a by the host), std[k] = sqrt(covariances_[k]). */
+    double mean[CDG_MAX_TCOMP], std[CDG_MAX_TCOMP], prec[CDG_MAX_TCOMP], log_a[CDG_MAX_TCOMP];
+    double category[CDG_MAX_TCAT];      /* discrete: value of the j-th one-hot position                           */
+} cdg_tvae_column;
+typedef struct {
+    int32_t n_col;                      /* raw columns                       */
+    int32_t out_dim;                    /* transformed columns (sum of blocks) */
+    cdg_tvae_column col[CDG_MAX_TCOL];
+} cdg_tvae_transform_config;
+
+int cdg_tvae_transform(const cdg_tvae_transform_config* cfg, const double* raw, int64_t ld_raw, const double* uniforms,
+                       int64_t rows, float* out, int64_t ld_out, void* stream);
+/* sigmas (fp32 [out_dim]) and normals may both be NULL: no draw, as inverse_transform(data) without sigmas. */
+int cdg_tvae_inverse_transform(const cdg_tvae_transform_config* cfg, const float* data, int64_t ld_data, const float* sigmas,
+                               const double* normals, int64_t rows, double* raw_out, int64_t ld_raw, void* stream);
+int cdg_gumbel_argmax(const float* logits, int64_t ld, int32_t n_class, const float* uniforms, int64_t rows,
+                      int64_t* out_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
