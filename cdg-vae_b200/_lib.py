@@ -111,6 +111,20 @@ class CelebaIO(C.Structure):
                 ("latent_in", C.c_void_p), ("epsilon2_in", C.c_void_p)]
 
 
+MAX_TCOL, MAX_TCOMP, MAX_TCAT = 16, 10, 16
+
+
+class TvaeColumn(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("out_start", C.c_int32), ("n_all", C.c_int32), ("n_valid", C.c_int32),
+                ("valid_idx", C.c_int32 * MAX_TCOMP), ("round_int", C.c_int32), ("mean", C.c_double * MAX_TCOMP),
+                ("std", C.c_double * MAX_TCOMP), ("prec", C.c_double * MAX_TCOMP), ("log_a", C.c_double * MAX_TCOMP),
+                ("category", C.c_double * MAX_TCAT)]
+
+
+class TvaeTransformConfig(C.Structure):
+    _fields_ = [("n_col", C.c_int32), ("out_dim", C.c_int32), ("col", TvaeColumn * MAX_TCOL)]
+
+
 # every symbol include/cdgvae.h declares
 EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
@@ -118,7 +132,8 @@ EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
-           "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit"]
+           "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit", "cdg_tvae_transform", "cdg_tvae_inverse_transform",
+           "cdg_gumbel_argmax"]
 
 _lib = None
 
@@ -176,6 +191,11 @@ def lib():
     L.cdg_split_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.cdg_gemm_bsplit.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    L.cdg_tvae_transform.argtypes = [C.POINTER(TvaeTransformConfig), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_tvae_inverse_transform.argtypes = [C.POINTER(TvaeTransformConfig), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_gumbel_argmax.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -1,0 +1,296 @@
+// CDG-TVAE data transform, apply side: mode-specific normalisation of a raw table and its inverse.
+//   forward : tabular/modules/data_transformer.py:163-182 (transform), :111-129 (per-column layout),
+//             tabular/modules/numerical.py:407-445 (ClusterBasedNormalizer._transform)
+//   inverse : tabular/modules/data_transformer.py:184-227, :131-147; tabular/modules/numerical.py:447-457, :175-177
+//   gumbel  : tabular/inference_tvae.py:232-235, :250-253
+// HBM-bound byte work: a block stages a tile of TILE_ROWS table rows in shared memory so that both the raw table
+// (fp64 row-major) and the transformed table (fp32 row-major) move as fully coalesced 16-byte accesses; inside the tile a
+// warp works on 32 consecutive rows of ONE raw column, so the injected random stream (column-major, the order in which
+// the reference's column loop draws it) is read coalesced and the per-column tables are warp-uniform.
+// Per-cell arithmetic is fp64: the component index is an inverse-cdf search and must agree with NumPy's float64 result.
+#include "common.cuh"
+
+namespace cdg {
+namespace {
+
+constexpr int TILE_ROWS = 128;
+constexpr int TT_THREADS = 256;
+
+struct TransformArgs {
+    cdg_tvae_transform_config c;
+    int32_t cont_index[CDG_MAX_TCOL];   // position of a continuous column in the injected random stream
+    const double* raw; int64_t ld_raw;
+    const double* rnd;                  // uniforms (forward) / standard normals (inverse), [n_cont][rows]
+    const float* data; int64_t ld_data; // transformed table (inverse input)
+    const float* sigmas;
+    float* out; int64_t ld_out;
+    double* raw_out;
+    int64_t rows;
+    int raw_pitch;                      // doubles per staged raw row (odd: conflict-free column walks)
+};
+
+// Copy a [n_rows, width] tile between global (row stride ld) and shared (row stride pitch) memory, 16-byte accesses when
+// the global tile is one contiguous, aligned run.
+template <typename T, bool TO_SHARED>
+__device__ __forceinline__ void tile_copy(T* sh, int pitch, T* gl, int64_t ld, int n_rows, int width) {
+    constexpr int V = 16 / sizeof(T);
+    const int64_t total = (int64_t)n_rows * width;
+    if (ld == width && pitch == width && (reinterpret_cast<uintptr_t>(gl) & 15) == 0) {
+        const int64_t nv = total / V;
+        for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+            if (TO_SHARED) reinterpret_cast<int4*>(sh)[i] = __ldg(reinterpret_cast<const int4*>(gl) + i);
+            else reinterpret_cast<int4*>(gl)[i] = reinterpret_cast<const int4*>(sh)[i];
+        }
+        for (int64_t i = nv * V + threadIdx.x; i < total; i += blockDim.x) {
+            if (TO_SHARED) sh[i] = gl[i]; else gl[i] = sh[i];
+        }
+        return;
+    }
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
+        if (TO_SHARED) sh[r * pitch + c] = gl[r * ld + c]; else gl[r * ld + c] = sh[r * pitch + c];
+    }
+}
+
+// numerical.py:407-445 for one cell.  Returns the kept-component index and the clipped normalised value.
+__device__ __forceinline__ void cbn_cell(const cdg_tvae_column& col, double x, double u, int& comp, double& value) {
+    // sklearn BaseMixture.predict_proba: exp(weighted_log_prob - logsumexp(weighted_log_prob)) over ALL fitted components
+    double lp[CDG_MAX_TCOMP];
+    double m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
+        if (k < col.n_all) {
+            const double d = x - col.mean[k];
+            lp[k] = col.log_a[k] - 0.5 * (d * d * col.prec[k]);
+            m = fmax(m, lp[k]);
+        }
+    }
+    // responsibilities exp(lp - logsumexp(lp)) evaluated as exp(lp - max) / sum: one exp per component, no log
+    // (differs from sklearn's form by rounding only; the component draw below is an interval test on the cdf)
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < CDG_MAX_TCOMP; ++k)
+        if (k < col.n_all) { lp[k] = exp(lp[k] - m); s += lp[k]; }
+    const double inv_s = 1.0 / s;
+    // numerical.py:424-434: keep the valid components, + 1e-6, renormalise, then np.random.choice(p=...) =
+    // cdf = cumsum(p); cdf /= cdf[-1]; index = searchsorted(cdf, u, side='right')
+    double p[CDG_MAX_TCOMP];
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j) {
+        if (j < col.n_valid) {
+            p[j] = lp[col.valid_idx[j]] * inv_s + 1e-6;
+            tot += p[j];
+        }
+    }
+    double run = 0.0, last = 0.0;
+#pragma unroll
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j)
+        if (j < col.n_valid) { p[j] = p[j] / tot; last += p[j]; }
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j) {
+        if (j < col.n_valid) {
+            run += p[j];
+            idx += (run / last <= u) ? 1 : 0;   // side='right': count cdf entries <= u
+        }
+    }
+    comp = idx < col.n_valid ? idx : col.n_valid - 1;
+    const int k = col.valid_idx[comp];
+    double v = __ddiv_rn(__dsub_rn(x, col.mean[k]), __dmul_rn(4.0, col.std[k]));   // STD_MULTIPLIER = 4 (numerical.py:365)
+    value = fmin(fmax(v, -0.99), 0.99);
+}
+
+__global__ void __launch_bounds__(TT_THREADS) tvae_transform_kernel(const __grid_constant__ TransformArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = a.c.n_col, D = a.c.out_dim;
+    double* sraw = reinterpret_cast<double*>(smem_raw);
+    float* sout = reinterpret_cast<float*>(sraw + (size_t)TILE_ROWS * a.raw_pitch);
+    const int64_t n_tiles = (a.rows + TILE_ROWS - 1) / TILE_ROWS;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * TILE_ROWS;
+        const int nr = (int)min((int64_t)TILE_ROWS, a.rows - r0);
+        __syncthreads();   // previous tile's stores are done with the staging buffers
+        if (a.ld_raw == C) {
+            // contiguous rows: coalesced 16-byte loads, then scattered into the odd-pitch staging rows
+            const int64_t total = (int64_t)nr * C;
+            const double* g = a.raw + r0 * a.ld_raw;
+            for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+                const int r = (int)(i / C), c = (int)(i - (int64_t)r * C);
+                sraw[r * a.raw_pitch + c] = __ldg(g + i);
+            }
+        } else {
+            tile_copy<double, true>(sraw, a.raw_pitch, const_cast<double*>(a.raw + r0 * a.ld_raw), a.ld_raw, nr, C);
+        }
+        for (int i = threadIdx.x; i < nr * D; i += blockDim.x) sout[i] = 0.f;
+        __syncthreads();
+        // cell (column, row): a warp covers 32 consecutive rows of one column (TILE_ROWS is a multiple of 32)
+        for (int cell = threadIdx.x; cell < C * TILE_ROWS; cell += blockDim.x) {
+            const int c = cell / TILE_ROWS, r = cell - c * TILE_ROWS;
+            if (r >= nr) continue;
+            const cdg_tvae_column& col = a.c.col[c];
+            const double x = sraw[r * a.raw_pitch + c];
+            float* o = sout + r * D + col.out_start;
+            if (col.kind == CDG_TCOL_CONTINUOUS) {
+                const double u = __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + r);
+                int comp; double v;
+                cbn_cell(col, x, u, comp, v);
+                o[0] = (float)v;
+                o[1 + comp] = 1.f;            // data_transformer.py:121-123
+            } else {
+                for (int j = 0; j < col.n_valid; ++j) o[j] = (x == col.category[j]) ? 1.f : 0.f;
+            }
+        }
+        __syncthreads();
+        tile_copy<float, false>(sout, D, a.out + r0 * a.ld_out, a.ld_out, nr, D);
+    }
+}
+
+__global__ void __launch_bounds__(TT_THREADS) tvae_inverse_kernel(const __grid_constant__ TransformArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = a.c.n_col, D = a.c.out_dim;
+    double* sraw = reinterpret_cast<double*>(smem_raw);
+    float* sdat = reinterpret_cast<float*>(sraw + (size_t)TILE_ROWS * C);
+    const int64_t n_tiles = (a.rows + TILE_ROWS - 1) / TILE_ROWS;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * TILE_ROWS;
+        const int nr = (int)min((int64_t)TILE_ROWS, a.rows - r0);
+        __syncthreads();
+        tile_copy<float, true>(sdat, D, const_cast<float*>(a.data + r0 * a.ld_data), a.ld_data, nr, D);
+        __syncthreads();
+        for (int cell = threadIdx.x; cell < C * TILE_ROWS; cell += blockDim.x) {
+            const int c = cell / TILE_ROWS, r = cell - c * TILE_ROWS;
+            if (r >= nr) continue;
+            const cdg_tvae_column& col = a.c.col[c];
+            const float* d = sdat + r * D + col.out_start;
+            double res;
+            if (col.kind == CDG_TCOL_CONTINUOUS) {
+                // data_transformer.py:134-140: component = argmax of the one-hot block (first maximum), optional draw
+                int best = 0; float bv = d[1];
+                for (int j = 1; j < col.n_valid; ++j) if (d[1 + j] > bv) { bv = d[1 + j]; best = j; }
+                double v = (double)d[0];
+                if (a.sigmas != nullptr && a.rnd != nullptr)
+                    v = __dadd_rn(v, __dmul_rn((double)__ldg(a.sigmas + col.out_start),      // no FMA contraction: NumPy rounds
+                                               __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + r)));   // the product first
+                v = fmin(fmax(v, -1.0), 1.0);                       // numerical.py:448
+                const int k = col.valid_idx[best];
+                res = __dadd_rn(__dmul_rn(__dmul_rn(v, 4.0), col.std[k]), col.mean[k]);   // numerical.py:453-455, left to right, no FMA
+                if (col.round_int) res = rint(res);                 // numerical.py:175-177 (np.round: half to even)
+            } else {
+                int best = 0; float bv = d[0];
+                for (int j = 1; j < col.n_valid; ++j) if (d[j] > bv) { bv = d[j]; best = j; }
+                res = col.category[best];
+            }
+            sraw[r * C + c] = res;
+        }
+        __syncthreads();
+        tile_copy<double, false>(sraw, C, a.raw_out + r0 * a.ld_raw, a.ld_raw, nr, C);
+    }
+}
+
+// inference_tvae.py:232-235, :250-253 — one row per thread (n_class <= 16), fp32 like the reference's torch ops.
+__global__ void gumbel_argmax_kernel(const float* __restrict__ logits, int64_t ld, int n_class, const float* __restrict__ U,
+                                     int64_t rows, int64_t* __restrict__ out) {
+    const float eps = 1e-20f;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const float* x = logits + r * ld;
+        float m = x[0];
+        for (int j = 1; j < n_class; ++j) m = fmaxf(m, x[j]);
+        float s = 0.f;
+        for (int j = 0; j < n_class; ++j) s += expf(x[j] - m);
+        const float ls = logf(s);
+        int best = 0; float bv = -INFINITY;
+        for (int j = 0; j < n_class; ++j) {
+            const float g = logf(-logf(U[r * n_class + j] + eps) + eps);   // the reference's sign: log(-log U)
+            const float v = (x[j] - m - ls) + g;
+            if (v > bv) { bv = v; best = j; }
+        }
+        out[r] = best;
+    }
+}
+
+int check_config(const cdg_tvae_transform_config* cfg, TransformArgs& a) {
+    CDG_REQUIRE(cfg != nullptr, "tvae transform: null config");
+    CDG_REQUIRE(cfg->n_col >= 1 && cfg->n_col <= CDG_MAX_TCOL, "tvae transform: n_col %d out of range", cfg->n_col);
+    int start = 0, nc = 0;
+    for (int c = 0; c < cfg->n_col; ++c) {
+        const cdg_tvae_column& col = cfg->col[c];
+        CDG_REQUIRE(col.out_start == start, "tvae transform: column %d starts at %d, expected %d", c, col.out_start, start);
+        if (col.kind == CDG_TCOL_CONTINUOUS) {
+            CDG_REQUIRE(col.n_all >= 1 && col.n_all <= CDG_MAX_TCOMP && col.n_valid >= 1 && col.n_valid <= col.n_all,
+                        "tvae transform: column %d has %d / %d components", c, col.n_valid, col.n_all);
+            for (int j = 0; j < col.n_valid; ++j)
+                CDG_REQUIRE(col.valid_idx[j] >= 0 && col.valid_idx[j] < col.n_all, "tvae transform: column %d bad component index", c);
+            a.cont_index[c] = nc++;
+            start += 1 + col.n_valid;
+        } else if (col.kind == CDG_TCOL_DISCRETE) {
+            CDG_REQUIRE(col.n_valid >= 1 && col.n_valid <= CDG_MAX_TCAT, "tvae transform: column %d has %d categories", c, col.n_valid);
+            a.cont_index[c] = -1;
+            start += col.n_valid;
+        } else {
+            CDG_REQUIRE(false, "tvae transform: column %d has unknown kind %d", c, col.kind);
+        }
+    }
+    CDG_REQUIRE(cfg->out_dim == start, "tvae transform: out_dim %d, blocks sum to %d", cfg->out_dim, start);
+    a.c = *cfg;
+    return CDG_OK;
+}
+
+unsigned tile_grid(int64_t rows, size_t smem) {
+    const int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    int per_sm = (int)imin64(8, (int64_t)(200 * 1024) / (int64_t)(smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    return (unsigned)imax64(1, imin64(tiles, (int64_t)kNumSMs * per_sm));
+}
+
+}  // namespace
+}  // namespace cdg
+
+using namespace cdg;
+
+extern "C" int cdg_tvae_transform(const cdg_tvae_transform_config* cfg, const double* raw, int64_t ld_raw, const double* uniforms,
+                                  int64_t rows, float* out, int64_t ld_out, void* stream) {
+    TransformArgs a{};
+    CDG_TRY(check_config(cfg, a));
+    CDG_REQUIRE(rows >= 0 && ld_raw >= cfg->n_col && ld_out >= cfg->out_dim, "tvae transform: bad extents");
+    if (rows == 0) return CDG_OK;
+    CDG_REQUIRE(raw && out, "tvae transform: null table pointer");
+    bool any_cont = false;
+    for (int c = 0; c < cfg->n_col; ++c) any_cont |= cfg->col[c].kind == CDG_TCOL_CONTINUOUS;
+    CDG_REQUIRE(!any_cont || uniforms, "tvae transform: continuous columns need the injected uniforms");
+    a.raw = raw; a.ld_raw = ld_raw; a.rnd = uniforms; a.out = out; a.ld_out = ld_out; a.rows = rows;
+    a.raw_pitch = cfg->n_col | 1;
+    const size_t smem = (size_t)TILE_ROWS * a.raw_pitch * sizeof(double) + (size_t)TILE_ROWS * cfg->out_dim * sizeof(float);
+    CDG_CHECK_CUDA(cudaFuncSetAttribute(tvae_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tvae_transform_kernel<<<tile_grid(rows, smem), TT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+extern "C" int cdg_tvae_inverse_transform(const cdg_tvae_transform_config* cfg, const float* data, int64_t ld_data,
+                                          const float* sigmas, const double* normals, int64_t rows, double* raw_out,
+                                          int64_t ld_raw, void* stream) {
+    TransformArgs a{};
+    CDG_TRY(check_config(cfg, a));
+    CDG_REQUIRE(rows >= 0 && ld_raw >= cfg->n_col && ld_data >= cfg->out_dim, "tvae inverse transform: bad extents");
+    CDG_REQUIRE((sigmas == nullptr) == (normals == nullptr), "tvae inverse transform: sigmas and normals go together");
+    if (rows == 0) return CDG_OK;
+    CDG_REQUIRE(data && raw_out, "tvae inverse transform: null table pointer");
+    a.data = data; a.ld_data = ld_data; a.sigmas = sigmas; a.rnd = normals; a.raw_out = raw_out; a.ld_raw = ld_raw; a.rows = rows;
+    const size_t smem = (size_t)TILE_ROWS * cfg->n_col * sizeof(double) + (size_t)TILE_ROWS * cfg->out_dim * sizeof(float);
+    CDG_CHECK_CUDA(cudaFuncSetAttribute(tvae_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tvae_inverse_kernel<<<tile_grid(rows, smem), TT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
+extern "C" int cdg_gumbel_argmax(const float* logits, int64_t ld, int32_t n_class, const float* uniforms, int64_t rows,
+                                 int64_t* out_index, void* stream) {
+    CDG_REQUIRE(n_class >= 1 && n_class <= 64 && ld >= n_class && rows >= 0, "gumbel argmax: bad extents");
+    if (rows == 0) return CDG_OK;
+    CDG_REQUIRE(logits && uniforms && out_index, "gumbel argmax: null pointer");
+    const unsigned blocks = (unsigned)imax64(1, imin64((rows + 255) / 256, (int64_t)kNumSMs * 8));
+    gumbel_argmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, ld, n_class, uniforms, rows, out_index);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}

@@ -30,10 +30,11 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     """ctypes mirrors vs the C compiler's view of include/cdgvae.h."""
     import subprocess, tempfile
-    src = '#include "cdgvae.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include "cdgvae.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(cdg_linear),sizeof(cdg_adam_args),sizeof(cdg_pendulum_config),sizeof(cdg_pendulum_io),' \
           'sizeof(cdg_pendulum_fwd_io),sizeof(cdg_tabular_config),sizeof(cdg_tabular_io),sizeof(cdg_conv),sizeof(cdg_bnorm),' \
-          'sizeof(cdg_gen_block),sizeof(cdg_generator),sizeof(cdg_res_block),sizeof(cdg_celeba_config),sizeof(cdg_celeba_io));return 0;}'
+          'sizeof(cdg_gen_block),sizeof(cdg_generator),sizeof(cdg_res_block),sizeof(cdg_celeba_config),sizeof(cdg_celeba_io),' \
+          'sizeof(cdg_tvae_column),sizeof(cdg_tvae_transform_config));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
         open(c, "w").write(src)
@@ -42,7 +43,8 @@ def test_struct_sizes_match_header():
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     mine = [ctypes.sizeof(t) for t in (_lib.Linear, _lib.AdamArgs, _lib.PendulumConfig, _lib.PendulumIO,
                                        _lib.PendulumFwdIO, _lib.TabularConfig, _lib.TabularIO, _lib.Conv, _lib.BNorm, _lib.GenBlock,
-                                       _lib.GeneratorDesc, _lib.ResBlock, _lib.CelebaConfig, _lib.CelebaIO)]
+                                       _lib.GeneratorDesc, _lib.ResBlock, _lib.CelebaConfig, _lib.CelebaIO, _lib.TvaeColumn,
+                                       _lib.TvaeTransformConfig)]
     assert sizes == mine
 
 
