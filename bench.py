@@ -105,13 +105,19 @@ def synth(batch, batch_l, seed):
 def synth_device(batch, batch_l, seed, dev):
     """Same distribution as synth(), generated on the device (a 131072-image batch is 6.4 GB: building it on the
     host would cost tens of seconds and a second host copy per rank)."""
+    from cdgvae_b200 import _lib
     g = torch.Generator(device=dev).manual_seed(seed)
-    x = torch.rand(batch, 64, 64, 3, device=dev, generator=g) * 2 - 1
-    x.masked_fill_(torch.rand(batch, 64, 64, 3, device=dev, generator=g) < 0.9, 1.0)
+    # image bytes as the pendulum PNGs hold them (modules/datasets.py:24-27): 90 % white (255), the rest uniform
+    xu8 = torch.randint(0, 256, (batch, 64, 64, 3), dtype=torch.uint8, device=dev, generator=g)
+    xu8.masked_fill_(torch.rand(batch, 64, 64, 3, device=dev, generator=g) < 0.9, 255)
+    x = torch.empty(batch, 64, 64, 3, device=dev)
+    _lib.check(_lib.lib().cdg_pixels_to_float(xu8.data_ptr(), xu8.numel(), x.data_ptr(),          # datasets.py:28
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    xlu8 = xu8[:batch_l].roll(1, 0).contiguous()
     xl = x[:batch_l].roll(1, 0).contiguous()
     yl = torch.rand(batch_l, 5, device=dev, generator=g)
     noise = torch.randn(batch, 4, device=dev, generator=g)
-    return x, xl, yl, noise
+    return x, xl, yl, noise, xu8, xlu8
 
 
 def cpu_baseline(threads, target_s=12.0, batch=1024, batch_l=256):
@@ -215,7 +221,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(os.cpu_count() or 1)
 
-    xd, xld, yld, nd = synth_device(B, BL, 1234 + rank, dev)
+    xd, xld, yld, nd, xu8, xlu8 = synth_device(B, BL, 1234 + rank, dev)
     model.noise_fn = lambda n, d: nd
 
     def barrier():
@@ -257,24 +263,35 @@ def main():
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t)
             return h
-        xp, xlp, ylp, noise_p = pinned(xd), pinned(xld), pinned(yld), pinned(nd)
-        h2d = xp.numel() * 4 + xlp.numel() * 4 + ylp.numel() * 4 + noise_p.numel() * 4
+        ylp, noise_p = pinned(yld), pinned(nd)
         model.noise_fn = lambda n, d: noise_p                     # CPU noise, copied H2D per step (model.py:276)
-        def run(k):
-            return train_CDGVAE_semi_loaders(DevicePrefetcher([(xlp, ylp)] * k, dev), DevicePrefetcher([xp] * k, dev),
-                                             model, cfg, opt, dev)
-        run(2)
-        barrier()
-        e0.record()
-        logs, _ = run(args.steps)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * args.steps / (float(t) / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4 * 8, "ms_per_step": float(t) / args.steps,
-               "api": "cdgvae_b200.modules.train.train_CDGVAE_semi_loaders + data.DevicePrefetcher (pinned host batches)"}
+
+        def measure(xs, xls, pixels):
+            def run(k):
+                return train_CDGVAE_semi_loaders(DevicePrefetcher([(xls, ylp)] * k, dev, pixels=pixels),
+                                                 DevicePrefetcher([xs] * k, dev, pixels=pixels), model, cfg, opt, dev)
+            run(2)
+            barrier()
+            e0.record()
+            run(args.steps)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            h2d = xs.numel() * xs.element_size() + xls.numel() * xls.element_size() + ylp.numel() * 4 + noise_p.numel() * 4
+            return {"value": B * world * args.steps / (float(t) / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4 * 8, "ms_per_step": float(t) / args.steps}
+
+        # headline: the host holds the images as the dataset stores them (uint8 pixels, modules/datasets.py:24-27); the
+        # (p - 127.5) / 127.5 of datasets.py:28 runs on the device (cdg_pixels_to_float), bit-identical fp32 batches
+        e2e = measure(pinned(xu8), pinned(xlu8), True)
+        e2e["api"] = ("cdgvae_b200.modules.train.train_CDGVAE_semi_loaders + data.DevicePrefetcher(pixels=True): pinned host "
+                      "batches of uint8 image bytes, converted on the device exactly as modules/datasets.py:28 does on the host")
+        # the same with the host holding the already converted fp32 images (4 bytes per pixel over PCIe)
+        e2e_fp32 = measure(pinned(xd), pinned(xld), False)
+        e2e_fp32["api"] = "same call, data.DevicePrefetcher over pinned fp32 host batches"
+        e2e["fp32_host_batches"] = e2e_fp32
 
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()

@@ -29,10 +29,15 @@ def _rebuild(item, it):
 class DevicePrefetcher:
     """Wrap any iterable of (nested tuples of) host tensors; yields the same structure on `device`.
     Pinned host tensors make the copies truly asynchronous.  The yielded tensors are only valid until the
-    third-next batch is requested (they are views of the staging ring)."""
+    third-next batch is requested (they are views of the staging ring).
 
-    def __init__(self, iterable, device, depth=3):
-        self.iterable, self.device, self.depth = iterable, torch.device(device), depth
+    pixels=True: uint8 tensors are image bytes in the dataset's native format (what modules/datasets.py:24-27 reads
+    from the PNGs).  They cross PCIe as bytes (1 instead of 4 per pixel) and are converted on the device, on the copy
+    stream, by `cdg_pixels_to_float` — the same `(p - 127.5) / 127.5` in float64 rounded to fp32 that the reference's
+    dataset applies on the host (datasets.py:28, :42) — so the consumer sees bit-identical fp32 batches."""
+
+    def __init__(self, iterable, device, depth=3, pixels=False):
+        self.iterable, self.device, self.depth, self.pixels = iterable, torch.device(device), depth, pixels
 
     def __len__(self):
         return len(self.iterable)
@@ -42,6 +47,7 @@ class DevicePrefetcher:
         side = torch.cuda.Stream(dev)
         ring = [None] * depth          # per slot: list of device buffers
         done = [None] * depth          # per slot: event after which the slot may be overwritten
+        decoded = [None] * depth       # per slot: fp32 buffers of the uint8 leaves (pixels=True), else None
         it = iter(self.iterable)
         count = 0
 
@@ -57,14 +63,20 @@ class DevicePrefetcher:
             bufs = ring[slot]
             if bufs is None or len(bufs) != len(src) or any(b.shape != s.shape or b.dtype != s.dtype for b, s in zip(bufs, src)):
                 bufs = ring[slot] = [torch.empty(s.shape, dtype=s.dtype, device=dev) for s in src]
+                decoded[slot] = [torch.empty(s.shape, dtype=torch.float32, device=dev)
+                                 if (self.pixels and s.dtype == torch.uint8) else None for s in src]
+            outs = [b if d is None else d for b, d in zip(bufs, decoded[slot])]
             with torch.cuda.stream(side):
                 if done[slot] is not None:
                     side.wait_event(done[slot])
-                for b, s in zip(bufs, src):
+                for b, d, s in zip(bufs, decoded[slot], src):
                     b.copy_(s, non_blocking=True)
+                    if d is not None:
+                        from . import _lib
+                        _lib.check(_lib.lib().cdg_pixels_to_float(b.data_ptr(), b.numel(), d.data_ptr(), side.cuda_stream))
                 ev = torch.cuda.Event()
                 ev.record(side)
-            return _rebuild(item, iter(bufs)), ev, slot
+            return _rebuild(item, iter(outs)), ev, slot
 
         nxt = load()
         prev_slot = None

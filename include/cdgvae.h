@@ -374,6 +374,14 @@ int cdg_tvae_inverse_transform(const cdg_tvae_transform_config* cfg, const float
 int cdg_gumbel_argmax(const float* logits, int64_t ld, int32_t n_class, const float* uniforms, int64_t rows,
                       int64_t* out_index, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Image bytes -> training-step input.  Replaces the host-side conversion of modules/datasets.py:28, :57
+ * (`(np.array(train_x).astype(float) - 127.5) / 127.5`, float64) + `torch.FloatTensor(...)` (:42, :64): out[i] =
+ * (float)(((double)pixels[i] - 127.5) / 127.5), bit-identical, so that the dataset's native bytes (1 per pixel instead
+ * of 4) are what crosses PCIe every step (data.py::DevicePrefetcher(pixels=True)).
+ * ---------------------------------------------------------------------------------------- */
+int cdg_pixels_to_float(const uint8_t* pixels, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,3 +241,43 @@ def test_gpu_transform_fullsize_properties():
     err = (back[:, :7] - raw_d[:, :7]).abs()
     assert float(err[unclipped].max()) < 1e-5
     assert float(unclipped.double().mean()) > 0.8
+
+
+# ------------------------------------------------------------------------------------------------------------
+# image bytes -> fp32 (modules/datasets.py:28, :42) and the prefetcher's pixel mode
+# ------------------------------------------------------------------------------------------------------------
+def _reference_pixels(u8):
+    """modules/datasets.py:28 + :42, literally: float64 arithmetic, then torch.FloatTensor."""
+    return torch.FloatTensor((np.asarray(u8).astype(float) - 127.5) / 127.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 15, 256, 4097, 3 * 64 * 64 * 5])
+def test_gpu_pixels_to_float_bit_exact(n):
+    from cdgvae_b200 import _lib
+    g = torch.Generator().manual_seed(n)
+    u8 = torch.arange(256, dtype=torch.uint8) if n == 256 else torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
+    d = u8.cuda()
+    out = torch.empty(n, device="cuda")
+    _lib.check(_lib.lib().cdg_pixels_to_float(d.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(out.cpu(), _reference_pixels(u8.numpy()))
+    if n > 16:                                                              # unaligned views take the scalar kernel
+        out2 = torch.empty(n, device="cuda")
+        _lib.check(_lib.lib().cdg_pixels_to_float(d.data_ptr() + 1, n - 1, out2.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert torch.equal(out2[:n - 1].cpu(), _reference_pixels(u8.numpy()[1:]))
+
+
+@pytest.mark.gpu
+def test_gpu_prefetcher_pixel_mode_yields_reference_batches():
+    from cdgvae_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randint(0, 256, (5, 8, 8, 3), dtype=torch.uint8, generator=g).pin_memory(), torch.rand(5, 5, generator=g))
+               for _ in range(7)]
+    seen = 0
+    for (x, y), (xh, yh) in zip(DevicePrefetcher(batches, "cuda", pixels=True), batches):
+        assert x.dtype == torch.float32 and x.is_cuda and torch.equal(x.cpu(), _reference_pixels(xh.numpy()))
+        assert torch.equal(y.cpu(), yh)
+        seen += 1
+    assert seen == 7
+    for (x, y), (xh, yh) in zip(DevicePrefetcher(batches, "cuda"), batches):     # default: bytes stay bytes
+        assert x.dtype == torch.uint8 and torch.equal(x.cpu(), xh)
