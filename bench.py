@@ -267,21 +267,50 @@ def main():
         model.noise_fn = lambda n, d: noise_p                     # CPU noise, copied H2D per step (model.py:276)
 
         def measure(xs, xls, pixels):
-            def run(k):
+            class Marked:                # starts the clock on the compute stream when step `at` is about to be enqueued
+                exact_len = True
+
+                def __init__(self, loader, at):
+                    self.loader, self.at = loader, at
+
+                def __len__(self):
+                    return len(self.loader)
+
+                def __iter__(self):
+                    for i, b in enumerate(self.loader):
+                        if i == self.at:
+                            e0.record()
+                        yield b
+
+            def run(k, mark_at=None):
+                pu = DevicePrefetcher([xs] * k, dev, pixels=pixels)
                 return train_CDGVAE_semi_loaders(DevicePrefetcher([(xls, ylp)] * k, dev, pixels=pixels),
-                                                 DevicePrefetcher([xs] * k, dev, pixels=pixels), model, cfg, opt, dev)
-            run(2)
+                                                 Marked(pu, mark_at) if mark_at is not None else pu, model, cfg, opt, dev)
+
+            def reduce_ms():
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t)
+            # steady state: ONE loop of W + K steps, every step with its own H2D copy; the clock starts after the W warm-up
+            # steps (pipeline full, as in any epoch longer than a few steps) and stops when the logs are back on the host
+            barrier()
+            run(W + args.steps, mark_at=W)
+            e1.record()
+            barrier()
+            warm = reduce_ms()
+            # cold: K steps from an empty pipeline (the first copy cannot overlap anything)
             barrier()
             e0.record()
             run(args.steps)
             e1.record()
             barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cold = reduce_ms()
             h2d = xs.numel() * xs.element_size() + xls.numel() * xls.element_size() + ylp.numel() * 4 + noise_p.numel() * 4
-            return {"value": B * world * args.steps / (float(t) / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4 * 8, "ms_per_step": float(t) / args.steps}
+            return {"value": B * world * args.steps / (warm / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4 * 8, "ms_per_step": warm / args.steps,
+                    "timed_region": f"steps {W + 1}..{W + args.steps} of one {W + args.steps}-step loop (pipeline warm)",
+                    "cold_start_ms_per_step": cold / args.steps}
 
         # headline: the host holds the images as the dataset stores them (uint8 pixels, modules/datasets.py:24-27); the
         # (p - 127.5) / 127.5 of datasets.py:28 runs on the device (cdg_pixels_to_float), bit-identical fp32 batches

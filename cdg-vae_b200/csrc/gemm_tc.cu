@@ -72,6 +72,7 @@ struct Params {
     int a16swap;                                // experiment switch: order of the two bf16 in a packed TMEM column
     int b_pre;                                  // bf16x3: B arrives pre-split (hi / lo bf16 tiles by TMA, no conversion)
     int sw32;                                   // bf16x3: bf16 tiles as two K = 16 sub-tiles of 32-byte rows (SWIZZLE_32B)
+    int tr;                                     // fused reconstruction head: transposing (row-coalesced) epilogue
     int conv_cb, conv_W, conv_H, conv_k;        // implicit-GEMM convolution: K-blocks per tap (0 = plain GEMM), extent, kernel
 };
 
@@ -288,7 +289,7 @@ __device__ __forceinline__ uint32_t sw_chunk(uint32_t r, uint32_t chunk) {
 // 32 rows x 32 floats (SWIZZLE_128B) moved by TMA, paid for with one ring stage.
 constexpr int EPI_NOUT = 2, EPI_CHUNK_BYTES = 32 * 128;
 
-template <int BN, int BK, int PASSES = 3, bool STG = false, bool CTA2 = false>
+template <int BN, int BK, int PASSES = 3, bool STG = false, bool CTA2 = false, bool TR = false>
 struct Cfg {
     // PASSES == 2 is the bf16x3 arithmetic (see the BF3X notes at the converter): the raw fp32 tile is converted IN PLACE
     // into a hi and a lo bf16 tile (a 128-byte fp32 row becomes two 64-byte bf16 rows), so a stage holds one copy of
@@ -306,7 +307,11 @@ struct Cfg {
     static constexpr int STAGE_BYTES = BF3X ? (A_BYTES + B_CTA_BYTES) : 2 * (A_BYTES + B_BYTES);  // hi + lo for both operands
     static constexpr int BIAS_LD = 320;                               // epilogue's bias tile (two tiles in flight)
     static constexpr int BIAS_BYTES = STG ? 0 : 2 * BIAS_LD * 4;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 384 /*barriers*/ + BIAS_BYTES;
+    // transposing epilogue of the fused reconstruction head (256-wide tiles): one 32 x 33 float scratch per epilogue warp
+    static constexpr int TR_LD = 33;
+    static constexpr int TR_BYTES = TR ? NUM_EPI_WARPS * 32 * TR_LD * 4 : 0;
+    static_assert(!TR || (!STG && BN % 32 == 0 && NUM_EPI_WARPS == 4), "transposing epilogue: whole 32-column chunks, one warp per lane quarter");
+    static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 384 /*barriers*/ + BIAS_BYTES + TR_BYTES;
     static_assert(!STG || (BF3X && BN % 32 == 0 && NUM_EPI_WARPS == 4), "staged epilogue: bf16x3 tiles, one warp per lane quarter");
     static constexpr int B_ROWS_PER_BOX = BN <= 256 ? BN : BN / 2;  // K-major TMA box rows (<= 256)
     static constexpr int B_CW = BN <= 128 ? BN : (BN % 128 == 0 ? 128 : (BN == 160 ? 80 : BN / 4));   // MN-major chunk width (<= 128)
@@ -601,12 +606,12 @@ __device__ __forceinline__ float epi_scalar(const Params& p, float val, int64_t 
     return val;
 }
 
-template <int BN, int BK, int PASSES, bool A_MN, bool B_MN, bool STG = false, bool CTA2 = false>
+template <int BN, int BK, int PASSES, bool A_MN, bool B_MN, bool STG = false, bool CTA2 = false, bool TR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmX,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmXh, const Params p) {
-    using C_ = Cfg<BN, BK, PASSES, STG, CTA2>;
+    using C_ = Cfg<BN, BK, PASSES, STG, CTA2, TR>;
     constexpr int EPI_NIN = C_::EPI_NIN;
     // CTA pairs: cluster c = blockIdx.x / 2 owns work items c, c + #clusters, ...; a work item covers TWO 128-row blocks
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -624,6 +629,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // bars[0..S) full (TMA landed), [S..2S) converted, [2S..3S) empty, then NACC acc-full, NACC acc-empty,
     // then (staged epilogue) EPI_NIN "target chunk landed" barriers per epilogue warp
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
+    float* tr_s = bias_s + 2 * C_::BIAS_LD;                          // transposing-epilogue scratch (TR_BYTES)
     uint64_t* acc_full = bars + 3 * STAGES;
     uint64_t* acc_empty = acc_full + NACC;
     uint64_t* in_full = acc_empty + NACC;
@@ -1053,6 +1059,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.epi == EPI_RECON) side = p.rx + m * p.rx_ld + (int64_t)n_blk * BN;
                 else if (p.epi == EPI_MUL_DACT) side = p.aux + m * p.aux_sm + (int64_t)n_blk * BN;
             }
+            // Fused reconstruction head on full 256-wide tiles: TRANSPOSING epilogue.  In the accumulator's natural layout a
+            // thread owns one output row, so the target reads and gradient stores of a warp touch 32 rows x 32 bytes per
+            // instruction (49 KB apart): measured 2x their HBM time.  Here each 32 x 32 accumulator chunk goes through a
+            // conflict-free shared-memory scratch (pitch 33) and comes back with lane = column, so every global access of the
+            // warp is one contiguous 128-byte row segment; tanh / loss / gradient are element-wise and do not care.
+            const bool tr_tile = C_::TR_BYTES > 0 && p.tr && p.epi == EPI_RECON && p.vec && !p.atomic && !p.extra &&
+                                 (int64_t)(n_blk + 1) * BN <= p.N && (int64_t)m_blk * BM + q * 32 + 32 <= p.M &&
+                                 p.rx_ld < (1 << 26) && p.sc_m < (1 << 26);
+            float xs[C_::TR_BYTES > 0 ? 32 : 1];
+            const int64_t trow0 = (int64_t)m_blk * BM + q * 32;
+            const float* xg = p.rx + trow0 * p.rx_ld + (int64_t)n_blk * BN + lane;
+            if (tr_tile) {
+                side = nullptr;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xs[i] = __ldg(xg + (int64_t)i * p.rx_ld);   // first chunk's targets: before the accumulator wait
+            }
             float4 r0[4], r1[4], r2[4];                                // chunks c0, c0+16, c0+32 in flight
             auto fetch = [&](int c0, float4* dst) {
                 const int64_t n0 = (int64_t)n_blk * BN + c0;
@@ -1082,6 +1104,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
             tc_fence_after();
+            if (C_::TR_BYTES > 0 && tr_tile) {
+                float* sc = tr_s + (warp - (2 + NUM_CONV_WARPS)) * (32 * C_::TR_LD);
+                float* cg = p.C + trow0 * p.sc_m + (int64_t)n_blk * BN + lane;
+                float* hg = p.rxhat ? p.rxhat + trow0 * p.sc_m + (int64_t)n_blk * BN + lane : nullptr;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                    // 16 columns at a time: 16, not 32, accumulator registers live
+                        float v[16];
+                        tmem_ld16(trow + (uint32_t)(c * 32 + 16 * h), v);
+                        if (h == 1 && c == BN / 32 - 1) {            // accumulator drained: the MMA warp may reuse the buffer
+                            tc_fence_before();
+                            if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&acc_empty[buf]));
+                            else mbar_arrive(smem_u32(&acc_empty[buf]));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sc[lane * C_::TR_LD + 16 * h + i] = v[i];
+                    }
+                    __syncwarp();
+                    const float bb = bs[c * 32 + lane];
+                    const bool more = c + 1 < BN / 32;
+                    // row strides re-read per chunk behind an empty asm: otherwise the 32 + 32 row offsets are hoisted out of
+                    // the chunk loop as loop invariants and spill (ptxas: 308 bytes of spill stores at the 128-register cap)
+                    uint32_t ldx = (uint32_t)p.rx_ld, ldc = (uint32_t)p.sc_m;
+                    asm volatile("" : "+r"(ldx), "+r"(ldc));
+                    const float* xr = xg + (c + 1) * 32;
+                    float* cr = cg + c * 32;
+                    float* hr = hg ? hg + c * 32 : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = tanh_fast(sc[i * C_::TR_LD + lane] + bb);
+                        const float df = t - xs[i];
+                        // the register is refilled at once with the next chunk's target of the same row: a full chunk of
+                        // work (32 rows) covers its DRAM latency, and no second array of targets is live
+                        if (more) xs[i] = __ldg(xr + (uint32_t)i * ldx);
+                        rloss += 0.5f * df * df;
+                        cr[(uint32_t)i * ldc] = df * (1.f - t * t) * p.inv_batch;
+                        if (hr) hr[(uint32_t)i * ldc] = t;
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             uint32_t vraw[16];
             tmem_ld16_issue(trow + (uint32_t)c_beg, vraw);           // accumulator chunks are read one ahead of their use
 #pragma unroll 1
@@ -1350,11 +1415,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 }
 
 // CTA-pair launch: clusters of 2, pre-split bf16 B (tb / tb2: first MMA's half rows, tb3 / tb4: second MMA's), A converted in the loop
-template <int BN, bool A_MN, bool STG = false>
+template <int BN, bool A_MN, bool STG = false, bool TR = false>
 static int launch_cta2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const CUtensorMap& tb3,
                        const CUtensorMap& tb4, const Params& p, unsigned clusters, cudaStream_t s, const CUtensorMap* txh = nullptr) {
-    auto kern = gemm_tc_kernel<BN, 32, 2, A_MN, false, STG, true>;
-    using C_ = Cfg<BN, 32, 2, STG, true>;
+    auto kern = gemm_tc_kernel<BN, 32, 2, A_MN, false, STG, true, TR>;
+    using C_ = Cfg<BN, 32, 2, STG, true, TR>;
     static bool attr_done = false;
     if (!attr_done) {
         CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
@@ -1570,6 +1635,13 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     if (no_stg < 0) { const char* e = getenv("CDG_TC_STG"); no_stg = (e && atoi(e) != 0) ? 0 : 1; }
     static int cta2 = -1;
     if (cta2 < 0) { const char* e = getenv("CDG_TC_CTA2"); cta2 = (e && atoi(e) == 0) ? 0 : 1; }
+    // transposing epilogue of the fused reconstruction head (row-coalesced 128-byte accesses through a shared-memory
+    // scratch).  Measured on B200: dec2 forward 13.3 vs 6.5 ms per step -- four 32-bit memory instructions per element
+    // (STS, LDS, LDG, STG) instead of half a 256-bit one: the single epilogue warp per scheduler is bound by the number of
+    // memory instructions it can issue, not by how the sectors coalesce.  Off unless CDG_TC_EPI_TR=1.
+    static int epi_tr = -1;
+    if (epi_tr < 0) { const char* e = getenv("CDG_TC_EPI_TR"); epi_tr = (e && atoi(e) != 0) ? 1 : 0; }
+    p.tr = epi_tr;
     if (passes == 2 && p.b_pre && cta2 && (BN == 304 || BN == 256 || BN == 160) && g.M >= 1024 && g.conv_C == 0) {
         // CTA pairs: a work item is two 128-row blocks; each CTA stages half of the B rows of each MMA
         const int N0 = BN <= 256 ? BN : 160, N1 = BN - N0;
@@ -1592,6 +1664,8 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
             else txh = tcm;
             r = launch_cta2<256, false, true>(ta, tb, tb2, tx, tcm, p, clusters, s, &txh);
         } else if (BN == 304) r = pl.a_mn ? launch_cta2<304, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<304, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
+        else if (BN == 256 && g.epi == EPI_RECON && p.tr && p.vec && !pl.a_mn)       // fused head: transposing epilogue
+            r = launch_cta2<256, false, false, true>(ta, tb, tb2, tb3, tb4, p, clusters, s);
         else if (BN == 256) r = pl.a_mn ? launch_cta2<256, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<256, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
         else r = pl.a_mn ? launch_cta2<160, true>(ta, tb, tb2, tb3, tb4, p, clusters, s) : launch_cta2<160, false>(ta, tb, tb2, tb3, tb4, p, clusters, s);
     } else if (passes == 2 && BN == 256 && g.epi == EPI_RECON && p.vec && !pl.a_mn && !pl.b_mn && !no_stg && g.M < (1ll << 31) &&

@@ -273,8 +273,8 @@ extern "C" int cdg_tvae_inverse_transform(const cdg_tvae_transform_config* cfg, 
     TransformArgs a{};
     CDG_TRY(check_config(cfg, a));
     CDG_REQUIRE(rows >= 0 && ld_raw >= cfg->n_col && ld_data >= cfg->out_dim, "tvae inverse transform: bad extents");
-    CDG_REQUIRE((sigmas == nullptr) == (normals == nullptr), "tvae inverse transform: sigmas and normals go together");
     if (rows == 0) return CDG_OK;
+    CDG_REQUIRE((sigmas == nullptr) == (normals == nullptr), "tvae inverse transform: sigmas and normals go together");
     CDG_REQUIRE(data && raw_out, "tvae inverse transform: null table pointer");
     a.data = data; a.ld_data = ld_data; a.sigmas = sigmas; a.rnd = normals; a.raw_out = raw_out; a.ld_raw = ld_raw; a.rows = rows;
     const size_t smem = (size_t)TILE_ROWS * cfg->n_col * sizeof(double) + (size_t)TILE_ROWS * cfg->out_dim * sizeof(float);

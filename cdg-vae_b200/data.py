@@ -38,6 +38,9 @@ class DevicePrefetcher:
 
     def __init__(self, iterable, device, depth=3, pixels=False):
         self.iterable, self.device, self.depth, self.pixels = iterable, torch.device(device), depth, pixels
+        # len() is exact when the wrapped loader's is (lists, DeviceDataLoader): lets the train loops know the last batch
+        # without reading one batch ahead of the step they enqueue
+        self.exact_len = isinstance(iterable, (list, tuple)) or getattr(iterable, "exact_len", False)
 
     def __len__(self):
         return len(self.iterable)
@@ -114,6 +117,7 @@ class DeviceDataLoader:
         self.n, self.batch_size, self.shuffle, self.drop_last = n, int(batch_size), shuffle, drop_last
         self.unpack_single = unpack_single
         self.device = torch.device(device)
+        self.exact_len = True
 
     @classmethod
     def from_dataset(cls, dataset, batch_size, shuffle=True, drop_last=False, device="cuda"):
