@@ -7,8 +7,11 @@
 // (fp64 row-major) and the transformed table (fp32 row-major) move as fully coalesced 16-byte accesses; inside the tile a
 // warp works on 32 consecutive rows of ONE raw column, so the injected random stream (column-major, the order in which
 // the reference's column loop draws it) is read coalesced and the per-column tables are warp-uniform.
-// Per-cell arithmetic is fp64: the component index is an inverse-cdf search and must agree with NumPy's float64 result.
+// The component index is an inverse-cdf search and must agree with NumPy's float64 result: it is decided by an fp32
+// evaluation whenever that is provably enough (cbn_select_fast) and by the fp64 evaluation otherwise; values are fp64.
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace cdg {
 namespace {
@@ -27,6 +30,8 @@ struct TransformArgs {
     double* raw_out;
     int64_t rows;
     int raw_pitch;                      // doubles per staged raw row (odd: conflict-free column walks)
+    int exact_only;                     // skip the fp32 filter (tests: both routes must give identical tables)
+    float log_a_f[CDG_MAX_TCOL][CDG_MAX_TCOMP], prec_f[CDG_MAX_TCOL][CDG_MAX_TCOMP];   // fp32 copies for the filter
 };
 
 // Copy a [n_rows, width] tile between global (row stride ld) and shared (row stride pitch) memory, 16-byte accesses when
@@ -50,6 +55,54 @@ __device__ __forceinline__ void tile_copy(T* sh, int pitch, T* gl, int64_t ld, i
         const int r = (int)(i / width), c = (int)(i - (int64_t)r * width);
         if (TO_SHARED) sh[r * pitch + c] = gl[r * ld + c]; else gl[r * ld + c] = sh[r * pitch + c];
     }
+}
+
+// Filtered component draw.  The draw is an interval test of u against the cdf of the kept components; evaluating the
+// responsibilities in fp32 (ten MUFU-based exp instead of ten fp64 exp, the cost of the whole kernel) decides it whenever u
+// is farther from every cdf boundary than a bound on the fp32 evaluation error -- otherwise the caller falls back to the
+// fp64 evaluation below, so the result is ALWAYS that of the fp64 route (tests compare the two routes cell by cell).
+// Error bound: components that matter have lp_k >= max - 30, so their fp32 log-densities carry at most
+// eps32 * (|max| + t_max + 32) absolute error each (t = 0.5 prec d^2 of the arg-max component, d from an fp64 subtraction);
+// the cdf inherits at most ~3x that; the threshold is 8x.
+__device__ __forceinline__ bool cbn_select_fast(const cdg_tvae_column& col, const float* __restrict__ log_a_f,
+                                                const float* __restrict__ prec_f, double x, double u, int& comp) {
+    float e[CDG_MAX_TCOMP];
+    float m = -INFINITY, t_m = 0.f;
+#pragma unroll
+    for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
+        if (k < col.n_all) {
+            const float d = (float)(x - col.mean[k]);
+            const float t = 0.5f * (d * d * prec_f[k]);
+            e[k] = log_a_f[k] - t;
+            if (e[k] > m) { m = e[k]; t_m = t; }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CDG_MAX_TCOMP; ++k)
+        if (k < col.n_all) { e[k] = __expf(e[k] - m); s += e[k]; }
+    const float inv_s = 1.f / s;
+    float p[CDG_MAX_TCOMP];
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j)
+        if (j < col.n_valid) { p[j] = e[col.valid_idx[j]] * inv_s + 1e-6f; tot += p[j]; }
+    const float inv_tot = 1.f / tot;
+    const float uf = (float)u;
+    // __expf: 2 ulp + 2^-21.4 * |arg| relative; everything else a few ulp -> 6e-7 per unit of log-density magnitude
+    const float tau = 8.f * 6e-7f * (fabsf(m) + t_m + 32.f);
+    float run = 0.f, gap = 1.f;
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j) {
+        if (j < col.n_valid - 1) {                        // the last boundary is 1: u < 1 always
+            run += p[j] * inv_tot;
+            idx += (run <= uf) ? 1 : 0;
+            gap = fminf(gap, fabsf(run - uf));
+        }
+    }
+    comp = idx;
+    return gap > tau;
 }
 
 // numerical.py:407-445 for one cell.  Returns the kept-component index and the clipped normalised value.
@@ -134,7 +187,13 @@ __global__ void __launch_bounds__(TT_THREADS) tvae_transform_kernel(const __grid
             if (col.kind == CDG_TCOL_CONTINUOUS) {
                 const double u = __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + r);
                 int comp; double v;
-                cbn_cell(col, x, u, comp, v);
+                if (!a.exact_only && cbn_select_fast(col, a.log_a_f[c], a.prec_f[c], x, u, comp)) {
+                    const int k = col.valid_idx[comp];
+                    v = __ddiv_rn(__dsub_rn(x, col.mean[k]), __dmul_rn(4.0, col.std[k]));
+                    v = fmin(fmax(v, -0.99), 0.99);
+                } else {
+                    cbn_cell(col, x, u, comp, v);
+                }
                 o[0] = (float)v;
                 o[1 + comp] = 1.f;            // data_transformer.py:121-123
             } else {
@@ -260,6 +319,12 @@ extern "C" int cdg_tvae_transform(const cdg_tvae_transform_config* cfg, const do
     CDG_REQUIRE(!any_cont || uniforms, "tvae transform: continuous columns need the injected uniforms");
     a.raw = raw; a.ld_raw = ld_raw; a.rnd = uniforms; a.out = out; a.ld_out = ld_out; a.rows = rows;
     a.raw_pitch = cfg->n_col | 1;
+    for (int c = 0; c < cfg->n_col; ++c)
+        for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
+            a.log_a_f[c][k] = (float)cfg->col[c].log_a[k];
+            a.prec_f[c][k] = (float)cfg->col[c].prec[k];
+        }
+    { const char* e = getenv("CDG_TVAE_EXACT_ONLY"); a.exact_only = (e && atoi(e) != 0) ? 1 : 0; }
     const size_t smem = (size_t)TILE_ROWS * a.raw_pitch * sizeof(double) + (size_t)TILE_ROWS * cfg->out_dim * sizeof(float);
     CDG_CHECK_CUDA(cudaFuncSetAttribute(tvae_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tvae_transform_kernel<<<tile_grid(rows, smem), TT_THREADS, smem, (cudaStream_t)stream>>>(a);

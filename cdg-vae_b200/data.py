@@ -65,9 +65,14 @@ class DevicePrefetcher:
             src = _leaves(item, [])
             bufs = ring[slot]
             if bufs is None or len(bufs) != len(src) or any(b.shape != s.shape or b.dtype != s.dtype for b, s in zip(bufs, src)):
-                bufs = ring[slot] = [torch.empty(s.shape, dtype=s.dtype, device=dev) for s in src]
-                decoded[slot] = [torch.empty(s.shape, dtype=torch.float32, device=dev)
-                                 if (self.pixels and s.dtype == torch.uint8) else None for s in src]
+                # allocate ON the copy stream: the caching allocator hands out blocks assuming they are next touched on the
+                # stream that is current at allocation time.  Allocated on the compute stream, a ring buffer could reuse
+                # the block of a temporary that the still-running previous step had just freed (its noise tensor, say), and
+                # the copy stream would overwrite it under that step (seen as a 1e-4 drift in step 1's loss).
+                with torch.cuda.stream(side):
+                    bufs = ring[slot] = [torch.empty(s.shape, dtype=s.dtype, device=dev) for s in src]
+                    decoded[slot] = [torch.empty(s.shape, dtype=torch.float32, device=dev)
+                                     if (self.pixels and s.dtype == torch.uint8) else None for s in src]
             outs = [b if d is None else d for b, d in zip(bufs, decoded[slot])]
             with torch.cuda.stream(side):
                 if done[slot] is not None:
@@ -88,6 +93,8 @@ class DevicePrefetcher:
             nxt = load()
             main = torch.cuda.current_stream(dev)
             main.wait_event(ev)
+            for t in _leaves(cur, []):
+                t.record_stream(main)      # read on the compute stream: the allocator must not recycle it under that work
             yield cur
             # the consumer is back asking for the next batch: the work reading the PREVIOUS batch is enqueued
             if prev_slot is not None:

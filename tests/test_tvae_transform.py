@@ -168,6 +168,40 @@ def test_gpu_transform_matches_oracle(n_cont, n_classes, rows):
 
 
 @pytest.mark.gpu
+def test_gpu_transform_fp32_filter_never_changes_a_cell(monkeypatch):
+    """The fp32-filtered component draw must reproduce the all-fp64 route cell for cell (2^21 rows x 7 mixtures, far
+    outliers included), and uniforms placed 1e-9 .. 1e-4 from a cdf boundary must still land on the oracle's side."""
+    rows = 1 << 21
+    cols, raw, u, z = orc.synth_table(7, 7, 4096, seed=21)
+    t = _dt(cols)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    idx = torch.randint(0, 4096, (rows,), device="cuda", generator=g)
+    raw_d = torch.from_numpy(raw).cuda()[idx].contiguous()
+    raw_d[::1013, :7] *= 50.0                                               # outliers: every component far away
+    ud = torch.rand(7, rows, dtype=torch.float64, device="cuda", generator=g)
+    monkeypatch.setenv("CDG_TVAE_EXACT_ONLY", "1")
+    exact = t.transform(raw_d, uniforms=ud)
+    monkeypatch.delenv("CDG_TVAE_EXACT_ONLY")
+    fast = t.transform(raw_d, uniforms=ud)
+    assert torch.equal(exact, fast)
+    p_rows = 4096
+    ua = u.copy()
+    for cc, col in enumerate(cols[:7]):
+        probs = orc.predict_proba(col, raw[:, cc])[:, col["valid"]] + 1e-6
+        probs = probs / probs.sum(1, keepdims=True)
+        cdf = np.cumsum(probs, axis=1)
+        cdf /= cdf[:, -1:]
+        b = cdf[np.arange(p_rows), np.random.RandomState(cc).randint(0, cdf.shape[1] - 1, p_rows)]
+        off = 10.0 ** np.random.RandomState(100 + cc).uniform(-9, -4, p_rows) * np.random.RandomState(200 + cc).choice([-1, 1], p_rows)
+        ua[cc] = np.clip(b + off, 1e-9, 1.0 - 1e-9)
+    out = t.transform(raw, uniforms=ua).cpu().numpy()
+    ref_a, margin_a = orc.transform(cols, raw, ua, return_margin=True)
+    ok = (margin_a > MARGIN).all(axis=0)                                    # rows with every column decidable in fp64
+    assert ok.mean() > 0.99
+    assert np.array_equal(out[ok], ref_a[ok])
+
+
+@pytest.mark.gpu
 def test_gpu_transform_strided_and_unseen_category():
     cols, raw, u, z = orc.synth_table(3, 5, 500, seed=2)
     raw[::7, -1] = 42.0                                                      # value the encoder never saw: all-zero block
