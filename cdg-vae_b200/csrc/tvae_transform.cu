@@ -3,10 +3,11 @@
 //             tabular/modules/numerical.py:407-445 (ClusterBasedNormalizer._transform)
 //   inverse : tabular/modules/data_transformer.py:184-227, :131-147; tabular/modules/numerical.py:447-457, :175-177
 //   gumbel  : tabular/inference_tvae.py:232-235, :250-253
-// HBM-bound byte work: a block stages a tile of TILE_ROWS table rows in shared memory so that both the raw table
-// (fp64 row-major) and the transformed table (fp32 row-major) move as fully coalesced 16-byte accesses; inside the tile a
-// warp works on 32 consecutive rows of ONE raw column, so the injected random stream (column-major, the order in which
-// the reference's column loop draws it) is read coalesced and the per-column tables are warp-uniform.
+// HBM-bound byte work: rows are staged through shared memory so that both the raw table (fp64 row-major) and the transformed
+// table (fp32 row-major) move as contiguous, coalesced runs (forward: one warp per 32-row strip, private staging; inverse:
+// 128-row block tiles); a warp always works on 32 consecutive rows of ONE raw column at a time, so the injected random
+// stream (column-major, the order in which the reference's column loop draws it) is read coalesced and the per-column
+// tables are warp-uniform.
 // The component index is an inverse-cdf search and must agree with NumPy's float64 result: it is decided by an fp32
 // evaluation whenever that is provably enough (cbn_select_fast) and by the fp64 evaluation otherwise; values are fp64.
 #include "common.cuh"
@@ -154,54 +155,77 @@ __device__ __forceinline__ void cbn_cell(const cdg_tvae_column& col, double x, d
     value = fmin(fmax(v, -0.99), 0.99);
 }
 
-__global__ void __launch_bounds__(TT_THREADS) tvae_transform_kernel(const __grid_constant__ TransformArgs a) {
+// Forward transform: ONE WARP per strip of 32 table rows, private staging in shared memory, __syncwarp only.
+// (The first version used 128-row block tiles: ncu showed warps waiting at the block barriers for as long as they issued --
+// 20 column tasks over 8 warps -- and 3 blocks per SM.)  A lane owns one row; the strip's columns are walked in order, so
+// the mixture tables are warp-uniform and the injected uniforms (column-major) are read as one 256-byte run per column.
+constexpr int WARP_ROWS = 32;
+__global__ void __launch_bounds__(TT_THREADS, 3) tvae_transform_kernel(const __grid_constant__ TransformArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.c.n_col, D = a.c.out_dim;
-    double* sraw = reinterpret_cast<double*>(smem_raw);
-    float* sout = reinterpret_cast<float*>(sraw + (size_t)TILE_ROWS * a.raw_pitch);
-    const int64_t n_tiles = (a.rows + TILE_ROWS - 1) / TILE_ROWS;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t r0 = t * TILE_ROWS;
-        const int nr = (int)min((int64_t)TILE_ROWS, a.rows - r0);
-        __syncthreads();   // previous tile's stores are done with the staging buffers
-        if (a.ld_raw == C) {
-            // contiguous rows: coalesced 16-byte loads, then scattered into the odd-pitch staging rows
-            const int64_t total = (int64_t)nr * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)WARP_ROWS * a.raw_pitch * sizeof(double) + (((size_t)WARP_ROWS * D * sizeof(float) + 15) & ~(size_t)15);
+    double* sraw = reinterpret_cast<double*>(smem_raw + warp * per_warp);
+    float* sout = reinterpret_cast<float*>(sraw + (size_t)WARP_ROWS * a.raw_pitch);
+    const int64_t n_strips = (a.rows + WARP_ROWS - 1) / WARP_ROWS;
+    const int64_t w_stride = (int64_t)gridDim.x * (TT_THREADS / 32);
+    for (int64_t t = (int64_t)blockIdx.x * (TT_THREADS / 32) + warp; t < n_strips; t += w_stride) {
+        const int64_t r0 = t * WARP_ROWS;
+        const int nr = (int)min((int64_t)WARP_ROWS, a.rows - r0);
+        __syncwarp();                                       // previous strip's stores have read the staging buffers
+        if (a.ld_raw == C) {                                // the strip is one contiguous run of nr * C doubles
             const double* g = a.raw + r0 * a.ld_raw;
-            for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-                const int r = (int)(i / C), c = (int)(i - (int64_t)r * C);
-                sraw[r * a.raw_pitch + c] = __ldg(g + i);
+            for (int i = lane; i < nr * C; i += 32) {
+                const int r = i / C;
+                sraw[r * a.raw_pitch + (i - r * C)] = __ldg(g + i);
             }
         } else {
-            tile_copy<double, true>(sraw, a.raw_pitch, const_cast<double*>(a.raw + r0 * a.ld_raw), a.ld_raw, nr, C);
-        }
-        for (int i = threadIdx.x; i < nr * D; i += blockDim.x) sout[i] = 0.f;
-        __syncthreads();
-        // cell (column, row): a warp covers 32 consecutive rows of one column (TILE_ROWS is a multiple of 32)
-        for (int cell = threadIdx.x; cell < C * TILE_ROWS; cell += blockDim.x) {
-            const int c = cell / TILE_ROWS, r = cell - c * TILE_ROWS;
-            if (r >= nr) continue;
-            const cdg_tvae_column& col = a.c.col[c];
-            const double x = sraw[r * a.raw_pitch + c];
-            float* o = sout + r * D + col.out_start;
-            if (col.kind == CDG_TCOL_CONTINUOUS) {
-                const double u = __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + r);
-                int comp; double v;
-                if (!a.exact_only && cbn_select_fast(col, a.log_a_f[c], a.prec_f[c], x, u, comp)) {
-                    const int k = col.valid_idx[comp];
-                    v = __ddiv_rn(__dsub_rn(x, col.mean[k]), __dmul_rn(4.0, col.std[k]));
-                    v = fmin(fmax(v, -0.99), 0.99);
-                } else {
-                    cbn_cell(col, x, u, comp, v);
-                }
-                o[0] = (float)v;
-                o[1 + comp] = 1.f;            // data_transformer.py:121-123
-            } else {
-                for (int j = 0; j < col.n_valid; ++j) o[j] = (x == col.category[j]) ? 1.f : 0.f;
+            for (int i = lane; i < nr * C; i += 32) {
+                const int r = i / C, c = i - r * C;
+                sraw[r * a.raw_pitch + c] = __ldg(a.raw + (r0 + r) * a.ld_raw + c);
             }
         }
-        __syncthreads();
-        tile_copy<float, false>(sout, D, a.out + r0 * a.ld_out, a.ld_out, nr, D);
+        {
+            float4* z = reinterpret_cast<float4*>(sout);
+            const int nz = (WARP_ROWS * D + 3) / 4;
+            for (int i = lane; i < nz; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane < nr) {
+            for (int c = 0; c < C; ++c) {
+                const cdg_tvae_column& col = a.c.col[c];
+                const double x = sraw[lane * a.raw_pitch + c];
+                float* o = sout + lane * D + col.out_start;
+                if (col.kind == CDG_TCOL_CONTINUOUS) {
+                    const double u = __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + lane);
+                    int comp; double v;
+                    if (!a.exact_only && cbn_select_fast(col, a.log_a_f[c], a.prec_f[c], x, u, comp)) {
+                        const int k = col.valid_idx[comp];
+                        v = __ddiv_rn(__dsub_rn(x, col.mean[k]), __dmul_rn(4.0, col.std[k]));
+                        v = fmin(fmax(v, -0.99), 0.99);
+                    } else {
+                        cbn_cell(col, x, u, comp, v);
+                    }
+                    o[0] = (float)v;
+                    o[1 + comp] = 1.f;            // data_transformer.py:121-123
+                } else {
+                    for (int j = 0; j < col.n_valid; ++j) o[j] = (x == col.category[j]) ? 1.f : 0.f;
+                }
+            }
+        }
+        __syncwarp();
+        // the strip's nr * D floats are contiguous in the output when ld_out == D
+        float* g = a.out + r0 * a.ld_out;
+        if (a.ld_out == D && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            const int nv = (nr * D) >> 2;
+            for (int i = lane; i < nv; i += 32) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(sout)[i];
+            for (int i = (nv << 2) + lane; i < nr * D; i += 32) g[i] = sout[i];
+        } else {
+            for (int i = lane; i < nr * D; i += 32) {
+                const int r = i / D, c = i - r * D;
+                g[(int64_t)r * a.ld_out + c] = sout[i];
+            }
+        }
     }
 }
 
@@ -325,9 +349,14 @@ extern "C" int cdg_tvae_transform(const cdg_tvae_transform_config* cfg, const do
             a.prec_f[c][k] = (float)cfg->col[c].prec[k];
         }
     { const char* e = getenv("CDG_TVAE_EXACT_ONLY"); a.exact_only = (e && atoi(e) != 0) ? 1 : 0; }
-    const size_t smem = (size_t)TILE_ROWS * a.raw_pitch * sizeof(double) + (size_t)TILE_ROWS * cfg->out_dim * sizeof(float);
+    const size_t per_warp = (size_t)WARP_ROWS * a.raw_pitch * sizeof(double) + (((size_t)WARP_ROWS * cfg->out_dim * sizeof(float) + 15) & ~(size_t)15);
+    const size_t smem = per_warp * (TT_THREADS / 32);
     CDG_CHECK_CUDA(cudaFuncSetAttribute(tvae_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tvae_transform_kernel<<<tile_grid(rows, smem), TT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    int per_sm = (int)imin64(3, (int64_t)(220 * 1024) / (int64_t)(smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t strips = (rows + WARP_ROWS - 1) / WARP_ROWS;
+    const unsigned blocks = (unsigned)imax64(1, imin64((strips + TT_THREADS / 32 - 1) / (TT_THREADS / 32), (int64_t)kNumSMs * per_sm));
+    tvae_transform_kernel<<<blocks, TT_THREADS, smem, (cudaStream_t)stream>>>(a);
     CDG_CHECK_LAUNCH();
     return CDG_OK;
 }

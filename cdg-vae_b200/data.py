@@ -36,8 +36,14 @@ class DevicePrefetcher:
     stream, by `cdg_pixels_to_float` — the same `(p - 127.5) / 127.5` in float64 rounded to fp32 that the reference's
     dataset applies on the host (datasets.py:28, :42) — so the consumer sees bit-identical fp32 batches."""
 
-    def __init__(self, iterable, device, depth=3, pixels=False):
+    def __init__(self, iterable, device, depth=3, pixels=False, convert_on=None):
+        import os
         self.iterable, self.device, self.depth, self.pixels = iterable, torch.device(device), depth, pixels
+        # where the byte -> fp32 kernel runs: "copy" (behind its DMA on the copy stream; default), "own" (a high-priority
+        # stream of its own) or "compute" (on the consumer's stream, right before the step).  Measured on B200 in a 12-step
+        # loop of the bench workload (tools/e2e_diag.py, copy alone 40.6 ms, step alone 28.0 ms): 38.8 / 48.3 / 49.1 ms per
+        # step -- the other two keep the byte staging buffer busy until the consumer's step has run, which delays the next DMA
+        self.convert_on = convert_on or os.environ.get("CDG_PREFETCH_CONVERT", "copy")
         # len() is exact when the wrapped loader's is (lists, DeviceDataLoader): lets the train loops know the last batch
         # without reading one batch ahead of the step they enqueue
         self.exact_len = isinstance(iterable, (list, tuple)) or getattr(iterable, "exact_len", False)
@@ -53,6 +59,12 @@ class DevicePrefetcher:
         decoded = [None] * depth       # per slot: fp32 buffers of the uint8 leaves (pixels=True), else None
         it = iter(self.iterable)
         count = 0
+        conv = side if self.convert_on == "copy" else torch.cuda.Stream(dev, priority=-1)
+
+        def convert(pairs, stream):
+            from . import _lib
+            for b, d in pairs:
+                _lib.check(_lib.lib().cdg_pixels_to_float(b.data_ptr(), b.numel(), d.data_ptr(), stream.cuda_stream))
 
         def load():
             nonlocal count
@@ -77,22 +89,29 @@ class DevicePrefetcher:
             with torch.cuda.stream(side):
                 if done[slot] is not None:
                     side.wait_event(done[slot])
-                for b, d, s in zip(bufs, decoded[slot], src):
+                for b, s in zip(bufs, src):
                     b.copy_(s, non_blocking=True)
-                    if d is not None:
-                        from . import _lib
-                        _lib.check(_lib.lib().cdg_pixels_to_float(b.data_ptr(), b.numel(), d.data_ptr(), side.cuda_stream))
                 ev = torch.cuda.Event()
                 ev.record(side)
-            return _rebuild(item, iter(outs)), ev, slot
+            pending = [(b, d) for b, d in zip(bufs, decoded[slot]) if d is not None]
+            if pending and self.convert_on != "compute":
+                with torch.cuda.stream(conv):
+                    conv.wait_event(ev)
+                    convert(pending, conv)
+                    ev = torch.cuda.Event()
+                    ev.record(conv)
+                pending = []
+            return _rebuild(item, iter(outs)), ev, slot, pending
 
         nxt = load()
         prev_slot = None
         while nxt is not None:
-            cur, ev, slot = nxt
+            cur, ev, slot, pending = nxt
             nxt = load()
             main = torch.cuda.current_stream(dev)
             main.wait_event(ev)
+            if pending:
+                convert(pending, main)
             for t in _leaves(cur, []):
                 t.record_stream(main)      # read on the compute stream: the allocator must not recycle it under that work
             yield cur

@@ -57,8 +57,28 @@ def main():
     out["copy_only_ms"] = timed(drain(False))
     out["copy_convert_ms"] = timed(drain(True))
     out["compute_only_ms"] = timed(lambda k: train_CDGVAE_semi_loaders([(xld, yld)] * k, [xd] * k, model, cfg, opt, dev))
-    out["e2e_ms"] = timed(lambda k: train_CDGVAE_semi_loaders(DevicePrefetcher([(xlp, ylp)] * k, dev, pixels=True),
-                                                              DevicePrefetcher([xp] * k, dev, pixels=True), model, cfg, opt, dev))
+    for mode in ("copy", "own", "compute"):
+        out["e2e_cold_ms_convert_on_" + mode] = timed(lambda k: train_CDGVAE_semi_loaders(
+            DevicePrefetcher([(xlp, ylp)] * k, dev, pixels=True, convert_on=mode),
+            DevicePrefetcher([xp] * k, dev, pixels=True, convert_on=mode), model, cfg, opt, dev))
+    # steady state: 12 steps in one loop, clock from step 4
+    class Marked:
+        exact_len = True
+        def __init__(self, loader, at): self.loader, self.at = loader, at
+        def __len__(self): return len(self.loader)
+        def __iter__(self):
+            for i, b in enumerate(self.loader):
+                if i == self.at: e0.record()
+                yield b
+    for mode in ("copy", "own", "compute"):
+        k = 12
+        torch.cuda.synchronize()
+        train_CDGVAE_semi_loaders(DevicePrefetcher([(xlp, ylp)] * k, dev, pixels=True, convert_on=mode),
+                                  Marked(DevicePrefetcher([xp] * k, dev, pixels=True, convert_on=mode), 4), model, cfg, opt, dev)
+        e1.record()
+        torch.cuda.synchronize()
+        out["e2e_warm_ms_convert_on_" + mode] = e0.elapsed_time(e1) / (k - 4)
+    # the same with the images already fp32 on the host and with U-only uint8 (no labeled loader H2D)
     # compute while an unrelated H2D stream is running: does the copy slow the step, or the step the copy?
     side = torch.cuda.Stream(dev)
     sink = torch.empty_like(xu8)
