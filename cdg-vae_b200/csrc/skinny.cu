@@ -6,6 +6,8 @@
 //   skinny_wgrad  min(M,N) <= 8, contraction over the batch: wgrad of those two layers
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cdg {
 
 template <bool VEC>
@@ -91,6 +93,110 @@ __global__ void __launch_bounds__(256) rowdot_kernel(GemmDesc g) {
     }
 }
 
+// ---- row-per-warp variants (the hot shapes: [batch, 300] activations with K or N <= 8) ----------------------------
+// The element-indexed kernels above pay a 64-bit division per 4 outputs and re-read the tiny operand through the
+// read-only cache for every element: ncu launch lists showed them at 1.2-1.4 TB/s.  Here the tiny operand (and the bias)
+// sits in shared memory, a warp owns one batch row at a time, and every global access is a 16-byte piece of one
+// contiguous 1,200-byte row.
+__global__ void __launch_bounds__(256) smallk_rows_kernel(GemmDesc g) {
+    extern __shared__ __align__(16) float sk_sm[];        // [K][N] weights, then [N] bias
+    const int K = (int)g.K, N = (int)g.N, n4 = N >> 2;
+    float* ws = sk_sm;
+    float* bs = sk_sm + K * N;
+    const bool has_bias = g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT;
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+        const int k = i / N, n = i - k * N;
+        ws[i] = g.B[n * g.sb_n + k * g.sb_k];
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bs[i] = has_bias ? g.bias[i] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4* ws4 = reinterpret_cast<const float4*>(ws);
+    const float4* bs4 = reinterpret_cast<const float4*>(bs);
+    for (int64_t m = warp0; m < g.M; m += nwarps) {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = k < K ? __ldg(g.A + m * g.sa_m + k * g.sa_k) : 0.f;
+        float4* crow = reinterpret_cast<float4*>(g.C + m * g.ldc);
+        const float4* hrow = g.epi == EPI_MUL_DACT ? reinterpret_cast<const float4*>(g.aux + m * g.ld_aux) : nullptr;
+        for (int q = lane; q < n4; q += 32) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < K) {
+                    const float4 w = ws4[k * n4 + q];
+                    s[0] = fmaf(a[k], w.x, s[0]); s[1] = fmaf(a[k], w.y, s[1]);
+                    s[2] = fmaf(a[k], w.z, s[2]); s[3] = fmaf(a[k], w.w, s[3]);
+                }
+            }
+            if (has_bias) {
+                const float4 b = bs4[q];
+                s[0] += b.x; s[1] += b.y; s[2] += b.z; s[3] += b.w;
+            }
+            if (g.epi == EPI_BIAS_ACT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] = act_fwd(s[e], g.act);
+            }
+            if (hrow) {
+                const float4 h = __ldg(hrow + q);
+                s[0] *= act_bwd_from_out(h.x, g.act); s[1] *= act_bwd_from_out(h.y, g.act);
+                s[2] *= act_bwd_from_out(h.z, g.act); s[3] *= act_bwd_from_out(h.w, g.act);
+            }
+            if (g.accumulate) {
+                const float4 o = crow[q];
+                s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
+            }
+            crow[q] = make_float4(s[0], s[1], s[2], s[3]);
+        }
+    }
+}
+
+// N <= 8 outputs per row, contraction over a contiguous row of K = 4 * k4 floats; B ([N][K]) in shared memory
+__global__ void __launch_bounds__(256) rowdot_rows_kernel(GemmDesc g) {
+    extern __shared__ __align__(16) float rd_sm[];        // [N][K]
+    const int K = (int)g.K, N = (int)g.N, k4 = K >> 2;
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+        const int n = i / K, k = i - n * K;
+        rd_sm[i] = g.B[n * g.sb_n + k * g.sb_k];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4* b4 = reinterpret_cast<const float4*>(rd_sm);
+    for (int64_t m = warp0; m < g.M; m += nwarps) {
+        float acc[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+        const float4* arow = reinterpret_cast<const float4*>(g.A + m * g.sa_m);
+        for (int q = lane; q < k4; q += 32) {
+            const float4 av = __ldg(arow + q);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (n < N) {
+                    const float4 w = b4[n * k4 + q];
+                    acc[n] = fmaf(av.x, w.x, fmaf(av.y, w.y, fmaf(av.z, w.z, fmaf(av.w, w.w, acc[n]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+            if (n < N) acc[n] = warp_sum(acc[n]);
+        if (lane < N) {
+            float s = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                if (n == lane) s = acc[n];
+            float* c = g.C + m * g.ldc + lane;
+            if (g.epi == EPI_BIAS) s += g.bias[lane];
+            if (g.accumulate) s += *c;
+            *c = s;
+        }
+    }
+}
+
 // C[m*ldc + n] += sum_k A[m + k*sa_k] * B[n + k*sb_k]; `wide_is_m` tells which side has the long extent
 struct SkinnyW {
     const float* wide; int64_t wide_ld; const float* narrow; int64_t narrow_ld;
@@ -134,6 +240,15 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
         const bool vec = g.N % 4 == 0 && g.ldc % 4 == 0 && (((uintptr_t)g.C) & 15) == 0 &&
                          (!(g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) || (((uintptr_t)g.bias) & 15) == 0) &&
                          (g.epi != EPI_MUL_DACT || (g.ld_aux % 4 == 0 && (((uintptr_t)g.aux) & 15) == 0));
+        static int rows_ok = -1;           // CDG_SKINNY_ROWS=0 restores the element-indexed kernels
+        if (rows_ok < 0) { const char* e = getenv("CDG_SKINNY_ROWS"); rows_ok = (e && atoi(e) == 0) ? 0 : 1; }
+        if (rows_ok && vec && g.M >= 64 && g.K * g.N <= 8192 && g.N >= 128) {
+            const size_t smem = sizeof(float) * (size_t)(g.K * g.N + g.N);
+            const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 8);
+            smallk_rows_kernel<<<blocks, 256, smem, s>>>(g);
+            CDG_CHECK_LAUNCH();
+            return CDG_OK;
+        }
         const int64_t total = vec ? g.M * g.N / 4 : g.M * g.N;
         const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 16);
         if (vec) smallk_elem_kernel<true><<<blocks, 256, 0, s>>>(g);
@@ -142,6 +257,14 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
         return CDG_OK;
     }
     if (g.N <= 8 && g.sa_k == 1 && (g.epi == EPI_NONE || g.epi == EPI_BIAS)) {
+        static int rows_ok = -1;
+        if (rows_ok < 0) { const char* e = getenv("CDG_SKINNY_ROWS"); rows_ok = (e && atoi(e) == 0) ? 0 : 1; }
+        if (rows_ok && g.M >= 64 && g.K % 4 == 0 && g.K >= 128 && g.N * g.K <= 8192 && g.sa_m % 4 == 0 && (((uintptr_t)g.A) & 15) == 0) {
+            const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 8);
+            rowdot_rows_kernel<<<blocks, 256, sizeof(float) * (size_t)(g.N * g.K), s>>>(g);
+            CDG_CHECK_LAUNCH();
+            return CDG_OK;
+        }
         const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 16);
         rowdot_kernel<<<blocks, 256, 0, s>>>(g);
         CDG_CHECK_LAUNCH();
