@@ -12,6 +12,7 @@
 // evaluation whenever that is provably enough (cbn_select_fast) and by the fp64 evaluation otherwise; values are fp64.
 #include "common.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 namespace cdg {
@@ -32,7 +33,10 @@ struct TransformArgs {
     int64_t rows;
     int raw_pitch;                      // doubles per staged raw row (odd: conflict-free column walks)
     int exact_only;                     // skip the fp32 filter (tests: both routes must give identical tables)
-    float log_a_f[CDG_MAX_TCOL][CDG_MAX_TCOMP], prec_f[CDG_MAX_TCOL][CDG_MAX_TCOMP];   // fp32 copies for the filter
+    // tables of the fp32 filter, components PERMUTED so that the kept ones come first (in their original order): the
+    // kept probabilities are then statically indexed registers instead of a dynamically indexed local array
+    float log_a_f[CDG_MAX_TCOL][CDG_MAX_TCOMP], prec_f[CDG_MAX_TCOL][CDG_MAX_TCOMP];
+    double mean_p[CDG_MAX_TCOL][CDG_MAX_TCOMP];
 };
 
 // Copy a [n_rows, width] tile between global (row stride ld) and shared (row stride pitch) memory, 16-byte accesses when
@@ -65,29 +69,30 @@ __device__ __forceinline__ void tile_copy(T* sh, int pitch, T* gl, int64_t ld, i
 // Error bound: components that matter have lp_k >= max - 30, so their fp32 log-densities carry at most
 // eps32 * (|max| + t_max + 32) absolute error each (t = 0.5 prec d^2 of the arg-max component, d from an fp64 subtraction);
 // the cdf inherits at most ~3x that; the threshold is 8x.
-__device__ __forceinline__ bool cbn_select_fast(const cdg_tvae_column& col, const float* __restrict__ log_a_f,
-                                                const float* __restrict__ prec_f, double x, double u, int& comp) {
+__device__ __forceinline__ bool cbn_select_fast(int n_all, int n_valid, const double* __restrict__ mean_p,
+                                                const float* __restrict__ log_a_f, const float* __restrict__ prec_f,
+                                                double x, double u, int& comp) {
+    // branch-free over the CDG_MAX_TCOMP slots: unused slots carry log_a = -inf (weight 0), so no per-slot predicates
     float e[CDG_MAX_TCOMP];
     float m = -INFINITY, t_m = 0.f;
 #pragma unroll
     for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
-        if (k < col.n_all) {
-            const float d = (float)(x - col.mean[k]);
-            const float t = 0.5f * (d * d * prec_f[k]);
-            e[k] = log_a_f[k] - t;
-            if (e[k] > m) { m = e[k]; t_m = t; }
-        }
+        const float d = (float)(x - mean_p[k]);
+        const float t = 0.5f * (d * d * prec_f[k]);
+        e[k] = log_a_f[k] - t;
+        t_m = e[k] > m ? t : t_m;
+        m = fmaxf(m, e[k]);
     }
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < CDG_MAX_TCOMP; ++k)
-        if (k < col.n_all) { e[k] = __expf(e[k] - m); s += e[k]; }
+    for (int k = 0; k < CDG_MAX_TCOMP; ++k) { e[k] = __expf(e[k] - m); s += e[k]; }
     const float inv_s = 1.f / s;
-    float p[CDG_MAX_TCOMP];
     float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < CDG_MAX_TCOMP; ++j)
-        if (j < col.n_valid) { p[j] = e[col.valid_idx[j]] * inv_s + 1e-6f; tot += p[j]; }
+    for (int j = 0; j < CDG_MAX_TCOMP; ++j) {
+        e[j] = j < n_valid ? e[j] * inv_s + 1e-6f : 0.f;
+        tot += e[j];
+    }
     const float inv_tot = 1.f / tot;
     const float uf = (float)u;
     // __expf: 2 ulp + 2^-21.4 * |arg| relative; everything else a few ulp -> 6e-7 per unit of log-density magnitude
@@ -95,15 +100,14 @@ __device__ __forceinline__ bool cbn_select_fast(const cdg_tvae_column& col, cons
     float run = 0.f, gap = 1.f;
     int idx = 0;
 #pragma unroll
-    for (int j = 0; j < CDG_MAX_TCOMP; ++j) {
-        if (j < col.n_valid - 1) {                        // the last boundary is 1: u < 1 always
-            run += p[j] * inv_tot;
-            idx += (run <= uf) ? 1 : 0;
-            gap = fminf(gap, fabsf(run - uf));
-        }
+    for (int j = 0; j < CDG_MAX_TCOMP - 1; ++j) {
+        run += e[j] * inv_tot;
+        const bool live = j < n_valid - 1;                // the last boundary is 1: u < 1 always
+        idx += (live && run <= uf) ? 1 : 0;
+        gap = live ? fminf(gap, fabsf(run - uf)) : gap;
     }
     comp = idx;
-    return gap > tau;
+    return gap > tau;                                      // NaN (every component infinitely far) -> false -> fp64 route
 }
 
 // numerical.py:407-445 for one cell.  Returns the kept-component index and the clipped normalised value.
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(TT_THREADS, 3) tvae_transform_kernel(const __g
                 if (col.kind == CDG_TCOL_CONTINUOUS) {
                     const double u = __ldg(a.rnd + (int64_t)a.cont_index[c] * a.rows + r0 + lane);
                     int comp; double v;
-                    if (!a.exact_only && cbn_select_fast(col, a.log_a_f[c], a.prec_f[c], x, u, comp)) {
+                    if (!a.exact_only && cbn_select_fast(col.n_all, col.n_valid, a.mean_p[c], a.log_a_f[c], a.prec_f[c], x, u, comp)) {
                         const int k = col.valid_idx[comp];
                         v = __ddiv_rn(__dsub_rn(x, col.mean[k]), __dmul_rn(4.0, col.std[k]));
                         v = fmin(fmax(v, -0.99), 0.99);
@@ -343,11 +347,21 @@ extern "C" int cdg_tvae_transform(const cdg_tvae_transform_config* cfg, const do
     CDG_REQUIRE(!any_cont || uniforms, "tvae transform: continuous columns need the injected uniforms");
     a.raw = raw; a.ld_raw = ld_raw; a.rnd = uniforms; a.out = out; a.ld_out = ld_out; a.rows = rows;
     a.raw_pitch = cfg->n_col | 1;
-    for (int c = 0; c < cfg->n_col; ++c)
-        for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
-            a.log_a_f[c][k] = (float)cfg->col[c].log_a[k];
-            a.prec_f[c][k] = (float)cfg->col[c].prec[k];
+    for (int c = 0; c < cfg->n_col; ++c) {
+        const cdg_tvae_column& col = cfg->col[c];
+        int order[CDG_MAX_TCOMP], n = 0;
+        bool kept[CDG_MAX_TCOMP] = {};
+        if (col.kind == CDG_TCOL_CONTINUOUS) {
+            for (int j = 0; j < col.n_valid; ++j) { order[n++] = col.valid_idx[j]; kept[col.valid_idx[j]] = true; }
+            for (int k = 0; k < col.n_all; ++k) if (!kept[k]) order[n++] = k;
         }
+        for (int k = 0; k < CDG_MAX_TCOMP; ++k) {
+            const bool used = k < n;
+            a.log_a_f[c][k] = used ? (float)col.log_a[order[k]] : -INFINITY;
+            a.prec_f[c][k] = used ? (float)col.prec[order[k]] : 0.f;
+            a.mean_p[c][k] = used ? col.mean[order[k]] : 0.0;
+        }
+    }
     { const char* e = getenv("CDG_TVAE_EXACT_ONLY"); a.exact_only = (e && atoi(e) != 0) ? 1 : 0; }
     const size_t per_warp = (size_t)WARP_ROWS * a.raw_pitch * sizeof(double) + (((size_t)WARP_ROWS * cfg->out_dim * sizeof(float) + 15) & ~(size_t)15);
     const size_t smem = per_warp * (TT_THREADS / 32);
