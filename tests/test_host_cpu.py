@@ -215,3 +215,38 @@ def test_celeba_host_model_matches_reference_layout(golden):
     assert model.adam_segments()[0][0] == 0
     with pytest.raises(RuntimeError):
         model(x)                                         # no CPU path
+
+
+def test_last_batch_detection_counts_sized_loaders_and_reads_ahead_otherwise():
+    """`xhat` is materialised for the last batch only (train.py:209).  Loaders with an exact len() are counted, so that
+    batch i+1 is not requested before step i is enqueued; anything else is read one batch ahead."""
+    from cdgvae_b200.modules.train import _lookahead
+    from cdgvae_b200.data import DevicePrefetcher
+    order = []
+
+    class Sized:
+        exact_len = True
+
+        def __len__(self):
+            return 3
+
+        def __iter__(self):
+            for i in range(3):
+                order.append(("pull", i))
+                yield i
+
+    for item, last in _lookahead(Sized()):
+        order.append(("step", item, last))
+    assert order == [("pull", 0), ("step", 0, False), ("pull", 1), ("step", 1, False), ("pull", 2), ("step", 2, True)]
+    assert list(_lookahead([7, 8])) == [(7, False), (8, True)]
+    assert list(_lookahead(x for x in [7, 8, 9])) == [(7, False), (8, False), (9, True)]       # no len(): look-ahead
+    assert list(_lookahead([])) == [] and list(_lookahead(x for x in [])) == []
+
+    class LyingLen:                      # a len() nobody vouched for is not trusted
+        def __len__(self):
+            return 5
+
+        def __iter__(self):
+            return iter([1, 2])
+    assert list(_lookahead(LyingLen())) == [(1, False), (2, True)]
+    assert DevicePrefetcher([1, 2], "cuda").exact_len and not DevicePrefetcher((x for x in [1]), "cuda").exact_len
