@@ -33,11 +33,28 @@ def stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every csrc/*.cu for sm_100a and link libcdgvae_sm100.so next to this file."""
+    """Compile every csrc/*.cu for sm_100a and link libcdgvae_sm100.so next to this file.
+
+    Safe under torchrun: ranks that find the library stale at the same time serialise on a file lock, the first one
+    builds (objects in a private directory, library linked under a temporary name and renamed into place atomically),
+    the others re-check and find it fresh.  (Eight ranks once rebuilt it concurrently and one of them loaded a
+    half-linked file: `undefined symbol`.)"""
+    import fcntl
     if not force and not stale():
         return LIB
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", f"obj.{os.getpid()}")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -54,10 +71,13 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIB
 
 
