@@ -58,30 +58,11 @@ class CelebaSpec:
         self.z_dims = [len(i) for i in DEC_INPUTS] + [self.latent_dim]
 
 
-def celeba_B(node: int = 6, structure: int = 0) -> Tensor:
-    """celeba/main.py:86-108 with dataset.nodes order [Smiling, Male, High_Cheekbones, Mouth_Slightly_Open,
-    Narrow_Eyes, Chubby] (celeba/module/datasets.py), adjacency scaling on."""
-    B = torch.zeros(node, node)
-    if structure == 0:
-        for j in (2, 3, 5, 4):
-            B[0, j] = 1
-        B[1, 4] = 1
-    indeg = B.sum(0)
-    m = indeg != 0
-    B[:, m] = B[:, m] / indeg[m]
-    return B
+import os as _os
+import sys as _sys
 
-
-def synth_celeba(batch: int, seed: int = 1234, noise_seed: int = 4321, size: int = 128):
-    """SURVEY.md §8(d) cfg 5: channels 0-2 U(0,1), channels 3-7 Bernoulli(0.5) masks, y Bernoulli(0.5)."""
-    g = torch.Generator().manual_seed(seed)
-    img = torch.rand(batch, size, size, 3, generator=g)
-    msk = (torch.rand(batch, size, size, 5, generator=g) < 0.5).float()
-    y = (torch.rand(batch, 6, generator=g) < 0.5).float()
-    gn = torch.Generator().manual_seed(noise_seed)
-    n1 = torch.randn(batch, 6, generator=gn)
-    n2 = torch.randn(batch, 6, generator=gn)
-    return torch.cat([img, msk], -1), y, n1, n2
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from synthetic_inputs import celeba_B, synth_celeba  # noqa: E402,F401  (shared with bench.py; see synthetic_inputs.py)
 
 
 # --------------------------------------------------------------------------------------
