@@ -126,7 +126,7 @@ class TvaeTransformConfig(C.Structure):
 
 
 # every symbol include/cdgvae.h declares
-EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_pendulum_profile_enable",
+EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_abi_sizeof", "cdg_flow_apply", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
@@ -136,6 +136,23 @@ EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count",
            "cdg_gumbel_argmax", "cdg_pixels_to_float"]
 
 _lib = None
+ABI_STRUCTS = [Linear, AdamArgs, PendulumConfig, PendulumIO, PendulumFwdIO, TabularConfig, TabularIO, Conv, BNorm, CelebaConfig,
+               CelebaIO, TvaeTransformConfig]      # filled below, in the order cdg_abi_sizeof() enumerates them
+
+
+def _check_abi(L, path):
+    """Refuse a library whose struct layouts differ from the ctypes declarations in this file (a stale prebuilt .so)."""
+    if not hasattr(L, "cdg_abi_sizeof"):
+        raise RuntimeError(f"{path} predates this binding (no cdg_abi_sizeof): rebuild it")
+    L.cdg_abi_sizeof.restype = C.c_int64
+    L.cdg_abi_sizeof.argtypes = [C.c_int]
+    for i, st in enumerate(ABI_STRUCTS):
+        got = L.cdg_abi_sizeof(i)
+        if got != C.sizeof(st):
+            raise RuntimeError(f"{path}: sizeof({st.__name__}) is {got} in the library, {C.sizeof(st)} in this binding; "
+                               "the library is stale -- rebuild it (python -m cdgvae_b200.build)")
+    if L.cdg_abi_sizeof(len(ABI_STRUCTS)) != -1:
+        raise RuntimeError(f"{path} declares more structs than this binding knows: the binding is stale")
 
 
 def lib():
@@ -147,12 +164,15 @@ def lib():
     if _build.stale():
         try:
             _build.build()
-        except Exception as e:  # no nvcc on the box: a prebuilt library must be present
+        except _build.NoCompiler as e:  # no nvcc on the box: a prebuilt library must be present (its layout is checked below)
             if not os.path.exists(path):
                 raise RuntimeError(f"libcdgvae_sm100.so is missing and cannot be built: {e}") from e
+        # any other failure (compile / link error, lock or permission problem) propagates: an older library on disk may
+        # not match the structures declared here
     if not os.path.exists(path):
         raise RuntimeError("libcdgvae_sm100.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(path)
+    _check_abi(L, path)
     L.cdg_last_error.restype = C.c_char_p
     L.cdg_launch_count.restype = C.c_longlong
     L.cdg_pendulum_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -197,6 +217,8 @@ def lib():
                                              C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     L.cdg_gumbel_argmax.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.cdg_pixels_to_float.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cdg_flow_apply.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
     _lib = L
     return L
 

@@ -13,10 +13,14 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include")]
 
 
+class NoCompiler(RuntimeError):
+    """nvcc is absent: the only build failure after which a prebuilt library may be used."""
+
+
 def _nvcc():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: libcdgvae_sm100.so cannot be built")
+        raise NoCompiler("nvcc not found: libcdgvae_sm100.so cannot be built")
     return nvcc
 
 

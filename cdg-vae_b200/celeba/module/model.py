@@ -274,7 +274,8 @@ class CDGVAE(ArenaModule):
         io.workspace, io.workspace_bytes, io.batch = _ptr(ws), ws.numel(), Bn
         io.backward, io.deterministic, io.encoder_passes, io.encode_only = int(backward), int(deterministic), int(encoder_passes), int(encode_only)
         io.logs = _ptr(logs_row)
-        _lib.check(_lib.lib().cdg_celeba_step(plan, C.byref(io), self._stream()))
+        with torch.cuda.device(self.arena_device):
+            _lib.check(_lib.lib().cdg_celeba_step(plan, C.byref(io), self._stream()))
         self._bump_counters(encoder_passes, generators=not encode_only)
         out["keep"] = keep
         return out
@@ -287,33 +288,13 @@ class CDGVAE(ArenaModule):
         return [n for n, _ in self._arena_named_parameters()]
 
     # -- the reference's public methods -------------------------------------------------------------------------------
-    @staticmethod
-    def _cols(t):
-        return list(torch.split(t, 1, dim=1))
-
-    def _logdet(self, log_determinant, batch):
-        if not log_determinant:
-            return [0] * self.config["node"]
-        if self.config["scm"] != "linear":
-            raise NotImplementedError("log_determinant=True is only provided for the linear SCM")
-        return [torch.log(f.p[0].abs()).repeat(batch, 1) for f in self.flows]
-
-    def inverse(self, input):
-        return list(map(lambda x, layer: layer.inverse(x), input, self.flows))       # model.py:153-155
-
     def get_posterior(self, input):
         L = self._run(x=input, deterministic=True, encoder_passes=1, encode_only=True, want_latents=True)["latents"]
         return L[0], L[1], L[6], L[7]
 
-    def transform(self, input, log_determinant=False):
-        latent = torch.matmul(input, self.I_B_inv)
-        orig_latent = latent.clone()
-        outs = [layer(c, log_determinant=log_determinant) for c, layer in zip(torch.split(latent, 1, dim=1), self.flows)]
-        return orig_latent, [o[0] for o in outs], [o[1] for o in outs]
-
     def encode(self, input, deterministic=False, log_determinant=False):
         L = self._run(x=input, deterministic=deterministic, encoder_passes=1, encode_only=True, want_latents=True)["latents"]
-        return ((L[0], L[1], L[2], L[3], self._cols(L[4]), self._logdet(log_determinant, input.shape[0])), (L[6], L[7], L[8]))
+        return ((L[0], L[1], L[2], L[3], self._cols(L[4]), self._logdet(log_determinant, L[3])), (L[6], L[7], L[8]))
 
     def decode(self, latent, epsilon2):
         o = self._run(latent_in=torch.cat(list(latent), dim=1), epsilon2_in=epsilon2, want_xhat=True, want_sep=True)
@@ -323,5 +304,5 @@ class CDGVAE(ArenaModule):
         o = self._run(x=input, deterministic=deterministic, encoder_passes=2, want_xhat=True, want_sep=True, want_latents=True)
         L = o["latents"]
         n = input.shape[0]
-        return ((L[0], L[1], L[2], L[3], self._cols(L[4]), self._logdet(log_determinant, n)), (L[6], L[7], L[8]),
+        return ((L[0], L[1], L[2], L[3], self._cols(L[4]), self._logdet(log_determinant, L[3])), (L[6], L[7], L[8]),
                 self._cols(L[5]), [s.permute(0, 3, 1, 2) for s in o["sep"].unbind(0)], o["xhat"])

@@ -9,6 +9,7 @@ the device and is read back once per call.
 import torch
 
 from ... import dist as _dist
+from ...modules.train import _lookahead
 from .model import LOG_KEYS
 
 
@@ -17,15 +18,14 @@ def train_CDGVAE(train_loader, model, config, optimizer, device):
         if k in config:
             model.config[k] = config[k]
     model.bind_optimizer(optimizer)
-    it = iter(train_loader)
-    xhat, n, nxt = None, 0, next(it, None)
-    while nxt is not None:
-        (x_batch, y_batch), nxt = nxt, next(it, None)
+    xhat, n = None, 0
+    # sized loaders are counted, anything else is read one batch ahead, to know which batch is the last (whose xhat is returned)
+    for (x_batch, y_batch), last in _lookahead(train_loader):
         rows = model._log_rows(n + 1, len(LOG_KEYS))
         noise = (model._noise(x_batch.shape[0]), model._noise(x_batch.shape[0]))        # model.py:182, :184
-        out = model.forward_backward(x_batch, y_batch, noise, rows[n], xhat=nxt is None)
+        out = model.forward_backward(x_batch, y_batch, noise, rows[n], xhat=last)
         model.adam_step(grad_scale=model.exchange_gradients())
-        if nxt is None:
+        if last:
             xhat = out["xhat"]                        # the reference returns the last batch's reconstruction (train.py:76)
         n += 1
     logs = {k: [] for k in LOG_KEYS}

@@ -11,6 +11,19 @@ namespace cdg {
 
 void set_error(const char* fmt, ...);
 
+// Experiment switches (tile variants measured slower, alternative kernels kept for A/B timing, timing probes whose results
+// are INVALID) exist only in builds made with -DCDG_EXPERIMENTS; the shipped library has every one of them fixed at its
+// default and does not read the environment for them.
+#ifdef CDG_EXPERIMENTS
+#include <stdlib.h>
+static inline int exp_switch(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#else
+#define exp_switch(name, dflt) (dflt)
+#endif
+
 #define CDG_CHECK_CUDA(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

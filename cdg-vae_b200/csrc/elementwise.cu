@@ -315,7 +315,13 @@ extern "C" int cdg_adam_step(float* params, const float* grads, float* exp_avg, 
 }
 
 extern "C" const char* cdg_last_error(void) { return cdg::get_error(); }
-extern "C" int cdg_version(void) { return 100; }
+extern "C" int cdg_version(void) { return 200; }
+extern "C" int64_t cdg_abi_sizeof(int which) {
+    static const int64_t sz[] = {sizeof(cdg_linear), sizeof(cdg_adam_args), sizeof(cdg_pendulum_config), sizeof(cdg_pendulum_io),
+                                 sizeof(cdg_pendulum_fwd_io), sizeof(cdg_tabular_config), sizeof(cdg_tabular_io), sizeof(cdg_conv),
+                                 sizeof(cdg_bnorm), sizeof(cdg_celeba_config), sizeof(cdg_celeba_io), sizeof(cdg_tvae_transform_config)};
+    return which >= 0 && which < (int)(sizeof(sz) / sizeof(sz[0])) ? sz[which] : -1;
+}
 extern "C" long long cdg_launch_count(void) { return cdg::g_launches; }
 extern "C" int cdg_device_ok(void) {
     int dev = 0;

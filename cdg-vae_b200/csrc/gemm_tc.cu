@@ -33,6 +33,12 @@
 
 namespace cdg {
 
+#ifdef CDG_EXPERIMENTS
+#define CDG_PROBE(p) ((p).probe)
+#else
+#define CDG_PROBE(p) 0          // the timing probes (skip conversion / skip TMA: results invalid) are not in the shipped kernels
+#endif
+
 namespace tc {
 
 constexpr int BM = 128;
@@ -702,7 +708,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(smem_u32(&bars[2 * STAGES + s]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bars[s]);
                     if (!elect_one()) continue;
-                    if (p.probe & 2) { mbar_arrive(full); continue; }
+                    if (CDG_PROBE(p) & 2) { mbar_arrive(full); continue; }
                     mbar_expect_tx(full, A_BYTES + C_::B_CTA_BYTES);
                     const int k0 = (kb_beg + i) * BK;
                     // the streamed operand comes from HBM: pull the tile needed PF K-blocks from now into L2
@@ -872,7 +878,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
-                if (p.probe & 1) {
+                if (CDG_PROBE(p) & 1) {
                     __syncwarp();
                     if (lane == 0) {
                         if (CTA2 && rank != 0) mbar_arrive_rank0(smem_u32(&bars[STAGES + s]));
@@ -1475,9 +1481,8 @@ struct Plan {
 };
 
 static bool no160() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CDG_TC_NO160"); v = (e && atoi(e) != 0) ? 1 : 0; }
-    return v == 1;
+    static const int v = exp_switch("CDG_TC_NO160", 0);
+    return v != 0;
 }
 // shape / layout analysis shared by gemm_tc and gemm_tc_can
 static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
@@ -1540,11 +1545,7 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
 
 // K-block of the 3xTF32 kernels: 16 (SWIZZLE_64B, 4 stages) unless CDG_TC_BK=32 asks for the 2-stage variant
 static int default_bk() {
-    static int bk = 0;
-    if (bk == 0) {
-        const char* e = getenv("CDG_TC_BK");
-        bk = (e && atoi(e) == 32) ? 32 : 16;
-    }
+    static const int bk = exp_switch("CDG_TC_BK", 16) == 32 ? 32 : 16;
     return bk;
 }
 
@@ -1576,22 +1577,16 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     p.tiles_n = (int)pl.tn; p.splits = splits; p.work_total = pl.tm * pl.tn * splits;
     p.extra = g.extra_col;
     {
-        static int sw = -1;
-        if (sw < 0) { const char* e = getenv("CDG_TC_A16SWAP"); sw = (e && atoi(e) != 0) ? 1 : 0; }
+        static const int sw = exp_switch("CDG_TC_A16SWAP", 0) != 0, sw32 = exp_switch("CDG_TC_SW32", 0) != 0;
         p.a16swap = sw;
-        static int sw32 = -1;
-        if (sw32 < 0) { const char* e = getenv("CDG_TC_SW32"); sw32 = (e && atoi(e) != 0) ? 1 : 0; }
         p.sw32 = sw32;
     }
     p.conv_cb = g.conv_C > 0 ? g.conv_C / BK : 0; p.conv_W = g.conv_W; p.conv_H = g.conv_H; p.conv_k = g.conv_k;
     {
-        static int rawhi = -1;
         // default on: measured on B200, tcgen05 kind::tf32 ignores the 13 low mantissa bits (results with the raw
-        // tile as `hi` match the explicitly rounded split to 2e-7); CDG_TC_RAWHI=0 restores the explicit rewrite
-        if (rawhi < 0) { const char* e = getenv("CDG_TC_RAWHI"); rawhi = (e && atoi(e) == 0) ? 0 : 1; }
+        // tile as `hi` match the explicitly rounded split to 2e-7)
+        static const int rawhi = exp_switch("CDG_TC_RAWHI", 1) != 0, probe = exp_switch("CDG_TC_PROBE", 0);
         p.rawhi = rawhi;
-        static int probe = -1;
-        if (probe < 0) { const char* e = getenv("CDG_TC_PROBE"); probe = e ? atoi(e) : 0; }
         p.probe = probe;
     }
     // 128-bit epilogue path: row-major output whose rows, bias, aux and recon operands are 16-byte aligned
@@ -1630,17 +1625,14 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     }
     dim3 grid((unsigned)imin64(p.work_total, kNumSMs));
     int r;
-    static int no_stg = -1;
-    // measured on B200: 7.8 vs 7.1 ms per step for the decoder-output GEMMs -> off unless CDG_TC_STG=1
-    if (no_stg < 0) { const char* e = getenv("CDG_TC_STG"); no_stg = (e && atoi(e) != 0) ? 0 : 1; }
-    static int cta2 = -1;
-    if (cta2 < 0) { const char* e = getenv("CDG_TC_CTA2"); cta2 = (e && atoi(e) == 0) ? 0 : 1; }
+    // single-buffered staged epilogue, measured on B200: 7.8 vs 7.1 ms per step for the decoder-output GEMMs -> experiments only
+    static const int no_stg = exp_switch("CDG_TC_STG", 0) == 0;
+    static const int cta2 = exp_switch("CDG_TC_CTA2", 1) != 0;
     // transposing epilogue of the fused reconstruction head (row-coalesced 128-byte accesses through a shared-memory
     // scratch).  Measured on B200: dec2 forward 13.3 vs 6.5 ms per step -- four 32-bit memory instructions per element
     // (STS, LDS, LDG, STG) instead of half a 256-bit one: the single epilogue warp per scheduler is bound by the number of
     // memory instructions it can issue, not by how the sectors coalesce.  Off unless CDG_TC_EPI_TR=1.
-    static int epi_tr = -1;
-    if (epi_tr < 0) { const char* e = getenv("CDG_TC_EPI_TR"); epi_tr = (e && atoi(e) != 0) ? 1 : 0; }
+    static const int epi_tr = exp_switch("CDG_TC_EPI_TR", 0) != 0;
     p.tr = epi_tr;
     if (passes == 2 && p.b_pre && cta2 && (BN == 304 || BN == 256 || BN == 160) && g.M >= 1024 && g.conv_C == 0) {
         // CTA pairs: a work item is two 128-row blocks; each CTA stages half of the B rows of each MMA

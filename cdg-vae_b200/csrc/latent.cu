@@ -180,4 +180,78 @@ int launch_latent_bwd(const LatentArgs& a, cudaStream_t s) {
     return CDG_OK;
 }
 
+// ---- stand-alone flow evaluation (evaluation scripts: inference.py:302-317, metric.py:226-255) -----------------------
+// One thread per (row, node).  direction 0: out = flow_j(in) [+ log|det|], direction 1: out = flow_j^-1(in).
+//   InvertiblePriorLinear (modules/model.py:20-29): o = p0 e + p1, log|p0|;  inverse (o - p1) / p0.
+//   PlanarFlows (modules/model.py:77-100), input_dim = 1: forward h <- h + u_hat ELU(h w + b) with
+//   logdet += log|1 + ELU'(h w + b) w u_hat| (evaluated before the update, :91-98); inverse = flows in reverse order,
+//   each `inverse_loop` fixed-point iterations z <- h - u_hat ELU(z w + b) started at z = h (:80-84).
+struct FlowApplyArgs {
+    int d, scm, flow_num, loops, direction;
+    float A[1];                   // (load_flow_table's interface; the causal matrix is not used here)
+    int64_t batch, ld_in, ld_out, ld_logdet;
+    const float* params;
+    int64_t flow_off[CDG_MAX_NODE];
+    const float* in;
+    float* out;
+    float* logdet;
+};
+
+__global__ void __launch_bounds__(256) flow_apply_kernel(FlowApplyArgs a) {
+    __shared__ FlowTable ft;
+    load_flow_table(ft, a);
+    __syncthreads();
+    const int d = a.d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.batch * d; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d;
+        const int j = (int)(i - r * d);
+        float h = a.in[r * a.ld_in + j];
+        float ld = 0.f;
+        if (a.scm == CDG_SCM_LINEAR) {
+            if (a.direction == 0) { h = ft.w[j][0] * h + ft.b[j][0]; ld = logf(fabsf(ft.w[j][0])); }
+            else h = (h - ft.b[j][0]) / ft.w[j][0];
+        } else if (a.direction == 0) {
+            for (int f = 0; f < a.flow_num; ++f) {
+                const float w = ft.w[j][f], uh = ft.uhat[j][f];
+                const float x = h * w + ft.b[j][f];
+                const float grad = x > 0.f ? 1.f : expf(x);
+                ld += logf(fabsf(1.f + (grad * w) * uh));
+                h = h + uh * elu_ref(x);
+            }
+        } else {
+            for (int f = a.flow_num - 1; f >= 0; --f) {
+                const float w = ft.w[j][f], uh = ft.uhat[j][f], b = ft.b[j][f];
+                float z = h;
+                for (int it = 0; it < a.loops; ++it) z = h - uh * elu_ref(z * w + b);
+                h = z;
+            }
+        }
+        a.out[r * a.ld_out + j] = h;
+        if (a.logdet) a.logdet[r * a.ld_logdet + j] = ld;
+    }
+}
+
 }  // namespace cdg
+
+extern "C" int cdg_flow_apply(int scm, int flow_num, int inverse_loop, int node, const float* params, const int64_t* flow_off,
+                              const float* in, int64_t ld_in, float* out, int64_t ld_out, float* logdet, int64_t ld_logdet,
+                              int64_t batch, int direction, void* stream) {
+    using namespace cdg;
+    CDG_REQUIRE(params && flow_off && in && out, "cdg_flow_apply: null argument");
+    CDG_REQUIRE(scm == CDG_SCM_LINEAR || scm == CDG_SCM_PLANAR, "Not supported SCM!");
+    CDG_REQUIRE(node >= 1 && node <= CDG_MAX_NODE, "cdg_flow_apply: node=%d out of range", node);
+    CDG_REQUIRE(scm == CDG_SCM_LINEAR || (flow_num >= 1 && flow_num <= CDG_MAX_FLOW), "cdg_flow_apply: flow_num=%d out of range", flow_num);
+    CDG_REQUIRE(direction == 0 || direction == 1, "cdg_flow_apply: direction must be 0 (forward) or 1 (inverse)");
+    CDG_REQUIRE(inverse_loop >= 0 && ld_in >= node && ld_out >= node && (!logdet || ld_logdet >= node), "cdg_flow_apply: bad extents");
+    if (batch <= 0) return CDG_OK;
+    FlowApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = node; a.scm = scm; a.flow_num = scm == CDG_SCM_LINEAR ? 1 : flow_num; a.loops = inverse_loop; a.direction = direction;
+    a.batch = batch; a.ld_in = ld_in; a.ld_out = ld_out; a.ld_logdet = ld_logdet;
+    a.params = params; a.in = in; a.out = out; a.logdet = logdet;
+    for (int i = 0; i < node; ++i) a.flow_off[i] = flow_off[i];
+    const int64_t n = batch * node;
+    flow_apply_kernel<<<(int)imin64((n + 255) / 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(a);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}

@@ -48,7 +48,7 @@ __device__ __forceinline__ float elu_ref(float t) { return t > 0.f ? t : expf(t)
 template <typename Args>
 __device__ __forceinline__ void load_flow_table(FlowTable& ft, const Args& a) {
     const int d = a.d;
-    for (int i = threadIdx.x; i < d * d; i += blockDim.x) ft.A[i] = a.A[i];
+    for (int i = threadIdx.x; i < d * d && i < (int)(sizeof(a.A) / sizeof(float)); i += blockDim.x) ft.A[i] = a.A[i];
     for (int t = threadIdx.x; t < d * CDG_MAX_FLOW; t += blockDim.x) {
         const int i = t / CDG_MAX_FLOW, f = t % CDG_MAX_FLOW;
         const float* p = a.params + a.flow_off[i];

@@ -241,7 +241,7 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
                          (!(g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT) || (((uintptr_t)g.bias) & 15) == 0) &&
                          (g.epi != EPI_MUL_DACT || (g.ld_aux % 4 == 0 && (((uintptr_t)g.aux) & 15) == 0));
         static int rows_ok = -1;           // CDG_SKINNY_ROWS=0 restores the element-indexed kernels
-        if (rows_ok < 0) { const char* e = getenv("CDG_SKINNY_ROWS"); rows_ok = (e && atoi(e) == 0) ? 0 : 1; }
+        if (rows_ok < 0) rows_ok = exp_switch("CDG_SKINNY_ROWS", 1) != 0;
         if (rows_ok && vec && g.M >= 64 && g.K * g.N <= 8192 && g.N >= 128) {
             const size_t smem = sizeof(float) * (size_t)(g.K * g.N + g.N);
             const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 8);
@@ -258,7 +258,7 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
     }
     if (g.N <= 8 && g.sa_k == 1 && (g.epi == EPI_NONE || g.epi == EPI_BIAS)) {
         static int rows_ok = -1;
-        if (rows_ok < 0) { const char* e = getenv("CDG_SKINNY_ROWS"); rows_ok = (e && atoi(e) == 0) ? 0 : 1; }
+        if (rows_ok < 0) rows_ok = exp_switch("CDG_SKINNY_ROWS", 1) != 0;
         if (rows_ok && g.M >= 64 && g.K % 4 == 0 && g.K >= 128 && g.N * g.K <= 8192 && g.sa_m % 4 == 0 && (((uintptr_t)g.A) & 15) == 0) {
             const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 8);
             rowdot_rows_kernel<<<blocks, 256, sizeof(float) * (size_t)(g.N * g.K), s>>>(g);

@@ -402,7 +402,7 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
     int64_t blocks = (io->batch + TAB_THREADS - 1) / TAB_THREADS;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     // the three fixed CDG-VAE tables have a compile-time specialised kernel (tabular_fixed.cu)
-    static const bool generic_only = getenv("CDG_TAB_GENERIC") != nullptr;
+    static const bool generic_only = exp_switch("CDG_TAB_GENERIC", 0) != 0;
     if (generic_only || !(launch_tab_fixed(a, (unsigned)blocks, smem, s) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
         tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
     CDG_CHECK_LAUNCH();

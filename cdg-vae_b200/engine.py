@@ -25,6 +25,24 @@ def _f32c(t, device):
     return t.contiguous()
 
 
+def flow_apply(scm, flow_num, inverse_loop, params, offsets, x, direction, log_determinant=False):
+    """`cdg_flow_apply` on a [batch, node] matrix: every node's flow (direction 0) or its inverse (1) in one launch.
+    `params`: fp32 device tensor holding the flow parameters, `offsets[j]`: float offset of node j's block in it."""
+    dev = _lib.require_cuda(params.device)
+    x = _f32c(x, dev)
+    if x.dim() != 2 or x.shape[1] != len(offsets):
+        raise ValueError(f"flow input must be [batch, {len(offsets)}], got {tuple(x.shape)}")
+    out = torch.empty_like(x)
+    logdet = torch.empty_like(x) if log_determinant else None
+    off = (C.c_int64 * len(offsets))(*[int(o) for o in offsets])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cdg_flow_apply(_lib.SCM[scm], int(flow_num), int(inverse_loop), len(offsets), _ptr(params), off,
+                                             _ptr(x), x.stride(0), _ptr(out), out.stride(0), _ptr(logdet),
+                                             0 if logdet is None else logdet.stride(0), x.shape[0], int(direction),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out, logdet
+
+
 class ArenaModule(nn.Module):
     """nn.Module whose parameters live in one flat arena (params / grads / exp_avg / exp_avg_sq)."""
 
@@ -146,8 +164,12 @@ class ArenaModule(nn.Module):
     def bind_optimizer(self, opt):
         """Make `opt.state[p]['exp_avg'|'exp_avg_sq']` views of the arena-shaped moment buffers and
         remember the hyper-parameters' source.  torch.optim.Adam only (the reference's optimizer)."""
-        if self._bound_opt is opt:
+        if self._bound_opt is opt and self._still_bound(opt):
             return
+        if self._bound_opt is opt:
+            # optimizer.load_state_dict() (or anything else) replaced the state tensors after binding: copy the new
+            # moments / step counts into the arenas below and forget graphs captured with the old device step
+            self.drop_graphs()
         if not isinstance(opt, torch.optim.Adam) or isinstance(opt, torch.optim.AdamW):
             raise TypeError("the reference trains with torch.optim.Adam; got %s" % type(opt).__name__)
         mine = {id(p): n for n, p in self._arena_named_parameters()}
@@ -184,8 +206,22 @@ class ArenaModule(nn.Module):
         self._step_count = step
         self._bound_opt = opt
 
+    def _still_bound(self, opt):
+        """True while every live parameter's `exp_avg` / `exp_avg_sq` in `opt.state` is still the arena view bound earlier."""
+        live = set(self.live_param_names())
+        for name, p in self._arena_named_parameters():
+            if name not in live:
+                continue
+            st = opt.state.get(p)
+            o = self._offsets[name]
+            if (not st or "exp_avg" not in st or st["exp_avg"].data_ptr() != self._exp_avg[o:].data_ptr()
+                    or st["exp_avg_sq"].data_ptr() != self._exp_avg_sq[o:].data_ptr()):
+                return False
+        return all(a is b for a, b in zip(self._step_tensors, (opt.state[p]["step"] for n, p in self._arena_named_parameters() if n in live)))
+
     # -- CUDA graphs for launch-bound (small-batch) steps ---------------------------------------
     GRAPH_MAX_ROWS = 4096      # above this the step is GPU-bound and graphs buy nothing
+    GRAPH_MAX_KEYS = 8         # captured graphs kept per model (least recently used dropped first)
 
     def graphed_step(self, key, inputs, body):
         """Run `body(static_inputs) -> dict of output tensors` as a replayed CUDA graph.
@@ -196,8 +232,19 @@ class ArenaModule(nn.Module):
         then on it is replayed: inputs are copied into the graph's static buffers, outputs are read from them.
         """
         cache = self.__dict__.setdefault("_graphs", {})
-        ent = cache.get(key)
+        ent = cache.pop(key, None)
+        if ent is not None:
+            cache[key] = ent                                   # most recently used last
         if ent is None:
+            # the key holds hyper-parameters (lr, beta, lambda): a scheduler stepping them every iteration must not grow
+            # one graph (static buffers + memory pool) per value -- keep the last few, and give graphs up when keys churn
+            self._graph_misses = getattr(self, "_graph_misses", 0) + 1
+            if self._graph_misses > self.GRAPH_MAX_KEYS * 4:
+                self.use_graphs = False
+                self.drop_graphs()
+                return body(inputs)
+            while len(cache) >= self.GRAPH_MAX_KEYS:
+                cache.pop(next(iter(cache)))
             cache[key] = "seen"
             return body(inputs)
         if ent == "seen":
@@ -263,9 +310,36 @@ class ArenaModule(nn.Module):
         else:
             a.clamp_off, a.clamp_len = -1, 0
         stream = torch.cuda.current_stream(self.arena_device).cuda_stream
-        _lib.check(_lib.lib().cdg_adam_step(_ptr(self._arena), _ptr(self._grads), _ptr(self._exp_avg),
-                                            _ptr(self._exp_avg_sq), C.byref(a), C.c_void_p(stream)))
+        with torch.cuda.device(self.arena_device):
+            _lib.check(_lib.lib().cdg_adam_step(_ptr(self._arena), _ptr(self._grads), _ptr(self._exp_avg),
+                                                _ptr(self._exp_avg_sq), C.byref(a), C.c_void_p(stream)))
         torch._foreach_add_(self._step_tensors, 1.0)
+
+    # -- the causal flows as the evaluation scripts call them (shared by every model family) -----
+    @staticmethod
+    def _cols(t):
+        return list(torch.split(t, 1, dim=1))
+
+    def _flows(self, x, direction, log_determinant=False):
+        """All node flows on a [batch, node] matrix in one launch (parameters read in place from the arena)."""
+        cfg = self.config
+        return flow_apply(cfg["scm"], cfg.get("flow_num", 1), cfg.get("inverse_loop", 100), self._arena,
+                          self._flow_offsets(cfg["node"]), x, direction, log_determinant)
+
+    def _logdet(self, log_determinant, orig_latent):
+        if not log_determinant:
+            return [0] * self.config["node"]
+        return self._cols(self._flows(orig_latent, 0, True)[1])                      # modules/model.py:22-25, :91-98
+
+    def inverse(self, input):
+        return self._cols(self._flows(torch.cat(list(input), dim=1), 1)[0])          # modules/model.py:252-254
+
+    def transform(self, input, log_determinant=False):
+        """u = input @ I_B_inv, then the per-node flows (modules/model.py:261-268).  The d x d product is bookkeeping on a
+        [batch, d] matrix (torch.matmul on the device); the flows and their log|det| run in cdg_flow_apply."""
+        orig_latent = torch.matmul(_f32c(input, self.arena_device), self.I_B_inv.to(self.arena_device))
+        z, ld = self._flows(orig_latent, 0, log_determinant)
+        return orig_latent, self._cols(z), (self._cols(ld) if log_determinant else [0] * self.config["node"])
 
     # -- data parallel -------------------------------------------------------------------------
     def exchange_gradients(self):

@@ -12,63 +12,54 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..engine import ArenaModule, _f32c, _ptr
+from ..engine import ArenaModule, _f32c, _ptr, flow_apply
 
 
 class InvertiblePriorLinear(nn.Module):
-    """Per-node affine flow o = p[0] * eps + p[1] (modules/model.py:8-29).  Holds the parameter;
-    inside CDGVAE the evaluation is fused into the latent kernels."""
+    """Per-node affine flow o = p[0] * eps + p[1] (modules/model.py:8-29).  Holds the parameter; inside CDGVAE's step the
+    evaluation is fused into the latent kernels, stand-alone calls (inference.py:317) run `cdg_flow_apply`."""
 
     def __init__(self, device="cpu"):
         super().__init__()
         self.p = nn.Parameter(torch.rand([2], device=device) * 0.1)        # model.py:18
 
     def forward(self, eps, log_determinant=False):
-        o = self.p[0] * eps + self.p[1]
-        logdet = 0
-        if log_determinant:
-            logdet += torch.log(self.p[0].abs()).repeat(eps.size(0), 1)
-        return o, logdet
+        o, ld = flow_apply("linear", 1, 0, self.p.data, [0], eps, 0, log_determinant)
+        return o, (ld if log_determinant else 0)                            # model.py:20-25
 
     def inverse(self, o):
-        return (o - self.p[1]) / self.p[0]
+        return flow_apply("linear", 1, 0, self.p.data, [0], o, 1)[0]       # model.py:27-29
 
 
 class PlanarFlows(nn.Module):
-    """ELU planar flow with the invertibility re-parameterisation of u (modules/model.py:31-100)."""
+    """ELU planar flow with the invertibility re-parameterisation of u (modules/model.py:31-100), input_dim = 1 as every
+    reference model builds it.  The arithmetic (build_u, the forward map with log|det|, the `inverse_loop` fixed-point
+    inverse) runs in `cdg_flow_apply`; inside CDGVAE's step it is fused into the latent kernels."""
 
     def __init__(self, input_dim, flow_num, inverse_loop, device="cpu"):
         super().__init__()
+        if input_dim != 1:
+            raise ValueError("PlanarFlows: the reference only instantiates input_dim = 1 (modules/model.py:236); other widths are not built")
         self.input_dim, self.flow_num, self.inverse_loop, self.device = input_dim, flow_num, inverse_loop, device
         self.alpha = torch.tensor(1, dtype=torch.float32).to(device)
         self.w = nn.ParameterList([nn.Parameter(torch.randn(input_dim, 1, device=device) * 0.1) for _ in range(flow_num)])
         self.b = nn.ParameterList([nn.Parameter(torch.randn(1, 1, device=device) * 0.1) for _ in range(flow_num)])
         self.u = nn.ParameterList([nn.Parameter(torch.randn(input_dim, 1, device=device) * 0.1) for _ in range(flow_num)])
 
-    def build_u(self, u_, w_):
-        wu = w_.t() @ u_
-        return u_ + ((-1 + torch.log(1 + torch.exp(wu))) - wu) * (w_ / torch.norm(w_, p=2) ** 2)
-
-    def inverse(self, inputs):
-        h = inputs
-        for j in reversed(range(self.flow_num)):
-            z = h
-            u_ = self.build_u(self.u[j], self.w[j])
-            for _ in range(self.inverse_loop):
-                z = h - u_.t() * nn.functional.elu(z @ self.w[j] + self.b[j])
-            h = z
-        return h
+    def _packed(self):
+        """{w[F], b[F], u[F]} as one contiguous fp32 block: the arena already lays a node's scalars out that way."""
+        ts = [t.data for t in list(self.w) + list(self.b) + list(self.u)]
+        base = ts[0]
+        if all(t.dtype == torch.float32 and t.device == base.device and t.data_ptr() == base.data_ptr() + 4 * i for i, t in enumerate(ts)):
+            return torch.as_strided(base, (len(ts),), (1,))
+        return torch.cat([t.reshape(-1).float() for t in ts])
 
     def forward(self, inputs, log_determinant=False):
-        h, logdet = inputs, 0
-        for j in range(self.flow_num):
-            u_ = self.build_u(self.u[j], self.w[j])
-            if log_determinant:
-                x = h @ self.w[j] + self.b[j]
-                gradient = torch.where(x > 0, torch.ones_like(x), torch.exp(x))
-                logdet += torch.log((1 + (gradient * self.w[j].squeeze()) @ u_).abs())
-            h = h + u_.t() * nn.functional.elu(h @ self.w[j] + self.b[j])
-        return h, logdet
+        o, ld = flow_apply("nonlinear", self.flow_num, self.inverse_loop, self._packed(), [0], inputs, 0, log_determinant)
+        return o, (ld if log_determinant else 0)
+
+    def inverse(self, inputs):
+        return flow_apply("nonlinear", self.flow_num, self.inverse_loop, self._packed(), [0], inputs, 1)[0]
 
 
 def mask_ranges(mask, n_cols):
@@ -194,10 +185,12 @@ class CDGVAE(ArenaModule):
         so Adam leaves them bit-unchanged."""
         segs, H = [], self.HIDDEN
         shapes = {n: p.numel() for n, p in self.named_parameters()}
+        # with weight decay the reference's update of those rows is not zero (g = wd * p): then every row is live
+        decays = bool(getattr(self, "_opt_group", None)) and float(self._opt_group.get("weight_decay", 0.0)) != 0.0
         for n in self.live_param_names():
             o = self._offsets[n]
             parts = n.split(".")
-            if parts[0] == "decoder" and len(parts) == 4 and parts[2] == "4":
+            if not decays and parts[0] == "decoder" and len(parts) == 4 and parts[2] == "4":
                 lo, hi = self._ranges[int(parts[1])]
                 w = H if parts[3] == "weight" else 1
                 segs.append((o + lo * w, (hi - lo) * w))
@@ -268,7 +261,8 @@ class CDGVAE(ArenaModule):
         io.logs = _ptr(logs_row)
         io.xhat = _ptr(xhat)
         io.masks = _ptr(self._masks_dev())
-        _lib.check(_lib.lib().cdg_pendulum_forward_backward(plan, C.byref(io), self._stream()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cdg_pendulum_forward_backward(plan, C.byref(io), self._stream()))
         return keep
 
     # -- inference API (modules/model.py:252-304) ---------------------------------------------------
@@ -304,40 +298,19 @@ class CDGVAE(ArenaModule):
         ws = self._get_workspace(nbytes)
         io.workspace, io.workspace_bytes, io.batch, io.deterministic = _ptr(ws), ws.numel(), Bn, int(deterministic)
         io.masks = _ptr(self._masks_dev())
-        _lib.check(_lib.lib().cdg_pendulum_forward(plan, C.byref(io), self._stream()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cdg_pendulum_forward(plan, C.byref(io), self._stream()))
         return out
-
-    @staticmethod
-    def _cols(t):
-        return list(torch.split(t, 1, dim=1))
-
-    def _logdet(self, log_determinant, batch):
-        if not log_determinant:
-            return [0] * self.config["node"]
-        if self.config["scm"] != "linear":
-            raise NotImplementedError("log_determinant=True is only provided for the linear SCM")
-        return [torch.log(f.p[0].abs()).repeat(batch, 1) for f in self.flows]
-
-    def inverse(self, input):
-        return list(map(lambda x, layer: layer.inverse(x), input, self.flows))      # model.py:252-254
 
     def get_posterior(self, input):
         o = self._run_forward(x=input, deterministic=True, want=("mean", "logvar"))
         return o["mean"], o["logvar"]
 
-    def transform(self, input, log_determinant=False):
-        """u = input @ I_B_inv, then the per-node flows (model.py:261-268).  Off the hot path: evaluated
-        with the parameter views (autograd-capable) rather than a dedicated kernel."""
-        latent = torch.matmul(input, self.I_B_inv)
-        orig_latent = latent.clone()
-        outs = [layer(c, log_determinant=log_determinant) for c, layer in zip(torch.split(latent, 1, dim=1), self.flows)]
-        return orig_latent, [o[0] for o in outs], [o[1] for o in outs]
-
     def encode(self, input, deterministic=False, log_determinant=False):
         o = self._run_forward(x=input, deterministic=deterministic,
                               want=("mean", "logvar", "epsilon", "orig_latent", "latent"))
         return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
-                self._logdet(log_determinant, input.shape[0]))
+                self._logdet(log_determinant, o["orig_latent"]))
 
     def decode(self, input):
         s = self.config["image_size"]
@@ -350,7 +323,7 @@ class CDGVAE(ArenaModule):
                               want=("mean", "logvar", "epsilon", "orig_latent", "latent", "align_latent",
                                     "xhat_separated", "xhat"))
         return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
-                self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]),
+                self._logdet(log_determinant, o["orig_latent"]), self._cols(o["align_latent"]),
                 list(o["xhat_separated"].unbind(0)), o["xhat"].view(-1, s, s, 3))
 
 
@@ -417,7 +390,7 @@ class VAE(CDGVAE):
         o = self._run_forward(x=input, deterministic=deterministic,
                               want=("mean", "logvar", "epsilon", "orig_latent", "latent", "align_latent", "xhat"))
         return (o["mean"], o["logvar"], o["epsilon"], o["orig_latent"], self._cols(o["latent"]),
-                self._logdet(log_determinant, input.shape[0]), self._cols(o["align_latent"]), o["xhat"].view(-1, s, s, 3))
+                self._logdet(log_determinant, o["orig_latent"]), self._cols(o["align_latent"]), o["xhat"].view(-1, s, s, 3))
 
 
 class Discriminator(ArenaModule):

@@ -137,7 +137,8 @@ class _TabularBase(ArenaModule):
         ws = self._get_workspace(256)
         io.params, io.grads, io.workspace, io.workspace_bytes = _ptr(self._arena), _ptr(self._grads), _ptr(ws), ws.numel()
         io.x, io.y, io.noise, io.batch, io.logs = _ptr(x), _ptr(y), _ptr(noise), x.shape[0], _ptr(logs_row)
-        _lib.check(_lib.lib().cdg_tabular_forward_backward(plan, C.byref(io), self._stream()))
+        with torch.cuda.device(self.arena_device):
+            _lib.check(_lib.lib().cdg_tabular_forward_backward(plan, C.byref(io), self._stream()))
         return [x, y, noise]
 
     # -- inference API ---------------------------------------------------------------------------------
@@ -156,36 +157,17 @@ class _TabularBase(ArenaModule):
         xhat = torch.empty(Bn, int(sum(self.mask)), device=dev)
         lat = torch.empty(Bn, 6 * d, device=dev)
         io.xhat, io.latents = _ptr(xhat), _ptr(lat)
-        _lib.check(_lib.lib().cdg_tabular_forward(plan, C.byref(io), int(deterministic), self._stream()))
+        with torch.cuda.device(self.arena_device):
+            _lib.check(_lib.lib().cdg_tabular_forward(plan, C.byref(io), int(deterministic), self._stream()))
         return xhat, lat
 
     def _default_ft(self):
         return None
 
-    @staticmethod
-    def _cols(t):
-        return list(torch.split(t, 1, dim=1))
-
-    def _logdet(self, log_determinant, batch):
-        if not log_determinant:
-            return [0] * self.config["node"]
-        if self.config["scm"] != "linear":
-            raise NotImplementedError("log_determinant=True is only provided for the linear SCM")
-        return [torch.log(f.p[0].abs()).repeat(batch, 1) for f in self.flows]
-
-    def inverse(self, input):
-        return list(map(lambda x, layer: layer.inverse(x), input, self.flows))
-
     def get_posterior(self, input):
         d = self.config["node"]
         _, lat = self._run_forward(input, deterministic=True)
         return lat[:, :d].contiguous(), lat[:, d:2 * d].contiguous()
-
-    def transform(self, input, log_determinant=False):
-        latent = torch.matmul(input, self.I_B_inv)
-        orig_latent = latent.clone()
-        outs = [layer(c, log_determinant=log_determinant) for c, layer in zip(torch.split(latent, 1, dim=1), self.flows)]
-        return orig_latent, [o[0] for o in outs], [o[1] for o in outs]
 
     def _unpack(self, lat):
         d = self.config["node"]
@@ -194,7 +176,7 @@ class _TabularBase(ArenaModule):
     def encode(self, input, deterministic=False, log_determinant=False):
         _, lat = self._run_forward(input, deterministic=deterministic)
         mean, logvar, eps, orig, z, _ = self._unpack(lat)
-        return mean, logvar, eps, orig, self._cols(z), self._logdet(log_determinant, input.shape[0])
+        return mean, logvar, eps, orig, self._cols(z), self._logdet(log_determinant, orig)
 
     def decode(self, input):
         """xhat_separated, xhat = cat (model.py:337-342).  Off the hot path: evaluated with the parameter views."""
@@ -206,7 +188,7 @@ class _TabularBase(ArenaModule):
         xhat, lat = self._run_forward(input, deterministic=deterministic)
         mean, logvar, eps, orig, z, zal = self._unpack(lat)
         sep = list(torch.split(xhat, [int(m) for m in self.mask], dim=1))
-        return (mean, logvar, eps, orig, self._cols(z), self._logdet(log_determinant, input.shape[0]), self._cols(zal),
+        return (mean, logvar, eps, orig, self._cols(z), self._logdet(log_determinant, orig), self._cols(zal),
                 sep, xhat)
 
 

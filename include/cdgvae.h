@@ -43,6 +43,11 @@ int cdg_version(void);
 int cdg_device_ok(void);
 /* Number of kernels this library has launched so far in this process (host-side counter). */
 long long cdg_launch_count(void);
+/* sizeof() of the i-th struct of this header as the library was compiled (order: cdg_linear, cdg_adam_args,
+ * cdg_pendulum_config, cdg_pendulum_io, cdg_pendulum_fwd_io, cdg_tabular_config, cdg_tabular_io, cdg_conv, cdg_bnorm,
+ * cdg_celeba_config, cdg_celeba_io, cdg_tvae_transform_config); -1 past the end.  A binding compares these with its own
+ * struct declarations at load time, so a stale library is refused instead of being fed mismatched layouts. */
+int64_t cdg_abi_sizeof(int which);
 
 /* A Linear layer's weight [out,in] and bias [out] as float offsets into the parameter arena
  * (the gradient / exp_avg / exp_avg_sq arenas share the layout). */
@@ -156,6 +161,15 @@ typedef struct {
 } cdg_pendulum_fwd_io;
 
 int cdg_pendulum_forward(cdg_pendulum_plan* p, const cdg_pendulum_fwd_io* io, void* stream);
+
+/* Stand-alone evaluation of the per-node flows on [batch, node] matrices (one launch for all nodes): the forward map with
+ * optional log|det| (InvertiblePriorLinear.forward modules/model.py:20-25, PlanarFlows.forward :87-100) or the inverse
+ * (InvertiblePriorLinear.inverse :27-29; PlanarFlows.inverse :77-85: `inverse_loop` fixed-point iterations per flow).
+ * `params` + flow_off[j] points at node j's parameters ({p0, p1} | {w[F], b[F], u[F]}); direction 0 = forward, 1 = inverse.
+ * Replaces the evaluation scripts' `model.inverse(...)` / `layer(x)` calls (inference.py:302-317, metric.py:226-255). */
+int cdg_flow_apply(int scm, int flow_num, int inverse_loop, int node, const float* params, const int64_t* flow_off,
+                   const float* in, int64_t ld_in, float* out, int64_t ld_out, float* logdet, int64_t ld_logdet,
+                   int64_t batch, int direction, void* stream);
 
 /* Optional device-side timing of the step by kernel category (cudaEvents recorded on the caller's stream
  * between the launches of cdg_pendulum_forward_backward).  cdg_pendulum_profile_read synchronises on the
