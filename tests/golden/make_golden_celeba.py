@@ -148,9 +148,42 @@ def celeba_case(name, scm, batch, nsteps):
     return case
 
 
+def celeba_free_case(name, batch, nsteps):
+    """`nsteps` consecutive reference steps (free-running: nothing is re-synchronised); per-step logs and the trainable
+    parameters after the last step.  The product is compared with this trajectory in tests/test_free_running_gpu.py."""
+    config = dict(node=6, latent_dim=6, scm="linear", flow_num=1, inverse_loop=100, beta=0.1, cuda=False, lr=1e-3,
+                  seed=1, batch_size=batch)
+    config["lambda"] = 5.0
+    x0 = corc.synth_celeba(batch, 1234, 4321)[0]
+    masks = torch.split(x0[..., 3:], 1, dim=-1)
+    torch.manual_seed(config["seed"])
+    model = rm.CDGVAE(corc.celeba_B(), masks, config, "cpu")
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=config["lr"])
+    case = {"name": name, "family": "celeba", "config": {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
+            "steps": []}
+    for s in range(nsteps):
+        x, y, n1, n2 = corc.synth_celeba(batch, 1234 + s, 4321 + s)
+        with NoiseInjector([n1, n2]):
+            logs, _ = rt.train_CDGVAE([(x, y)], model, config, opt, "cpu")
+        case["steps"].append({"logs": {k: float(v[0]) for k, v in logs.items()}})
+    case["final_params"] = {n: summary(p) for n, p in model.named_parameters() if p.requires_grad}
+    print(f"{name}: {nsteps} free-running reference steps")
+    return case
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
-    for c in (celeba_case("celeba_linear", "linear", 2, 2), celeba_case("celeba_nonlinear", "nonlinear", 2, 1)):
+    if sys.argv[1:] == ["celeba_free6"]:
+        c = celeba_free_case("celeba_free6", 2, 6)
+        with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
+            json.dump(c, f)
+        print("wrote", c["name"])
+        return
+    # celeba_b16_linear: the reference's own batch (celeba/main.py:70), one step
+    cases = {"celeba_linear": ("linear", 2, 2), "celeba_nonlinear": ("nonlinear", 2, 1), "celeba_b16_linear": ("linear", 16, 1)}
+    want = sys.argv[1:] or list(cases)
+    for c in (celeba_case(n, *cases[n]) for n in want):
         with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
             json.dump(c, f)
         print("wrote", c["name"], os.path.getsize(os.path.join(OUT, c["name"] + ".json")), "bytes")

@@ -8,8 +8,9 @@ five train-mode-BatchNorm generators at tiny batch: heavy cancellation).  They a
 oracle at GRAD_RTOL = 1e-2, i.e. the CUDA path must be as close to the exact gradient as the reference itself is
 (tools/celeba_grad_noise.py prints the three-way comparison: fp32 oracle, tcgen05 3xTF32 path, SIMT fp32 path); the 12
 flow scalars are compared as one gradient vector (a component that is tiny next to its neighbours carries the absolute
-noise of the whole vector).  The single layers are compared with torch at 1e-5.  Updated parameters: within Adam's 2*lr
-bound per step.
+noise of the whole vector).  The single layers are compared with torch at 1e-5.  Updated parameters: 1e-4 relative on
+every element whose gradient stands clear of the noise floor (adam_param_check below), Adam's 2*lr bound on the rest.
+Batches: 2 (two teacher-forced steps) and the reference's own 16 (celeba/main.py:70).
 """
 import ctypes as C
 
@@ -112,7 +113,23 @@ def _build(scm, batch):
     return cfg, model, masks
 
 
-@pytest.mark.parametrize("name", ["celeba_linear", "celeba_nonlinear"])
+def adam_param_check(p_new, p_ref, g_ref, lr, tol, what):
+    """Updated-parameter parity, as tests/test_pendulum_gpu.py::adam_param_check does it.  Adam's early steps move a weight by
+    ~lr * g / (|g| + eps): the SIGN of g decides the update, not its size, so wherever the gradient stands clear of its
+    noise floor the updated parameters must agree to `tol` relative even though the gradients themselves only agree to
+    GRAD_RTOL.  Elements whose |g| is within 10 % of the tensor's rms (the measured fp32 noise is <= 3 % of rms per element,
+    profiles/r02_celeba_grad_noise.txt) may take either sign and are held to Adam's 2 * lr bound instead."""
+    p_new, p_ref, g = (t.detach().double().cpu().reshape(-1) for t in (p_new, p_ref, g_ref))
+    ill = g.abs() < 0.1 * g.pow(2).mean().sqrt()
+    ok = ~ill
+    assert float(ok.float().mean()) >= 0.5, (what, "too few well-conditioned elements")
+    r = float((p_new[ok] - p_ref[ok]).norm() / (p_ref[ok].norm() + 1e-30))
+    assert r < tol, (what, r)
+    if ill.any():
+        assert float((p_new[ill] - p_ref[ill]).abs().max()) <= 2.2 * lr, what
+
+
+@pytest.mark.parametrize("name", ["celeba_linear", "celeba_nonlinear", "celeba_b16_linear"])
 def test_celeba_step_matches_oracle_and_reference_golden(golden, name):
     from cdgvae_b200.celeba.module.train import train_CDGVAE
     c = golden(name)
@@ -168,7 +185,8 @@ def test_celeba_step_matches_oracle_and_reference_golden(golden, name):
         cur = _full_state(model)
         for k, v in st64.items():
             if k in c["trainable"]:
-                assert float((cur[k].double() - v).abs().max()) <= 2 * cfg["lr"] + 1e-7, (s, k)
+                # one step from identical state; later steps carry GRAD_RTOL-sized differences of the new gradient into m, v
+                adam_param_check(cur[k], v, og[k], cfg["lr"], RTOL if s == 1 else 5 * RTOL, (s, k))
             elif v.dtype.is_floating_point:
                 assert rel(cur[k], v) < RTOL, (s, k, rel(cur[k], v))
             else:

@@ -11,7 +11,7 @@ from helpers import exact_check, summary_check
 GRAD_RTOL = 2e-2
 
 
-@pytest.mark.parametrize("name", ["celeba_linear", "celeba_nonlinear"])
+@pytest.mark.parametrize("name", ["celeba_linear", "celeba_nonlinear", "celeba_b16_linear"])
 def test_celeba_oracle_matches_reference_golden(golden, name):
     c = golden(name)
     cfg = dict(c["config"])

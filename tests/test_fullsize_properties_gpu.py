@@ -126,3 +126,67 @@ def test_tabular_mean_of_shards_large(kind):
     loss, logs, _ = orc.step_losses(leaves, spec, A, x[:m].cpu(), y[:m].cpu(), noise[:m].cpu())
     rp, _ = run(slice(0, m))
     assert abs(float(rp[0]) - float(loss.detach())) <= 1e-4 * abs(float(loss.detach()))
+
+
+def test_pendulum_semi_at_the_benchmarked_shape():
+    """bench.py's configuration itself: semi-supervised, nonlinear SCM, U = 131,072 / L = 32,768 per GPU, default GEMM
+    mode (bf16x3 with pre-split weights, CTA pairs, fused reconstruction head).  x alone is 6.4 GB / 1.6e9 elements, the
+    size at which 32-bit index slips would show.
+
+      * against the ORACLE at 1e-4 (logs and every gradient): the batch is a 2,048-row (512 labeled) oracle-sized block
+        tiled 64 times, so every batch mean equals the block's and the oracle costs one 2,048-row step;
+      * mean of shards: the full batch against the average over its two 65,536-row halves;
+      * dead decoder output rows are exactly zero at this size."""
+    U, L, T = 1 << 17, 1 << 15, 64
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free device memory")
+    xb, _, nb = orc.synth_pendulum(U // T, 64, 4, 21, 22)
+    xlb, ylb, _ = orc.synth_pendulum(L // T, 64, 4, 23, 24)
+    model, cfg = pend_model("auto")
+    # tile so that the two halves hold the same multiset of rows too
+    x = xb.cuda().repeat(T, 1, 1, 1)
+    noise = nb.cuda().repeat(T, 1)
+    xl, yl = xlb.cuda().repeat(T, 1, 1, 1), ylb.cuda().repeat(T, 1)
+    assert x.numel() > (1 << 30)
+    row, g = fwd_bwd(model, x, None, noise, x_l=xl, y_l=yl)
+    # ---- oracle on the block ----
+    spec = orc.pendulum_spec(dict(cfg, batch_size=U // T, batch_sizeL=L // T), orc.pendulum_masks(64))
+    params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ologs, ograds, _ = orc.train_step(params, orc.new_adam_state(params), spec, orc.i_b_inv(orc.pendulum_B(4)), xb, None, nb, xlb, ylb)
+    keys = ["loss", "recon", "KL", "alignment"] + [f"posterior_variance{i + 1}" for i in range(4)]
+    for j, k in enumerate(keys):
+        assert abs(float(row[j]) - ologs[k]) <= 1e-4 * abs(ologs[k]) + 1e-7, (k, float(row[j]), ologs[k])
+    named = dict(model.named_parameters())
+    for n, p in named.items():
+        if n.startswith("flows."):
+            continue
+        o, k = model._offsets[n], p.numel()
+        assert rel(g[o:o + k].cpu(), ograds[n]) < 1e-4, (n, rel(g[o:o + k].cpu(), ograds[n]))
+    for i in range(4):                                                   # a PlanarFlows module's scalars as one vector
+        ks = [k for k in named if k.startswith(f"flows.{i}.")]
+        mine = torch.cat([g[model._offsets[k]:model._offsets[k] + 1] for k in ks]).cpu()
+        assert rel(mine, torch.cat([ograds[k].reshape(-1) for k in ks])) < 1e-4, f"flows.{i}"
+    # ---- dead decoder rows ----
+    for k, (lo, hi) in enumerate(model._ranges):
+        o = model._offsets[f"decoder.{k}.4.weight"]
+        w = g[o:o + 12288 * 300].view(12288, 300)
+        assert float(w[:lo].abs().max() if lo else 0.0) == 0.0 and float(w[hi:].abs().max() if hi < 12288 else 0.0) == 0.0
+        ob = model._offsets[f"decoder.{k}.4.bias"]
+        bgrad = g[ob:ob + 12288]
+        assert float(bgrad[:lo].abs().max() if lo else 0.0) == 0.0 and float(bgrad[hi:].abs().max() if hi < 12288 else 0.0) == 0.0
+    # ---- mean of shards: 2 x 65,536 ----
+    h, hl = U // 2, L // 2
+    r0, g0 = fwd_bwd(model, x[:h], None, noise[:h], x_l=xl[:hl], y_l=yl[:hl])
+    r1, g1 = fwd_bwd(model, x[h:], None, noise[h:], x_l=xl[hl:], y_l=yl[hl:])
+    assert rel((r0 + r1) / 2, row) < 1e-4
+    assert rel((g0 + g1) / 2, g) < 1e-4
+    # ---- and one on genuinely different rows per half (device-generated): halves vs whole ----
+    del x, xl
+    xr, _, nr = synth(U, 31)
+    xlr, ylr, _ = synth(L, 32)
+    rw, gw = fwd_bwd(model, xr, None, nr, x_l=xlr, y_l=ylr)
+    r0, g0 = fwd_bwd(model, xr[:h], None, nr[:h], x_l=xlr[:hl], y_l=ylr[:hl])
+    r1, g1 = fwd_bwd(model, xr[h:], None, nr[h:], x_l=xlr[hl:], y_l=ylr[hl:])
+    assert rel((r0 + r1) / 2, rw) < 1e-4
+    assert rel((g0 + g1) / 2, gw) < 1e-4
