@@ -188,7 +188,6 @@ int launch_latent_bwd(const LatentArgs& a, cudaStream_t s) {
 //   each `inverse_loop` fixed-point iterations z <- h - u_hat ELU(z w + b) started at z = h (:80-84).
 struct FlowApplyArgs {
     int d, scm, flow_num, loops, direction;
-    float A[1];                   // (load_flow_table's interface; the causal matrix is not used here)
     int64_t batch, ld_in, ld_out, ld_logdet;
     const float* params;
     int64_t flow_off[CDG_MAX_NODE];
@@ -199,7 +198,7 @@ struct FlowApplyArgs {
 
 __global__ void __launch_bounds__(256) flow_apply_kernel(FlowApplyArgs a) {
     __shared__ FlowTable ft;
-    load_flow_table(ft, a);
+    load_flow_table<false>(ft, a);
     __syncthreads();
     const int d = a.d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.batch * d; i += (int64_t)gridDim.x * blockDim.x) {

@@ -45,10 +45,13 @@ struct FlowGrad {
 
 __device__ __forceinline__ float elu_ref(float t) { return t > 0.f ? t : expf(t) - 1.f; }
 
-template <typename Args>
+// WITH_A = false: the caller has no causal matrix (stand-alone flow evaluation); a.A is then never read.  (A.A may be an
+// array member or a pointer: no sizeof-based bound here -- one once truncated the tabular kernels' I_B_inv to 2 floats.)
+template <bool WITH_A = true, typename Args>
 __device__ __forceinline__ void load_flow_table(FlowTable& ft, const Args& a) {
     const int d = a.d;
-    for (int i = threadIdx.x; i < d * d && i < (int)(sizeof(a.A) / sizeof(float)); i += blockDim.x) ft.A[i] = a.A[i];
+    if constexpr (WITH_A)
+        for (int i = threadIdx.x; i < d * d; i += blockDim.x) ft.A[i] = a.A[i];
     for (int t = threadIdx.x; t < d * CDG_MAX_FLOW; t += blockDim.x) {
         const int i = t / CDG_MAX_FLOW, f = t % CDG_MAX_FLOW;
         const float* p = a.params + a.flow_off[i];

@@ -25,8 +25,18 @@ CASES = {
     "pendulum": ("pendulum_full_linear", 5e-4, 3e-3),
     "tabular": ("tabular_adult", 5e-4, 3e-3),
     "tvae": ("tvae_loan", 5e-4, 3e-3),
-    "celeba": ("celeba_free6", 2e-3, None),          # parameters: Adam's 2 * lr * steps bound (gradient noise floor 1e-3..5e-3)
+    # CelebA: the reference's own trajectory moves by up to 1e-1 in the logs over six steps when only its BLAS thread count
+    # changes (tools/celeba_free_noise.py -> profiles/r02_celeba_free_running_noise.json: L1 loss through train-mode BatchNorm
+    # at batch 2, Adam's sign-like first updates).  Per-step bound = 3 x that recorded drift (never below 2e-3); parameters:
+    # Adam's 2 * lr * steps bound.
+    "celeba": ("celeba_free6", None, None),
 }
+
+
+def _celeba_log_bounds():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_celeba_free_running_noise.json")))
+    per = [max(v["log_rel_dev_per_step"][s] for v in d.values()) for s in range(6)]
+    return [max(2e-3, 3.0 * p) for p in per]
 
 
 def _record(family, entry):
@@ -97,12 +107,13 @@ def test_six_free_running_steps_against_the_reference(golden, family):
             return run(b)
 
     worst_log, per_step = 0.0, []
+    log_bounds = _celeba_log_bounds() if family == "celeba" else [log_tol] * 6
     for s, e in enumerate(c["steps"]):
         logs = step(s)
         dev = max(abs(logs[k][0] - v) / (abs(v) + 1e-12) for k, v in e["logs"].items() if abs(v) > 1e-6)
         per_step.append(dev)
         worst_log = max(worst_log, dev)
-    entry = {"golden": name, "steps": 6, "log_rel_dev_per_step": per_step, "log_rel_dev_max": worst_log, "log_bound": log_tol}
+    entry = {"golden": name, "steps": 6, "log_rel_dev_per_step": per_step, "log_rel_dev_max": worst_log, "log_bound_per_step": log_bounds}
     sd = dict(model.named_parameters())
     if family == "celeba":
         moved = max(float((sd[n].detach() - before[n]).abs().max()) for n in before)
@@ -122,4 +133,4 @@ def test_six_free_running_steps_against_the_reference(golden, family):
         _record(family, entry)
         for n, (ds, dl) in devs.items():
             assert ds <= par_tol and dl <= par_tol, (family, n, ds, dl)
-    assert worst_log <= log_tol, (family, per_step)
+    assert all(d <= b for d, b in zip(per_step, log_bounds)), (family, per_step, log_bounds)
