@@ -126,13 +126,13 @@ class TvaeTransformConfig(C.Structure):
 
 
 # every symbol include/cdgvae.h declares
-EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_abi_sizeof", "cdg_flow_apply", "cdg_pendulum_profile_enable",
+EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_launch_count_add", "cdg_abi_sizeof", "cdg_flow_apply", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
-           "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit", "cdg_tvae_transform", "cdg_tvae_inverse_transform",
+           "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit", "cdg_gemm_planes", "cdg_tvae_transform", "cdg_tvae_inverse_transform",
            "cdg_gumbel_argmax", "cdg_pixels_to_float"]
 
 _lib = None
@@ -160,10 +160,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.stale():
+    exp = os.environ.get("CDG_EXPERIMENTS_LIB") == "1"     # development only: the build with the experiment switches live
+    path = _build.LIB_EXP if exp else _build.LIB
+    if _build.stale(exp):
         try:
-            _build.build()
+            _build.build(experiments=exp)
         except _build.NoCompiler as e:  # no nvcc on the box: a prebuilt library must be present (its layout is checked below)
             if not os.path.exists(path):
                 raise RuntimeError(f"libcdgvae_sm100.so is missing and cannot be built: {e}") from e
@@ -175,6 +176,8 @@ def lib():
     _check_abi(L, path)
     L.cdg_last_error.restype = C.c_char_p
     L.cdg_launch_count.restype = C.c_longlong
+    L.cdg_launch_count_add.argtypes = [C.c_longlong]
+    L.cdg_launch_count_add.restype = None
     L.cdg_pendulum_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.cdg_pendulum_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cdg_pendulum_workspace_bytes.restype = C.c_int64
@@ -209,6 +212,9 @@ def lib():
     L.cdg_conv2d_dgrad.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Conv),
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.cdg_split_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.cdg_gemm_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_void_p]
     L.cdg_gemm_bsplit.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.cdg_tvae_transform.argtypes = [C.POINTER(TvaeTransformConfig), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

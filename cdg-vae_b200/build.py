@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdgvae_sm100.so")
+LIB_EXP = os.path.join(HERE, "libcdgvae_sm100_exp.so")      # -DCDG_EXPERIMENTS: A/B switches read from the environment (development)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include")]
 
@@ -28,15 +29,16 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def stale():
-    if not os.path.exists(LIB):
+def stale(experiments=False):
+    lib = LIB_EXP if experiments else LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "cdgvae.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, experiments=False):
     """Compile every csrc/*.cu for sm_100a and link libcdgvae_sm100.so next to this file.
 
     Safe under torchrun: ranks that find the library stale at the same time serialise on a file lock, the first one
@@ -44,20 +46,23 @@ def build(force=False, verbose=False):
     the others re-check and find it fresh.  (Eight ranks once rebuilt it concurrently and one of them loaded a
     half-linked file: `undefined symbol`.)"""
     import fcntl
-    if not force and not stale():
-        return LIB
+    lib = LIB_EXP if experiments else LIB
+    if not force and not stale(experiments):
+        return lib
     with open(os.path.join(HERE, ".build.lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
-            if not force and not stale():
-                return LIB
-            return _build_locked(verbose)
+            if not force and not stale(experiments):
+                return lib
+            return _build_locked(verbose, experiments)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
-def _build_locked(verbose):
+def _build_locked(verbose, experiments=False):
     nvcc = _nvcc()
+    LIB = LIB_EXP if experiments else globals()["LIB"]
+    flags = NVCC_FLAGS + (["-DCDG_EXPERIMENTS"] if experiments else [])
     objdir = os.path.join(HERE, "build", f"obj.{os.getpid()}")
     os.makedirs(objdir, exist_ok=True)
     objs = []
@@ -65,7 +70,7 @@ def _build_locked(verbose):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + flags + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -171,6 +171,9 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG
 // tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the
 // dispatcher can route it to the SIMT kernel.
 int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+// CTA-pair bf16x3 kernel for operands that BOTH arrive as bf16 (hi, lo) planes (gemm_ps.cu): needs a_hi16 / a_lo16 and
+// b_hi16 / b_lo16 (no operand swap); out_hi / out_lo (optional) receive the planes of the result for the next GEMM.
+int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cudaStream_t s);
 bool gemm_tc_can(const GemmDesc& g);   // would gemm_tc accept this contraction (without split-K)?
 int gemm_dispatch(int mode, const GemmDesc& g, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 

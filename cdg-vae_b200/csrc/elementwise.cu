@@ -323,6 +323,7 @@ extern "C" int64_t cdg_abi_sizeof(int which) {
     return which >= 0 && which < (int)(sizeof(sz) / sizeof(sz[0])) ? sz[which] : -1;
 }
 extern "C" long long cdg_launch_count(void) { return cdg::g_launches; }
+extern "C" void cdg_launch_count_add(long long n) { cdg::g_launches += n; }
 extern "C" int cdg_device_ok(void) {
     int dev = 0;
     cudaDeviceProp prop;

@@ -29,10 +29,11 @@ static inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }
 static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
 // batches from which the step pre-splits its weights (below, the extra ~0.1 ms per step is not repaid)
 constexpr int64_t kSplitMinBatch = 2048;
+constexpr int64_t kLd16 = 304;          // row stride (bf16 elements) of an activation's planes: pad16(hidden = 300)
 
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
-        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, total;
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, a16, total;
     int64_t asplit_half;           // elements of one (hi or lo) transposed activation copy
     // InfoMax discriminator (allocated only when requested)
     int64_t dx, dh1j, dh1m, dh2j, dh2m, dj, dm, dgj, dgm, dg2, dg1j, dg1m, deps_perm, dtj, dtm, dgeps;
@@ -66,6 +67,8 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, i
     // wgrad: the narrow [batch, <= 304] operand, split + transposed per call (hi then lo)
     w.asplit_half = pad64(304 * pad8(B > BL ? B : BL));
     w.asplit = take(B >= kSplitMinBatch && split_elems > 0 ? w.asplit_half : 0);
+    // bf16 (hi, lo) planes [B][304] of an activation feeding the pre-split kernel (gemm_ps.cu) as its A operand
+    w.a16 = take(B >= kSplitMinBatch && split_elems > 0 ? B * kLd16 : 0);
     const int64_t Bi = infomax ? B : 0;
     w.dx = take(Bi * H); w.dh1j = take(Bi * H); w.dh1m = take(Bi * H); w.dh2j = take(Bi * H); w.dh2m = take(Bi * H);
     w.dj = take(Bi); w.dm = take(Bi); w.dgj = take(Bi); w.dgm = take(Bi);
@@ -128,6 +131,10 @@ static int gemm_weights(const Ctx& c, GemmDesc& g, bool have_split) {
     return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
 }
 
+static bool use_ps() {
+    static const int v = exp_switch("CDG_PS", 1);
+    return v != 0;
+}
 // once per call: bf16 (hi, lo) copies of every big weight, in both orientations
 static int split_weights(Ctx& c, int64_t B) {
     c.split = false;
@@ -283,7 +290,17 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
             GemmDesc g = dec_out_desc(c, k, B, pre, x, xhat, acc);
             const bool sp = use_split_fwd(c, cf.dec[k][2], cf.col_lo[k], g);
             if (x) {
-                int r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
+                int r = CDG_ERR_UNSUPPORTED;
+                if (sp && c.w.a16 > 0 && H <= kLd16 && use_ps()) {
+                    // both operands as bf16 planes: TMA feeds the MMA directly, eight epilogue warps (gemm_ps.cu)
+                    uint16_t* ah = reinterpret_cast<uint16_t*>(c.W + c.w.a16);
+                    uint16_t* al = ah + B * kLd16;
+                    CDG_TRY(launch_split_bf16(a2, B, H, H, ah, al, kLd16, 0, c.s));
+                    g.a_hi16 = ah; g.a_lo16 = al; g.ld_a16 = kLd16;
+                    r = gemm_ps(g, nullptr, nullptr, 0, c.s);
+                    g.a_hi16 = g.a_lo16 = nullptr;
+                }
+                if (r == CDG_ERR_UNSUPPORTED) r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
                 if (r == CDG_ERR_UNSUPPORTED) {
                     g.b_hi16 = g.b_lo16 = nullptr;
                     r = gemm_tc(g, c.mode == CDG_GEMM_TC1X ? 1 : (c.mode == CDG_GEMM_BF3X ? 2 : 3), nullptr, 0, c.s);
@@ -788,4 +805,18 @@ extern "C" int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const
     g.b_hi16 = b_hi; g.b_lo16 = b_lo; g.ld_b16 = ld16;
     g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
     return gemm_tc(g, 2, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a16, const void* b_hi, const void* b_lo, int64_t ld_b16,
+                               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epi, const float* bias, const float* aux,
+                               int64_t ld_aux, void* out_hi, void* out_lo, int64_t ld_out16, void* stream) {
+    CDG_REQUIRE(a_hi && a_lo && b_hi && b_lo && (C || out_hi), "cdg_gemm_planes: null pointer");
+    CDG_REQUIRE(epi >= 0 && epi <= 3, "cdg_gemm_planes: epi=%d out of range", epi);
+    GemmDesc g;
+    g.A = nullptr; g.sa_m = ld_a16; g.sa_k = 1; g.B = nullptr; g.sb_n = ld_b16; g.sb_k = 1;
+    g.a_hi16 = a_hi; g.a_lo16 = a_lo; g.ld_a16 = ld_a16; g.b_hi16 = b_hi; g.b_lo16 = b_lo; g.ld_b16 = ld_b16;
+    g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+    g.epi = epi == 1 ? EPI_BIAS : epi == 2 ? EPI_BIAS_ACT : epi == 3 ? EPI_MUL_DACT : EPI_NONE;
+    g.act = CDG_ACT_ELU; g.bias = bias; g.aux = aux; g.ld_aux = ld_aux;
+    return gemm_ps(g, out_hi, out_lo, ld_out16, (cudaStream_t)stream);
 }

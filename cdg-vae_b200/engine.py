@@ -259,24 +259,28 @@ class ArenaModule(nn.Module):
             torch.cuda.synchronize(self.arena_device)
             graph = torch.cuda.CUDAGraph()
             count0, tensors0 = self._step_count, [float(t) for t in self._step_tensors[:1]]
+            n0 = _lib.lib().cdg_launch_count()
             try:
                 with torch.cuda.graph(graph):
                     outs = body(static)
             finally:
                 self._use_dev_step = False
+            nodes = int(_lib.lib().cdg_launch_count() - n0)    # kernels of this library inside the graph
+            _lib.lib().cdg_launch_count_add(-nodes)            # capturing does not execute them
             # capturing does not execute: undo the host-side step bookkeeping the body did
             undo = self._step_count - count0
             self._step_count = count0
             if undo:
                 torch._foreach_add_(self._step_tensors, -float(undo))
-            ent = cache[key] = (graph, static, outs)
-        graph, static, outs = ent
+            ent = cache[key] = (graph, static, outs, nodes)
+        graph, static, outs, nodes = ent
         for k, v in inputs.items():
             if v is not None:
                 static[k].copy_(v, non_blocking=True)
         if int(self._dev_step_mirror) != self._step_count:
             self._dev_step.fill_(self._step_count)
         graph.replay()
+        _lib.lib().cdg_launch_count_add(nodes)
         self._step_count += 1
         self._dev_step_mirror = self._step_count
         torch._foreach_add_(self._step_tensors, 1.0)

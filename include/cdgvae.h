@@ -43,6 +43,9 @@ int cdg_version(void);
 int cdg_device_ok(void);
 /* Number of kernels this library has launched so far in this process (host-side counter). */
 long long cdg_launch_count(void);
+/* A caller that replays a captured CUDA graph of this library's launches adds the graph's kernel count here (launches made
+ * by a replay never pass through the library's host code). */
+void cdg_launch_count_add(long long n);
 /* sizeof() of the i-th struct of this header as the library was compiled (order: cdg_linear, cdg_adam_args,
  * cdg_pendulum_config, cdg_pendulum_io, cdg_pendulum_fwd_io, cdg_tabular_config, cdg_tabular_io, cdg_conv, cdg_bnorm,
  * cdg_celeba_config, cdg_celeba_io, cdg_tvae_transform_config); -1 past the end.  A binding compares these with its own
@@ -334,6 +337,14 @@ int cdg_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void*
                    void* stream);
 int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const void* b_hi, const void* b_lo, int64_t ld16, float* C,
                     int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream);
+/* The same product with BOTH operands as bf16 (hi, lo) planes (A: [M][ld_a16], B: [N][ld_b16], made by cdg_split_bf16 or by
+ * a previous call's out_hi / out_lo): the CTA-pair kernel of csrc/gemm_ps.cu, TMA-fed with no in-kernel conversion.
+ * epi: 0 = none, 1 = + bias[n], 2 = ELU(+ bias[n]), 3 = * ELU'(aux[m,n]) (aux = post-activation values, row stride ld_aux).
+ * C (row stride ldc, 32-byte aligned rows) and / or out_hi / out_lo ([M][ld_out16] bf16 planes of the fp32 result) are written.
+ * Returns CDG_ERR_UNSUPPORTED for shapes the kernel does not take (M < 1024, N % 16 != 0, K > 2048, misaligned operands). */
+int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a16, const void* b_hi, const void* b_lo, int64_t ld_b16,
+                    float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epi, const float* bias, const float* aux,
+                    int64_t ld_aux, void* out_hi, void* out_lo, int64_t ld_out16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * CDG-TVAE data transform, APPLY side: the step on either side of train_TVAE.

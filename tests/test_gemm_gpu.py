@@ -53,3 +53,73 @@ def test_gemm_layouts(mode, layout, shape):
         out2 = run(mode, A, sa, B, sb, M, N, K, accumulate=True, C0=C0)
         err2 = float((out2.double() - (ref + C0.double())).norm() / (ref + C0.double()).norm())
         assert err2 < tol
+
+
+# ---- both operands as bf16 (hi, lo) planes: the CTA-pair kernel of csrc/gemm_ps.cu through cdg_gemm_planes ----------------
+def _planes(W, ld16):
+    from cdgvae_b200 import _lib
+    rows, cols = W.shape
+    hi = torch.zeros(rows, ld16, dtype=torch.bfloat16, device="cuda")
+    lo = torch.zeros_like(hi)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().cdg_split_bf16(C.c_void_p(W.data_ptr()), rows, cols, cols, C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()),
+                                         ld16, 0, C.c_void_p(s)))
+    return hi, lo
+
+
+PLANE_SHAPES = [(4096, 256, 300), (4096, 304, 300), (2048 + 128, 3840, 300), (4096 + 77, 5952, 300), (1024, 2496, 300),
+                (4096, 64, 512), (2048, 128, 96), (4096, 304, 1024), (1024, 16, 64)]
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", PLANE_SHAPES)
+def test_gemm_planes(shape, epi):
+    """a = hi + lo carries 16 mantissa bits per operand: 5e-5 against the float64 product of the ORIGINAL fp32 operands (the
+    bound the bf16x3 mode has everywhere), 6e-6 against the float64 product of the planes themselves (what the tensor core
+    was asked to compute, fp32 accumulation over K <= 2048)."""
+    from cdgvae_b200 import _lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + epi)
+    A = torch.randn(M, K, generator=g).cuda(); B = (torch.randn(N, K, generator=g) * 0.1).cuda()
+    bias = torch.randn(N, generator=g).cuda(); aux = torch.randn(M, N, generator=g).cuda()
+    lda = (K + 15) // 16 * 16
+    ah, al = _planes(A, lda); bh, bl = _planes(B, lda)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ld_out = (N + 15) // 16 * 16
+    oh = torch.zeros(M, ld_out, dtype=torch.bfloat16, device="cuda"); ol = torch.zeros_like(oh)
+    s = torch.cuda.current_stream().cuda_stream
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib().cdg_gemm_planes(p(ah), p(al), lda, p(bh), p(bl), lda, p(out), N, M, N, K, epi, p(bias), p(aux), N,
+                                    p(oh), p(ol), ld_out, C.c_void_p(s))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+
+    def post(acc):
+        if epi in (1, 2):
+            acc = acc + bias.double()
+        if epi == 2:
+            acc = torch.where(acc > 0, acc, torch.exp(acc) - 1)
+        if epi == 3:
+            acc = acc * torch.where(aux > 0, torch.ones_like(aux), aux + 1).double()
+        return acc
+    ref = post(A.double() @ B.double().t())
+    Ap = ah[:, :K].double() + al[:, :K].double(); Bp = bh[:, :K].double() + bl[:, :K].double()
+    ref_planes = post(Ap @ Bp.t())
+    err = float((out.double() - ref).norm() / ref.norm())
+    errp = float((out.double() - ref_planes).norm() / ref_planes.norm())
+    assert err < 5e-5 and errp < 6e-6, (shape, epi, err, errp)
+    # the emitted planes reproduce the fp32 result to 16 mantissa bits
+    back = oh[:, :N].double() + ol[:, :N].double()
+    assert float((back - out.double()).norm() / out.double().norm()) < 2e-5
+    assert torch.equal(oh[:, :N], out.to(torch.bfloat16))                  # hi = round-to-nearest bf16 of the fp32 value
+
+
+def test_gemm_planes_rejects_what_it_cannot_take():
+    from cdgvae_b200 import _lib
+    A = torch.randn(512, 64).cuda(); B = torch.randn(32, 64).cuda()
+    ah, al = _planes(A, 64); bh, bl = _planes(B, 64)
+    out = torch.zeros(512, 32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib().cdg_gemm_planes(p(ah), p(al), 64, p(bh), p(bl), 64, p(out), 32, 512, 32, 64, 0, None, None, 0, None, None, 0,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 4                                                          # CDG_ERR_UNSUPPORTED: M < 1024
