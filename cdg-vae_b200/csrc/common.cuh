@@ -166,6 +166,10 @@ struct GemmDesc {
 int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
                       cudaStream_t s, int ones_row = 0);   // ones_row (transposed only): append output row `cols` = 1.0
 
+// row-major planes [rows][ld16] with 16-byte accesses; column `cols` (if ld16 > cols) = extra[r], or 1 when `ones`, else 0
+int launch_split_rows(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, const float* extra,
+                      int ones, cudaStream_t s);
+
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
 int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG_ERR_UNSUPPORTED otherwise
 // tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the

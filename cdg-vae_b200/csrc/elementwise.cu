@@ -198,6 +198,57 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
         }
     }
 }
+// Row-major split with 16-byte accesses: thread = (row, group of 8 columns) -> one uint4 of hi and one of lo.  Column `cols`
+// (when ld16 > cols) receives extra[r] (a Linear's bias beside its weight row) or the constant 1 (an activation row that
+// multiplies that bias column): the bias then comes out of the GEMM itself.  Columns past that are zero.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ W, int64_t rows, int cols, int64_t ld,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld16,
+                                                         const float* __restrict__ extra, int ones) {
+    const int groups = (int)(ld16 / 8);
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / groups;
+        const int c0 = (int)(i - r * groups) * 8;
+        float v[8];
+        const float* src = W + r * ld + c0;
+        if (vec && c0 + 8 <= cols) {
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k;
+                v[k] = c < cols ? src[k] : (c == cols ? (extra ? extra[r] : (ones ? 1.f : 0.f)) : 0.f);
+            }
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(hi + r * ld16 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + r * ld16 + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+int launch_split_rows(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, const float* extra,
+                      int ones, cudaStream_t s) {
+    if (rows == 0) return CDG_OK;
+    if (ld16 % 8 != 0 || ld16 < cols || ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) != 0 ||
+        cols > (1 << 30)) {
+        set_error("launch_split_rows: planes must be 16-byte aligned with a row stride that is a multiple of 8");
+        return CDG_ERR_INVALID;
+    }
+    const int64_t work = (rows * (ld16 / 8) + 255) / 256;
+    split_rows_kernel<<<(int)imin64(work, kNumSMs * 16), 256, 0, s>>>(W, rows, (int)cols, ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                    ld16, extra, ones);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
 int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
                       cudaStream_t s, int ones_row) {
     if (rows * cols == 0) return CDG_OK;

@@ -285,6 +285,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             uint32_t j = 0, ccount = 0;
             float rloss = 0.f;
             double dloss = 0.0;
+            const bool has_bias = p.bias != nullptr;
             uint8_t* xo = ebuf + (size_t)EPI_NIN * EPI_CHUNK_BYTES;
             for (int64_t w = w_first; w < p.work_total; w += w_step, ++j) {
                 int m_pair, n_blk;
@@ -293,12 +294,15 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int row0 = (2 * m_pair + (int)rank) * BM + q * 32;
                 const bool row_ok = (int64_t)row0 + lane < p.M;
                 float* bs = bias_s + (j & 1u) * BN;
-                for (int c = et; c < BN; c += 32 * NE) {
-                    const int64_t n = (int64_t)n_blk * BN + c;
-                    bs[c] = (n < p.N ? p.bias[n] : 0.f) * K2LOG2E;
+                if (has_bias) {
+                    for (int c = et; c < BN; c += 32 * NE) {
+                        const int64_t n = (int64_t)n_blk * BN + c;
+                        bs[c] = (n < p.N ? p.bias[n] : 0.f) * K2LOG2E;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
                 const uint32_t bsh = smem_u32(bs + half * HC);
+                float* xh_row = (p.rxhat && row_ok) ? p.rxhat + ((int64_t)row0 + lane) * p.ldc : nullptr;
                 mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + buf * BN + (uint32_t)(half * HC) + ((uint32_t)(q * 32) << 16);
@@ -339,11 +343,12 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     __syncwarp();
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        float4 bb;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
-                                     : "r"(bsh + (uint32_t)(c * 32 + 4 * g) * 4u));
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_bias)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                                         : "r"(bsh + (uint32_t)(c * 32 + 4 * g) * 4u));
                         const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
-                        float o[4], t4[4];
+                        float o[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int i = 4 * g + e;
@@ -353,12 +358,23 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             const float df = t - xs[i];
                             rloss = fmaf(df, df, rloss);
                             o[e] = (df * p.inv_batch) * fmaf(-t, t, 1.f);
-                            t4[e] = t;
                         }
                         *reinterpret_cast<float4*>(xo + sw_chunk<32>((uint32_t)lane, (uint32_t)g)) = make_float4(o[0], o[1], o[2], o[3]);
-                        if (p.rxhat && row_ok)                       // only the step whose xhat is returned: row-per-thread stores
-                            *reinterpret_cast<float4*>(p.rxhat + ((int64_t)row0 + lane) * p.ldc + col0 + 4 * g) =
-                                make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                    if (xh_row) {
+                        // only the step whose xhat is returned (the last of a train_* call): tanh recomputed from the accumulator
+                        // registers, row-per-thread stores -- kept out of the loop above so that it costs the other steps nothing
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            float t4[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float b = has_bias ? bs[half * HC + c * 32 + 4 * g + e] : 0.f;
+                                const float ex = ex2_approx(fmaf(__uint_as_float(vraw[4 * g + e]), K2LOG2E, b));
+                                t4[e] = fmaf(-2.f, rcp_approx(1.f + ex), 1.f);
+                            }
+                            *reinterpret_cast<float4*>(xh_row + col0 + 4 * g) = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                        }
                     }
                     fence_async_smem();
                     __syncwarp();
@@ -367,9 +383,9 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                                          reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(xo)), "r"(col0), "r"(row0) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    if (!row_ok) rloss = 0.f;                        // rows past M: zero-filled operands, not part of the loss
-                    else { dloss += (double)rloss; rloss = 0.f; }
                 }
+                if (row_ok) dloss += (double)rloss;                  // (rows past M: zero-filled operands, not part of the loss)
+                rloss = 0.f;
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (p.racc) {
@@ -390,7 +406,8 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const bool row_ok = m < p.M;
             const int64_t n_base = (int64_t)n_blk * BN + half * HC;
             float* bs = bias_s + (j & 1u) * BN;
-            if (EPI == EPI_RECON || EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) {
+            const bool has_bias = p.bias != nullptr;
+            if ((EPI == EPI_RECON || EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) && has_bias) {
                 for (int c = et; c < BN; c += 32 * NE) {
                     const int64_t n = (int64_t)n_blk * BN + c;
                     const float b = n < p.N ? p.bias[n] : 0.f;
@@ -443,8 +460,8 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     // results leave in halves of 8 columns (one 256-bit store each): keeps the live temporaries small
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        float o[8], bb[8];
-                        if (EPI == EPI_RECON || EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) {
+                        float o[8], bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if ((EPI == EPI_RECON || EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) && has_bias) {
 #pragma unroll
                             for (int g = 0; g < 2; ++g)
                                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb[4 * g]), "=f"(bb[4 * g + 1]),
@@ -616,7 +633,7 @@ int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cud
     if (g.C && !(g.ldc % 8 == 0 && al32p(g.C))) return CDG_ERR_UNSUPPORTED;
     if (!g.C && !out_hi) return CDG_ERR_UNSUPPORTED;
     if (out_hi && !(out_lo && ld_out16 % 16 == 0 && al32p(out_hi) && al32p(out_lo))) return CDG_ERR_UNSUPPORTED;
-    if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_ACT || g.epi == EPI_RECON) && !g.bias) return CDG_ERR_UNSUPPORTED;
+    // (a null bias with a bias epilogue = the bias is folded into the contraction: a ones column in A, the bias column in B)
     if (g.epi == EPI_MUL_DACT && !(g.aux && g.ld_aux % 8 == 0 && al32p(g.aux))) return CDG_ERR_UNSUPPORTED;
     if (g.epi == EPI_RECON) {
         if (!g.recon_x || !g.C) { set_error("EPI_RECON without target / gradient buffer"); return CDG_ERR_INVALID; }

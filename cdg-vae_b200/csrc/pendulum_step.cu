@@ -143,7 +143,10 @@ static int split_weights(Ctx& c, int64_t B) {
     uint16_t* pool = reinterpret_cast<uint16_t*>(c.W + c.w.wsplit);
     auto one = [&](const cdg_linear& L, int id) -> int {
         if (c.p->f_hi[id] < 0) return CDG_OK;
-        CDG_TRY(launch_split_bf16(c.P + L.w, L.out, L.in, L.in, pool + c.p->f_hi[id], pool + c.p->f_lo[id], pad8(L.in), 0, c.s));
+        // forward orientation [out][pad8(in)]: where the padding leaves room, column `in` carries the bias (a GEMM whose A planes
+        // hold a 1 there, K = in + 1, then delivers X W^T + b with no bias pass in its epilogue)
+        CDG_TRY(launch_split_rows(c.P + L.w, L.out, L.in, L.in, pool + c.p->f_hi[id], pool + c.p->f_lo[id], pad8(L.in),
+                                  pad8(L.in) > L.in ? c.P + L.b : nullptr, 0, c.s));
         CDG_TRY(launch_split_bf16(c.P + L.w, L.out, L.in, L.in, pool + c.p->t_hi[id], pool + c.p->t_lo[id], pad8(L.out), 1, c.s));
         return CDG_OK;
     };
@@ -295,10 +298,12 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
                     // both operands as bf16 planes: TMA feeds the MMA directly, eight epilogue warps (gemm_ps.cu)
                     uint16_t* ah = reinterpret_cast<uint16_t*>(c.W + c.w.a16);
                     uint16_t* al = ah + B * kLd16;
-                    CDG_TRY(launch_split_bf16(a2, B, H, H, ah, al, kLd16, 0, c.s));
+                    CDG_TRY(launch_split_rows(a2, B, H, H, ah, al, kLd16, nullptr, 1, c.s));      // column H = 1: the bias column
                     g.a_hi16 = ah; g.a_lo16 = al; g.ld_a16 = kLd16;
+                    const float* bias = g.bias;
+                    g.K = H + 1; g.bias = nullptr;                    // W2's planes carry b2 in column H (split_weights)
                     r = gemm_ps(g, nullptr, nullptr, 0, c.s);
-                    g.a_hi16 = g.a_lo16 = nullptr;
+                    g.a_hi16 = g.a_lo16 = nullptr; g.K = H; g.bias = bias;
                 }
                 if (r == CDG_ERR_UNSUPPORTED) r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
                 if (r == CDG_ERR_UNSUPPORTED) {
