@@ -160,7 +160,16 @@ struct GemmDesc {
     // A weight-gradient GEMM whose pre-split B carries a row of ones there yields the bias gradient (the column sum of dY)
     // for free, instead of a separate pass over dY.
     float* extra_col = nullptr;
+    // bf16 (hi, lo) planes of the fp32 result for a following GEMM of the pre-split kernel (gemm_ps.cu): [M][ld_out16],
+    // columns >= N zero except column N = 1 when out_ones (the consumer's weight planes then carry its bias in that column).
+    // Kernels that can, write them from their epilogue; for the others the dispatcher adds a split pass over C (finish_planes).
+    void* out_hi16 = nullptr;
+    void* out_lo16 = nullptr;
+    int64_t ld_out16 = 0;
+    int out_ones = 0;
 };
+extern thread_local bool tl_planes_done;     // set by a kernel launch that wrote g.out_hi16 / out_lo16 itself
+int finish_planes(const GemmDesc& g, cudaStream_t s);   // split pass over C when the routed kernel did not emit the planes
 
 // W[rows, cols] (row stride ld) -> hi / lo bf16 copies; transpose != 0 writes them as [cols][rows] (row stride ld16 either way)
 int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, int transpose,
@@ -177,12 +186,13 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG
 int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 // CTA-pair bf16x3 kernel for operands that BOTH arrive as bf16 (hi, lo) planes (gemm_ps.cu): needs a_hi16 / a_lo16 and
 // b_hi16 / b_lo16 (no operand swap); out_hi / out_lo (optional) receive the planes of the result for the next GEMM.
-int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cudaStream_t s);
+int gemm_ps(const GemmDesc& g, cudaStream_t s);
 bool gemm_tc_can(const GemmDesc& g);   // would gemm_tc accept this contraction (without split-K)?
 int gemm_dispatch(int mode, const GemmDesc& g, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 
 int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,
-                    const float* aux, int64_t ld_aux, cudaStream_t s);
+                    const float* aux, int64_t ld_aux, cudaStream_t s, void* out_hi = nullptr, void* out_lo = nullptr,
+                    int64_t ld_out16 = 0, int out_ones = 0);
 int launch_colsum(const float* G, int64_t ld, int64_t M, int64_t N, float* out, cudaStream_t s);
 
 }  // namespace cdg

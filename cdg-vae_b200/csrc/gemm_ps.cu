@@ -67,6 +67,8 @@ struct Params {
     const float* aux; int64_t ld_aux;            // EPI_MUL_DACT: post-activation values
     const float* rx; int64_t rx_ld; float* rxhat; double* racc; float inv_batch;   // EPI_RECON
     __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int64_t ld16;                    // optional bf16 planes of the result
+    int ones_col;                                // planes: column N = 1 (the consumer's bias column), later columns 0
+    int c8, side8;                               // C / xhat rows (side operand rows) are 32-byte aligned: 256-bit accesses
     int kb_total, tiles_n;
     int64_t work_total;
 };
@@ -421,13 +423,24 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (EPI == EPI_RECON) side = p.rx + m * p.rx_ld + n_base;
             if (EPI == EPI_MUL_DACT) side = p.aux + m * p.ld_aux + n_base;
             constexpr bool SIDE = EPI == EPI_RECON || EPI == EPI_MUL_DACT;
-            constexpr int U = NCH < 4 ? NCH : 4;       // chunks per unrolled group: sd[] / vraw[] indices are static inside it
-            static_assert(NCH % U == 0, "whole groups of chunks");
+            constexpr int U = NCH % 4 == 0 ? 4 : NCH;  // chunks per unrolled group: sd[] / vraw[] indices are static inside it
+            static_assert(NCH % U == 0 && (U >= 3 || U == NCH), "whole groups of chunks, side buffers reused two chunks later");
             float sd[U][16];
-            auto fetch = [&](int c, float* dst) {     // side operand of chunk c (two chunks ahead of its use)
-                if (c < NCH && row_ok && n_base + 16 * c + 16 <= p.N) {
+            // side operand of chunk c (two chunks ahead of its use): 32-byte pieces when the rows allow it, else 16-byte ones;
+            // groups of 4 columns past N are not touched (N is a multiple of 4)
+            auto fetch = [&](int c, float* dst) {
+                if (c >= NCH || !row_ok) return;
+                const int64_t n0 = n_base + 16 * c;
+                if (p.side8 && n0 + 16 <= p.N) {
                     ld_nc_v8f(side + 16 * c, dst);
                     ld_nc_v8f(side + 16 * c + 8, dst + 8);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (n0 + 4 * g + 4 <= p.N) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(side + 16 * c + 4 * g));
+                            dst[4 * g] = t.x; dst[4 * g + 1] = t.y; dst[4 * g + 2] = t.z; dst[4 * g + 3] = t.w;
+                        }
                 }
             };
             if (SIDE) { fetch(0, sd[0]); if (U > 1) fetch(1, sd[1 % U]); }
@@ -456,10 +469,11 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         }
                     }
                     const int64_t n0 = n_base + 16 * c;
-                    const bool live = row_ok && n0 + 16 <= p.N;
                     // results leave in halves of 8 columns (one 256-bit store each): keeps the live temporaries small
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        const int64_t n8 = n0 + 8 * h;                    // first of these 8 columns
+                        const bool v0 = row_ok && n8 + 4 <= p.N, v1 = row_ok && n8 + 8 <= p.N;   // its two groups of 4
                         float o[8], bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         if ((EPI == EPI_RECON || EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) && has_bias) {
 #pragma unroll
@@ -475,10 +489,17 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                                 const float r = rcp_approx(1.f + e);
                                 t[i] = fmaf(-2.f, r, 1.f);
                                 const float df = t[i] - sd[u][8 * h + i];
-                                if (live) rloss = fmaf(df, df, rloss);
+                                if (i < 4 ? v0 : v1) rloss = fmaf(df, df, rloss);
                                 o[i] = (df * p.inv_batch) * fmaf(-t[i], t[i], 1.f);
                             }
-                            if (live && p.rxhat) st_v8f(p.rxhat + m * p.ldc + n0 + 8 * h, t);
+                            if (p.rxhat) {
+                                float* xh = p.rxhat + m * p.ldc + n8;
+                                if (v1 && p.c8) st_v8f(xh, t);
+                                else {
+                                    if (v0) *reinterpret_cast<float4*>(xh) = make_float4(t[0], t[1], t[2], t[3]);
+                                    if (v1) *reinterpret_cast<float4*>(xh + 4) = make_float4(t[4], t[5], t[6], t[7]);
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -489,8 +510,24 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                                 o[i] = x;
                             }
                         }
-                        if (live && p.C) st_v8f(p.C + m * p.ldc + n0 + 8 * h, o);
-                        if (live && p.out_hi) store_planes8(p.out_hi + m * p.ld16 + n0 + 8 * h, p.out_lo + m * p.ld16 + n0 + 8 * h, o);
+                        if (p.C) {
+                            float* crow = p.C + m * p.ldc + n8;
+                            if (v1 && p.c8) st_v8f(crow, o);
+                            else {
+                                if (v0) *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+                                if (v1) *reinterpret_cast<float4*>(crow + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                            }
+                        }
+                        if (p.out_hi && row_ok && n8 < p.ld16) {
+                            // planes of the result for the next GEMM: columns past N are 0, except column N itself when the
+                            // consumer wants its bias column multiplied by 1 there
+                            if (!v1) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (n8 + i >= p.N) o[i] = (p.ones_col && n8 + i == p.N) ? 1.f : 0.f;
+                            }
+                            store_planes8(p.out_hi + m * p.ld16 + n8, p.out_lo + m * p.ld16 + n8, o);
+                        }
                     }
                     if (SIDE) fetch(c + 2, sd[(u + 2) % U]);     // its buffer was consumed two chunks ago (this one when U = 2)
                 }
@@ -623,30 +660,38 @@ static bool al32p(const void* q) { return ((uintptr_t)q & 31) == 0; }
 // C = A B^T with A(m,k) = a_hi16 + a_lo16 ([M][ld_a16] bf16 planes) and B(n,k) = b_hi16 + b_lo16 ([N][ld_b16]); out_hi / out_lo
 // (optional, [M][ld_out16]) receive the bf16 planes of the fp32 result.  CDG_ERR_UNSUPPORTED when the shape / alignment does
 // not fit (the caller then takes the converting kernel).
-int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cudaStream_t s) {
+int gemm_ps(const GemmDesc& g, cudaStream_t s) {
     using namespace ps;
+    void* out_hi = g.out_hi16; void* out_lo = g.out_lo16;
+    const int64_t ld_out16 = g.ld_out16;
+    const int ones_col = g.out_ones;
     if (!g.a_hi16 || !g.a_lo16 || !g.b_hi16 || !g.b_lo16) return CDG_ERR_UNSUPPORTED;
-    if (g.M < 1024 || g.N < 16 || g.N % 16 != 0 || g.K < 16 || g.K > 2048 || g.accumulate || g.extra_col || g.conv_C > 0)
+    if (g.M < 1024 || g.N < 16 || g.N % 4 != 0 || g.K < 16 || g.K > 2048 || g.accumulate || g.extra_col || g.conv_C > 0)
         return CDG_ERR_UNSUPPORTED;
+    auto al16p = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     if (g.ld_a16 % 8 != 0 || g.ld_b16 % 8 != 0 || (((uintptr_t)g.a_hi16 | (uintptr_t)g.a_lo16 | (uintptr_t)g.b_hi16 | (uintptr_t)g.b_lo16) & 15))
         return CDG_ERR_UNSUPPORTED;
-    if (g.C && !(g.ldc % 8 == 0 && al32p(g.C))) return CDG_ERR_UNSUPPORTED;
+    if (g.C && !(g.ldc % 4 == 0 && al16p(g.C))) return CDG_ERR_UNSUPPORTED;
     if (!g.C && !out_hi) return CDG_ERR_UNSUPPORTED;
-    if (out_hi && !(out_lo && ld_out16 % 16 == 0 && al32p(out_hi) && al32p(out_lo))) return CDG_ERR_UNSUPPORTED;
+    if (out_hi && !(out_lo && ld_out16 % 8 == 0 && ld_out16 >= g.N + (ones_col ? 1 : 0) && al16p(out_hi) && al16p(out_lo)))
+        return CDG_ERR_UNSUPPORTED;
     // (a null bias with a bias epilogue = the bias is folded into the contraction: a ones column in A, the bias column in B)
-    if (g.epi == EPI_MUL_DACT && !(g.aux && g.ld_aux % 8 == 0 && al32p(g.aux))) return CDG_ERR_UNSUPPORTED;
+    if (g.epi == EPI_MUL_DACT && !(g.aux && g.ld_aux % 4 == 0 && al16p(g.aux))) return CDG_ERR_UNSUPPORTED;
     if (g.epi == EPI_RECON) {
         if (!g.recon_x || !g.C) { set_error("EPI_RECON without target / gradient buffer"); return CDG_ERR_INVALID; }
-        if (!(g.ld_x % 8 == 0 && al32p(g.recon_x) && (!g.recon_xhat || al32p(g.recon_xhat)))) return CDG_ERR_UNSUPPORTED;
+        if (!(g.ld_x % 4 == 0 && al16p(g.recon_x) && (!g.recon_xhat || al16p(g.recon_xhat)))) return CDG_ERR_UNSUPPORTED;
     }
-    const int BN = g.N > 128 ? 256 : g.N > 64 ? 128 : 64;
+    // tile width: 256 for wide outputs; the hidden layers (N = 300) take two 160-wide tiles
+    const int BN = g.N > 320 ? 256 : g.N > 256 ? 160 : g.N > 160 ? 256 : g.N > 128 ? 160 : g.N > 64 ? 128 : 64;
     const int64_t tm = (g.M + 2 * BM - 1) / (2 * BM), tn = (g.N + BN - 1) / BN;
     if (tn > (1 << 30) || tm > (1 << 30) || g.M >= (1ll << 31) || g.N >= (1ll << 31)) return CDG_ERR_UNSUPPORTED;
     Params p;
     memset(&p, 0, sizeof(p));
     p.C = g.C; p.ldc = g.ldc; p.M = g.M; p.N = g.N; p.act = g.act; p.bias = g.bias; p.aux = g.aux; p.ld_aux = g.ld_aux;
     p.rx = g.recon_x; p.rx_ld = g.ld_x; p.rxhat = g.recon_xhat; p.racc = g.recon_acc; p.inv_batch = g.inv_batch;
-    p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo; p.ld16 = ld_out16;
+    p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo; p.ld16 = ld_out16; p.ones_col = ones_col;
+    p.c8 = (!g.C || (g.ldc % 8 == 0 && al32p(g.C))) && (!g.recon_xhat || al32p(g.recon_xhat)) ? 1 : 0;
+    p.side8 = g.epi == EPI_RECON ? (g.ld_x % 8 == 0 && al32p(g.recon_x)) : g.epi == EPI_MUL_DACT ? (g.ld_aux % 8 == 0 && al32p(g.aux)) : 0;
     p.kb_total = (int)((g.K + BK - 1) / BK); p.tiles_n = (int)tn; p.work_total = tm * tn;
     CUtensorMap tah, tal, tbh, tbl;
     CDG_TRY(plane_map(g.a_hi16, g.M, g.K, g.ld_a16, BM, &tah));
@@ -654,7 +699,11 @@ int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cud
     CDG_TRY(plane_map(g.b_hi16, g.N, g.K, g.ld_b16, BN / 2, &tbh));
     CDG_TRY(plane_map(g.b_lo16, g.N, g.K, g.ld_b16, BN / 2, &tbl));
     static const int staged = exp_switch("CDG_PS_STG", 1);
-    if (g.epi == EPI_RECON && BN == 256 && g.N % 32 == 0 && staged) {
+    if (out_hi) {
+        if (g.epi == EPI_RECON) return CDG_ERR_UNSUPPORTED;          // (the staged head writes fp32 gradients only)
+        tl_planes_done = true;
+    }
+    if (g.epi == EPI_RECON && BN == 256 && g.N % 32 == 0 && staged && p.c8 && p.side8) {
         // reconstruction head: target in / gradient out through shared memory by TMA
         CUtensorMap tx, tcm;
         CDG_TRY(chunk_map_f32(g.recon_x, g.M, g.N, g.ld_x, &tx));
@@ -662,6 +711,7 @@ int gemm_ps(const GemmDesc& g, void* out_hi, void* out_lo, int64_t ld_out16, cud
         return launch<256, EPI_RECON, true>(tah, tal, tbh, tbl, p, s, &tx, &tcm);
     }
     if (BN == 256) return launch_epi<256>(g.epi, tah, tal, tbh, tbl, p, s);
+    if (BN == 160) return launch_epi<160>(g.epi, tah, tal, tbh, tbl, p, s);
     if (BN == 128) return launch_epi<128>(g.epi, tah, tal, tbh, tbl, p, s);
     return launch_epi<64>(g.epi, tah, tal, tbh, tbl, p, s);
 }

@@ -5,6 +5,8 @@
 // reference batch size, and (iii) the on-device cross-check of the tensor-core kernel.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace cdg {
 
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
@@ -113,10 +115,72 @@ __global__ void bias_act_kernel(float* C, int64_t ldc, int64_t M, int64_t N, con
         C[m * ldc + n] = v;
     }
 }
+// The same pass over groups of 4 columns (16-byte accesses), optionally writing the bf16 (hi, lo) planes of the result
+// [M][ld16] for a following pre-split GEMM: columns >= N are 0, column N is 1 when `ones`.
+__global__ void __launch_bounds__(256) bias_act_rows_kernel(float* C, int64_t ldc, int64_t M, int N, const float* __restrict__ bias,
+                                                            int epi, int act, const float* __restrict__ aux, int64_t ld_aux,
+                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                            int64_t ld16, int ones) {
+    const int n4 = N >> 2, groups = hi ? (int)(ld16 >> 2) : n4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / groups;
+        const int q = (int)(i - m * groups);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q < n4) {
+            float4* cp = reinterpret_cast<float4*>(C + m * ldc) + q;
+            const float4 c = *cp;
+            v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+            if (epi == EPI_BIAS || epi == EPI_BIAS_ACT) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            }
+            if (epi == EPI_BIAS_ACT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = act_fwd(v[e], act);
+            }
+            if (epi == EPI_MUL_DACT) {
+                const float4 h = __ldg(reinterpret_cast<const float4*>(aux + m * ld_aux) + q);
+                v[0] *= act_bwd_from_out(h.x, act); v[1] *= act_bwd_from_out(h.y, act);
+                v[2] *= act_bwd_from_out(h.z, act); v[3] *= act_bwd_from_out(h.w, act);
+            }
+            if (epi != EPI_NONE) *cp = make_float4(v[0], v[1], v[2], v[3]);
+        } else if (q == n4 && ones) {
+            v[0] = 1.f;
+        }
+        if (hi) {
+            uint32_t h2[2], l2[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+                h2[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                l2[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint2*>(hi + m * ld16 + 4 * q) = make_uint2(h2[0], h2[1]);
+            *reinterpret_cast<uint2*>(lo + m * ld16 + 4 * q) = make_uint2(l2[0], l2[1]);
+        }
+    }
+}
 
 int launch_bias_act(float* C, int64_t ldc, int64_t M, int64_t N, const float* bias, int epi, int act,
-                    const float* aux, int64_t ld_aux, cudaStream_t s) {
-    if (M * N == 0 || epi == EPI_NONE) return CDG_OK;
+                    const float* aux, int64_t ld_aux, cudaStream_t s, void* out_hi, void* out_lo, int64_t ld_out16, int out_ones) {
+    if (M * N == 0 || (epi == EPI_NONE && !out_hi)) return CDG_OK;
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    const bool rows = N % 4 == 0 && N < (1 << 30) && ldc % 4 == 0 && al16(C) &&
+                      (!(epi == EPI_BIAS || epi == EPI_BIAS_ACT) || al16(bias)) &&
+                      (epi != EPI_MUL_DACT || (ld_aux % 4 == 0 && al16(aux))) &&
+                      (!out_hi || (out_lo && ld_out16 % 4 == 0 && ld_out16 >= N + (out_ones ? 1 : 0) &&
+                                   ((uintptr_t)out_hi & 7) == 0 && ((uintptr_t)out_lo & 7) == 0));
+    if (rows) {
+        const int64_t total = M * (out_hi ? ld_out16 / 4 : N / 4);
+        bias_act_rows_kernel<<<(int)imin64((total + 255) / 256, kNumSMs * 16), 256, 0, s>>>(
+            C, ldc, M, (int)N, bias, epi, act, aux, ld_aux, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out16, out_ones);
+        CDG_CHECK_LAUNCH();
+        if (out_hi) tl_planes_done = true;
+        return CDG_OK;
+    }
+    if (epi == EPI_NONE) return CDG_OK;
     const int64_t total = M * N;
     const int blocks = (int)imin64((total + 255) / 256, kNumSMs * 8);
     bias_act_kernel<<<blocks, 256, 0, s>>>(C, ldc, M, N, bias, epi, act, aux, ld_aux);

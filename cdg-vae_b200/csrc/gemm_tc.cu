@@ -1488,7 +1488,8 @@ int gemm_tc(const GemmDesc& g0, int passes, void*, int64_t, cudaStream_t s) {
     }
     CDG_TRY(r);
     if (p.atomic && g0.epi != EPI_NONE)
-        CDG_TRY(launch_bias_act(g0.C, g0.ldc, g0.M, g0.N, g0.bias, g0.epi, g0.act, g0.aux, g0.ld_aux, s));
+        CDG_TRY(launch_bias_act(g0.C, g0.ldc, g0.M, g0.N, g0.bias, g0.epi, g0.act, g0.aux, g0.ld_aux, s, g0.out_hi16, g0.out_lo16,
+                                g0.ld_out16, g0.out_ones));
     return CDG_OK;
 }
 

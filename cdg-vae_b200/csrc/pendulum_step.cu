@@ -29,11 +29,13 @@ static inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }
 static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
 // batches from which the step pre-splits its weights (below, the extra ~0.1 ms per step is not repaid)
 constexpr int64_t kSplitMinBatch = 2048;
-constexpr int64_t kLd16 = 304;          // row stride (bf16 elements) of an activation's planes: pad16(hidden = 300)
+// row stride (bf16 elements) of a hidden activation's planes: room for the column of ones behind the `hidden` values
+static inline int64_t plane_ld(int64_t hidden) { return pad8(hidden + 1); }
+struct PlaneBuf { uint16_t* hi; uint16_t* lo; };
 
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
-        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, a16, total;
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, a16, b16, plane_half, total;
     int64_t asplit_half;           // elements of one (hi or lo) transposed activation copy
     // InfoMax discriminator (allocated only when requested)
     int64_t dx, dh1j, dh1m, dh2j, dh2m, dj, dm, dgj, dgm, dg2, dg1j, dg1m, deps_perm, dtj, dtm, dgeps;
@@ -67,8 +69,11 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, i
     // wgrad: the narrow [batch, <= 304] operand, split + transposed per call (hi then lo)
     w.asplit_half = pad64(304 * pad8(B > BL ? B : BL));
     w.asplit = take(B >= kSplitMinBatch && split_elems > 0 ? w.asplit_half : 0);
-    // bf16 (hi, lo) planes [B][304] of an activation feeding the pre-split kernel (gemm_ps.cu) as its A operand
-    w.a16 = take(B >= kSplitMinBatch && split_elems > 0 ? B * kLd16 : 0);
+    // two buffers of bf16 (hi, lo) planes [rows][ld16] for the activations / gradients that feed the pre-split kernel
+    // (gemm_ps.cu) as its A operand: a producer writes one, the next GEMM reads it (and may write the other)
+    w.plane_half = pad64((B > BL ? B : BL) * plane_ld(c.hidden) / 2);     // floats per plane (2 bf16 per float)
+    w.a16 = take(B >= kSplitMinBatch && split_elems > 0 ? 2 * w.plane_half : 0);
+    w.b16 = take(B >= kSplitMinBatch && split_elems > 0 ? 2 * w.plane_half : 0);
     const int64_t Bi = infomax ? B : 0;
     w.dx = take(Bi * H); w.dh1j = take(Bi * H); w.dh1m = take(Bi * H); w.dh2j = take(Bi * H); w.dh2m = take(Bi * H);
     w.dj = take(Bi); w.dm = take(Bi); w.dgj = take(Bi); w.dgm = take(Bi);
@@ -98,6 +103,12 @@ struct Ctx {
         return -1;
     }
     const uint16_t* pool() const { return reinterpret_cast<const uint16_t*>(W + w.wsplit); }
+    int64_t ld16() const { return plane_ld(p->c.hidden); }
+    bool planes_ok() const { return split && w.a16 > 0 && p->c.hidden % 4 == 0; }
+    PlaneBuf planes(int which) const {
+        uint16_t* hi = reinterpret_cast<uint16_t*>(W + (which ? w.b16 : w.a16));
+        return PlaneBuf{hi, hi + 2 * w.plane_half};
+    }
 };
 
 // point a forward GEMM (B = W[row_lo:, :], K = in) at the pre-split copy of L; false when L has none
@@ -124,11 +135,26 @@ static bool use_split_dgrad(const Ctx& c, const cdg_linear& L, int64_t row_lo, G
 // the bf16x3 kernel with ready-made weight tiles; anything it cannot take goes the usual way
 static int gemm_weights(const Ctx& c, GemmDesc& g, bool have_split) {
     if (have_split) {
+        tl_planes_done = false;
         const int r = gemm_tc(g, 2, nullptr, 0, c.s);
+        if (r == CDG_OK) return finish_planes(g, c.s);
         if (r != CDG_ERR_UNSUPPORTED) return r;
         g.b_hi16 = g.b_lo16 = nullptr;
     }
     return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
+}
+static bool use_ps();
+// the pre-split kernel on planes of A made by the producer of the activation; CDG_ERR_UNSUPPORTED = take the usual route
+static int gemm_planes_a(const Ctx& c, GemmDesc g, const PlaneBuf* in) {
+    if (!in || !c.planes_ok() || !use_ps()) return CDG_ERR_UNSUPPORTED;
+    g.a_hi16 = in->hi; g.a_lo16 = in->lo; g.ld_a16 = c.ld16();
+    tl_planes_done = false;
+    const int r = gemm_ps(g, c.s);
+    return r == CDG_OK ? finish_planes(g, c.s) : r;
+}
+static void want_planes(const Ctx& c, GemmDesc& g, const PlaneBuf* out, int ones) {
+    if (!out || !c.planes_ok()) return;
+    g.out_hi16 = out->hi; g.out_lo16 = out->lo; g.ld_out16 = c.ld16(); g.out_ones = ones;
 }
 
 static bool use_ps() {
@@ -158,15 +184,25 @@ static int split_weights(Ctx& c, int64_t B) {
 }
 
 // Y[M,N] = act(X[M,K] W[N,K]^T + b)   (nn.Linear forward)
+// `in`: planes of X (with the column of ones) written by X's producer; `out`: where to leave the planes of Y
 static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
-                      float* Y, int64_t ldy, int64_t M, bool act, int cat = PROF_GEMM_OTHER) {
+                      float* Y, int64_t ldy, int64_t M, bool act, int cat = PROF_GEMM_OTHER, const PlaneBuf* in = nullptr,
+                      const PlaneBuf* out = nullptr) {
     c.mark(cat);
     GemmDesc g;
     g.A = X; g.sa_m = ldx; g.sa_k = 1;
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = L.in; g.sb_k = 1;
     g.C = Y; g.ldc = ldy; g.M = M; g.N = n_rows; g.K = L.in;
     g.epi = act ? EPI_BIAS_ACT : EPI_BIAS; g.act = CDG_ACT_ELU; g.bias = c.P + L.b + row_lo;
-    return gemm_weights(c, g, use_split_fwd(c, L, row_lo, g));
+    want_planes(c, g, out, 1);
+    const bool sp = use_split_fwd(c, L, row_lo, g);
+    if (sp && in) {
+        GemmDesc h = g;
+        if (pad8(L.in) > L.in) { h.K = L.in + 1; h.bias = nullptr; }    // the weight planes carry the bias in column `in`
+        const int r = gemm_planes_a(c, h, in);
+        if (r != CDG_ERR_UNSUPPORTED) return r;
+    }
+    return gemm_weights(c, g, sp);
 }
 // dW[rows,K] += dY[M,rows]^T X[M,K];  db[rows] += colsum(dY)
 static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float* X, int64_t ldx, const cdg_linear& L,
@@ -206,14 +242,21 @@ static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float*
 }
 // dX[M,K] = (dY[M,rows] W[rows,K]) * act'(Hout)      (Hout == nullptr: no activation in front)
 static int linear_dgrad(const Ctx& c, const float* dY, int64_t ldy, const cdg_linear& L, int64_t row_lo, int64_t n_rows,
-                        float* dX, int64_t lddx, const float* Hout, int64_t ldh, int64_t M, int cat = PROF_GEMM_OTHER) {
+                        float* dX, int64_t lddx, const float* Hout, int64_t ldh, int64_t M, int cat = PROF_GEMM_OTHER,
+                        const PlaneBuf* in = nullptr, const PlaneBuf* out = nullptr) {
     c.mark(cat);
     GemmDesc g;
     g.A = dY; g.sa_m = ldy; g.sa_k = 1;
     g.B = c.P + L.w + row_lo * L.in; g.sb_n = 1; g.sb_k = L.in;
     g.C = dX; g.ldc = lddx; g.M = M; g.N = L.in; g.K = n_rows;
     if (Hout) { g.epi = EPI_MUL_DACT; g.act = CDG_ACT_ELU; g.aux = Hout; g.ld_aux = ldh; }
-    return gemm_weights(c, g, use_split_dgrad(c, L, row_lo, g));
+    want_planes(c, g, out, 0);
+    const bool sp = use_split_dgrad(c, L, row_lo, g);
+    if (sp && in) {
+        const int r = gemm_planes_a(c, g, in);
+        if (r != CDG_ERR_UNSUPPORTED) return r;
+    }
+    return gemm_weights(c, g, sp);
 }
 
 static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
@@ -227,8 +270,9 @@ static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
 static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float* h2, float* ml) {
     const cdg_pendulum_config& cf = c.p->c;
     const int64_t H = cf.hidden, d = cf.node;
-    CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true, PROF_ENC0_FWD));
-    CDG_TRY(linear_fwd(c, h1, H, cf.enc[1], 0, H, h2, H, B, true));
+    const PlaneBuf p0 = c.planes(0);
+    CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true, PROF_ENC0_FWD, nullptr, &p0));
+    CDG_TRY(linear_fwd(c, h1, H, cf.enc[1], 0, H, h2, H, B, true, PROF_GEMM_OTHER, &p0));
     CDG_TRY(linear_fwd(c, h2, H, cf.enc[2], 0, 2 * d, ml, 2 * d, B, false));
     return CDG_OK;
 }
@@ -238,9 +282,10 @@ static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1,
     const cdg_pendulum_config& cf = c.p->c;
     const int64_t H = cf.hidden, d = cf.node;
     CDG_TRY(linear_wgrad(c, g_ml, 2 * d, h2, H, cf.enc[2], 0, 2 * d, B));
-    CDG_TRY(linear_dgrad(c, g_ml, 2 * d, cf.enc[2], 0, 2 * d, g_h2, H, h2, H, B));
+    const PlaneBuf p0 = c.planes(0);
+    CDG_TRY(linear_dgrad(c, g_ml, 2 * d, cf.enc[2], 0, 2 * d, g_h2, H, h2, H, B, PROF_GEMM_OTHER, nullptr, &p0));
     CDG_TRY(linear_wgrad(c, g_h2, H, h1, H, cf.enc[1], 0, H, B));
-    CDG_TRY(linear_dgrad(c, g_h2, H, cf.enc[1], 0, H, g_h1, H, h1, H, B));
+    CDG_TRY(linear_dgrad(c, g_h2, H, cf.enc[1], 0, H, g_h1, H, h1, H, B, PROF_GEMM_OTHER, &p0));
     CDG_TRY(linear_wgrad(c, g_h1, H, x, cf.input_dim, cf.enc[0], 0, H, B, PROF_ENC0_WGRAD));
     return CDG_OK;
 }
@@ -286,24 +331,21 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
         float* a2 = c.W + c.w.a2[k];
         const float* zin; int64_t ldz;
         CDG_TRY(dec_input(c, k, z, B, &zin, &ldz));
-        CDG_TRY(linear_fwd(c, zin, ldz, cf.dec[k][0], 0, H, a1, H, B, true));
-        CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true));
+        const PlaneBuf p0 = c.planes(0), p1 = c.planes(1);
+        CDG_TRY(linear_fwd(c, zin, ldz, cf.dec[k][0], 0, H, a1, H, B, true, PROF_GEMM_OTHER, nullptr, &p0));
+        CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true, PROF_GEMM_OTHER, &p0, x ? &p1 : nullptr));
         if (cf.col_hi[k] - cf.col_lo[k] > 0) {
             c.mark(PROF_DEC2_FWD);
             GemmDesc g = dec_out_desc(c, k, B, pre, x, xhat, acc);
             const bool sp = use_split_fwd(c, cf.dec[k][2], cf.col_lo[k], g);
             if (x) {
                 int r = CDG_ERR_UNSUPPORTED;
-                if (sp && c.w.a16 > 0 && H <= kLd16 && use_ps()) {
-                    // both operands as bf16 planes: TMA feeds the MMA directly, eight epilogue warps (gemm_ps.cu)
-                    uint16_t* ah = reinterpret_cast<uint16_t*>(c.W + c.w.a16);
-                    uint16_t* al = ah + B * kLd16;
-                    CDG_TRY(launch_split_rows(a2, B, H, H, ah, al, kLd16, nullptr, 1, c.s));      // column H = 1: the bias column
-                    g.a_hi16 = ah; g.a_lo16 = al; g.ld_a16 = kLd16;
-                    const float* bias = g.bias;
-                    g.K = H + 1; g.bias = nullptr;                    // W2's planes carry b2 in column H (split_weights)
-                    r = gemm_ps(g, nullptr, nullptr, 0, c.s);
-                    g.a_hi16 = g.a_lo16 = nullptr; g.K = H; g.bias = bias;
+                if (sp && c.planes_ok() && use_ps()) {
+                    // both operands as bf16 planes (a2's were written by the Linear that produced it, with the column of
+                    // ones that multiplies b2 in W2's planes): TMA feeds the MMA directly, eight epilogue warps (gemm_ps.cu)
+                    GemmDesc h = g;
+                    if (pad8(H) > H) { h.K = H + 1; h.bias = nullptr; }
+                    r = gemm_planes_a(c, h, &p1);
                 }
                 if (r == CDG_ERR_UNSUPPORTED) r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
                 if (r == CDG_ERR_UNSUPPORTED) {
@@ -686,16 +728,17 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         const float* a1 = W + c.w.a1[k];
         const float* a2 = W + c.w.a2[k];
         const bool dr = cf.dec_extra[k] >= 0;
+        const PlaneBuf bp0 = c.planes(0);
         const float* zk = dr ? W + c.w.zin[k] : W + c.w.z + p->lat_off[k];
         const int64_t ldzk = dr ? cf.factor[k] + 1 : d;
         if (n > 0) {
             CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B, PROF_DEC2_WGRAD));
-            CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B, PROF_DEC2_DGRAD));
+            CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B, PROF_DEC2_DGRAD, nullptr, &bp0));
         } else {
             CDG_CHECK_CUDA(cudaMemsetAsync(ga2, 0, sizeof(float) * B * H, s));
         }
         CDG_TRY(linear_wgrad(c, ga2, H, a1, H, cf.dec[k][1], 0, H, B));
-        CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B));
+        CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B, PROF_GEMM_OTHER, n > 0 ? &bp0 : nullptr));
         CDG_TRY(linear_wgrad(c, ga1, H, zk, ldzk, cf.dec[k][0], 0, H, B));
         if (!dr) {
             CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, g_z + p->lat_off[k], d, nullptr, 0, B));
@@ -823,5 +866,6 @@ extern "C" int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a1
     g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
     g.epi = epi == 1 ? EPI_BIAS : epi == 2 ? EPI_BIAS_ACT : epi == 3 ? EPI_MUL_DACT : EPI_NONE;
     g.act = CDG_ACT_ELU; g.bias = bias; g.aux = aux; g.ld_aux = ld_aux;
-    return gemm_ps(g, out_hi, out_lo, ld_out16, (cudaStream_t)stream);
+    g.out_hi16 = out_hi; g.out_lo16 = out_lo; g.ld_out16 = ld_out16;
+    return gemm_ps(g, (cudaStream_t)stream);
 }

@@ -6,6 +6,7 @@
 //   skinny_wgrad  min(M,N) <= 8, contraction over the batch: wgrad of those two layers
 #include "common.cuh"
 
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace cdg {
@@ -98,6 +99,21 @@ __global__ void __launch_bounds__(256) rowdot_kernel(GemmDesc g) {
 // read-only cache for every element: ncu launch lists showed them at 1.2-1.4 TB/s.  Here the tiny operand (and the bias)
 // sits in shared memory, a warp owns one batch row at a time, and every global access is a 16-byte piece of one
 // contiguous 1,200-byte row.
+// 4 adjacent results -> 4 bf16 of the hi plane and 4 of the lo plane (8-byte stores)
+__device__ __forceinline__ void planes4(const GemmDesc& g, int64_t m, int q, const float* v) {
+    uint32_t h2[2], l2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
+        h2[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l2[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out_hi16) + m * g.ld_out16 + 4 * q) = make_uint2(h2[0], h2[1]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out_lo16) + m * g.ld_out16 + 4 * q) = make_uint2(l2[0], l2[1]);
+}
+
 __global__ void __launch_bounds__(256) smallk_rows_kernel(GemmDesc g) {
     extern __shared__ __align__(16) float sk_sm[];        // [K][N] weights, then [N] bias
     const int K = (int)g.K, N = (int)g.N, n4 = N >> 2;
@@ -149,6 +165,13 @@ __global__ void __launch_bounds__(256) smallk_rows_kernel(GemmDesc g) {
                 s[0] += o.x; s[1] += o.y; s[2] += o.z; s[3] += o.w;
             }
             crow[q] = make_float4(s[0], s[1], s[2], s[3]);
+            if (g.out_hi16) planes4(g, m, q, s);
+        }
+        if (g.out_hi16) {                                  // padding groups: column N = 1 when asked, the rest 0
+            for (int q = n4 + lane; q < (int)(g.ld_out16 >> 2); q += 32) {
+                const float z[4] = {(q == n4 && g.out_ones) ? 1.f : 0.f, 0.f, 0.f, 0.f};
+                planes4(g, m, q, z);
+            }
         }
     }
 }
@@ -245,8 +268,13 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
         if (rows_ok && vec && g.M >= 64 && g.K * g.N <= 8192 && g.N >= 128) {
             const size_t smem = sizeof(float) * (size_t)(g.K * g.N + g.N);
             const int blocks = (int)imin64((g.M + 7) / 8, kNumSMs * 8);
-            smallk_rows_kernel<<<blocks, 256, smem, s>>>(g);
+            GemmDesc gg = g;
+            const bool planes = g.out_hi16 && g.out_lo16 && g.ld_out16 % 4 == 0 && g.ld_out16 >= g.N + (g.out_ones ? 1 : 0) &&
+                                (((uintptr_t)g.out_hi16 | (uintptr_t)g.out_lo16) & 7) == 0;
+            if (!planes) gg.out_hi16 = gg.out_lo16 = nullptr;      // (the dispatcher then adds the split pass)
+            smallk_rows_kernel<<<blocks, 256, smem, s>>>(gg);
             CDG_CHECK_LAUNCH();
+            if (planes) tl_planes_done = true;
             return CDG_OK;
         }
         const int64_t total = vec ? g.M * g.N / 4 : g.M * g.N;
