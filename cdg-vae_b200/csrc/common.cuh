@@ -187,6 +187,9 @@ int gemm_tc(const GemmDesc& g, int passes, void* workspace, int64_t workspace_by
 // CTA-pair bf16x3 kernel for operands that BOTH arrive as bf16 (hi, lo) planes (gemm_ps.cu): needs a_hi16 / a_lo16 and
 // b_hi16 / b_lo16 (no operand swap); out_hi / out_lo (optional) receive the planes of the result for the next GEMM.
 int gemm_ps(const GemmDesc& g, cudaStream_t s);
+// long contractions on planes, accumulated into C with fp32 atomics per <= 2048-long segment (gemm_pk.cu); mn_major: the
+// planes are stored with the contraction index outermost ([K][M], [K][N]: weight gradients)
+int gemm_pk(const GemmDesc& g, int mn_major, cudaStream_t s);
 bool gemm_tc_can(const GemmDesc& g);   // would gemm_tc accept this contraction (without split-K)?
 int gemm_dispatch(int mode, const GemmDesc& g, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 

@@ -869,3 +869,14 @@ extern "C" int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a1
     g.out_hi16 = out_hi; g.out_lo16 = out_lo; g.ld_out16 = ld_out16;
     return gemm_ps(g, (cudaStream_t)stream);
 }
+
+extern "C" int cdg_gemm_planes_acc(const void* a_hi, const void* a_lo, int64_t ld_a16, const void* b_hi, const void* b_lo,
+                                   int64_t ld_b16, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int mn_major,
+                                   float* extra_col, void* stream) {
+    CDG_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "cdg_gemm_planes_acc: null pointer");
+    GemmDesc g;
+    g.A = nullptr; g.sa_m = 0; g.sa_k = 0; g.B = nullptr; g.sb_n = 0; g.sb_k = 0;
+    g.a_hi16 = a_hi; g.a_lo16 = a_lo; g.ld_a16 = ld_a16; g.b_hi16 = b_hi; g.b_lo16 = b_lo; g.ld_b16 = ld_b16;
+    g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.accumulate = 1; g.extra_col = extra_col;
+    return gemm_pk(g, mn_major, (cudaStream_t)stream);
+}

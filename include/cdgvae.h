@@ -346,6 +346,15 @@ int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a16, const vo
                     float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epi, const float* bias, const float* aux,
                     int64_t ld_aux, void* out_hi, void* out_lo, int64_t ld_out16, void* stream);
 
+/* Long contractions on planes (csrc/gemm_pk.cu): C[M,N] += sum_k A(m,k) B(n,k), N <= 304, K cut into segments of <= 2048
+ * whose partial tiles are added to C with fp32 atomics (C must hold the value to accumulate into, e.g. zeros).
+ * mn_major = 0: planes are [M][ld_a16] / [N][ld_b16] (contraction index contiguous: input gradients);
+ * mn_major = 1: planes are [K][ld_a16] / [K][ld_b16] (contraction index outermost: weight gradients, contraction over the
+ * batch, both operands read as they lie in memory).  extra_col (optional, [M]): column N-1 of the product is added there
+ * instead of to C (a ones column in B then yields the bias gradient); C then has N-1 columns. */
+int cdg_gemm_planes_acc(const void* a_hi, const void* a_lo, int64_t ld_a16, const void* b_hi, const void* b_lo, int64_t ld_b16,
+                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int mn_major, float* extra_col, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * CDG-TVAE data transform, APPLY side: the step on either side of train_TVAE.
  * Fitting (BayesianGaussianMixture, category discovery) stays on the host; its result arrives here as tables.

@@ -123,3 +123,48 @@ def test_gemm_planes_rejects_what_it_cannot_take():
     rc = _lib.lib().cdg_gemm_planes(p(ah), p(al), 64, p(bh), p(bl), 64, p(out), 32, 512, 32, 64, 0, None, None, 0, None, None, 0,
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 4                                                          # CDG_ERR_UNSUPPORTED: M < 1024
+
+
+# ---- long contractions on planes, K-major (input gradients) and MN-major (weight gradients): csrc/gemm_pk.cu ----------------
+ACC_SHAPES = [  # (M, N, K, mn_major, with_extra_col)
+    (4096, 300, 2496, 0, False), (2048 + 100, 300, 5952, 0, False), (1024, 304, 4096, 0, False), (512, 64, 256, 0, False),
+    (2496, 301, 8192, 1, True), (5952, 301, 4096 + 40, 1, True), (300, 300, 16384, 1, False), (1000, 304, 2048, 1, False),
+    (300, 301, 8192, 1, True), (128, 16, 64, 1, False),
+]
+
+
+@pytest.mark.parametrize("shape", ACC_SHAPES)
+def test_gemm_planes_acc(shape):
+    from cdgvae_b200 import _lib
+    M, N, K, mn, extra = shape
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + mn)
+    A = torch.randn(M, K, generator=g).cuda(); B = (torch.randn(N, K, generator=g) * 0.1).cuda()
+    if extra:
+        B[N - 1] = 1.0                                      # the ones column of a weight-gradient's activation operand
+    pad8 = lambda n: (n + 7) // 8 * 8
+    if mn:                                                  # planes stored [K][M] / [K][N]
+        ah, al = _planes(A.t().contiguous(), pad8(M)); bh, bl = _planes(B.t().contiguous(), pad8(N))
+        lda, ldb = pad8(M), pad8(N)
+        Ap = (ah[:, :M].double() + al[:, :M].double()).t(); Bp = (bh[:, :N].double() + bl[:, :N].double()).t()
+    else:
+        ah, al = _planes(A, pad8(K)); bh, bl = _planes(B, pad8(K))
+        lda = ldb = pad8(K)
+        Ap = ah[:, :K].double() + al[:, :K].double(); Bp = bh[:, :K].double() + bl[:, :K].double()
+    nc = N - 1 if extra else N
+    C0 = torch.randn(M, nc, generator=g).cuda()
+    out = C0.clone()
+    ex0 = torch.randn(M, generator=g).cuda()
+    ex = ex0.clone()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib().cdg_gemm_planes_acc(p(ah), p(al), lda, p(bh), p(bl), ldb, p(out), nc, M, N, K, mn, p(ex) if extra else None,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    full = A.double() @ B.double().t()
+    fullp = Ap @ Bp.t()
+    ref, refp = C0.double() + full[:, :nc], C0.double() + fullp[:, :nc]
+    err = float((out.double() - ref).norm() / ref.norm()); errp = float((out.double() - refp).norm() / refp.norm())
+    assert err < 5e-5 and errp < 8e-6, (shape, err, errp)
+    if extra:
+        r = ex0.double() + full[:, nc]
+        assert float((ex.double() - r).norm() / r.norm()) < 5e-5
