@@ -128,7 +128,7 @@ class TvaeTransformConfig(C.Structure):
 # every symbol include/cdgvae.h declares
 EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_launch_count_add", "cdg_abi_sizeof", "cdg_flow_apply", "cdg_pendulum_profile_enable",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
-           "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward",
+           "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_offset", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
@@ -182,6 +182,8 @@ def lib():
     L.cdg_pendulum_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cdg_pendulum_workspace_bytes.restype = C.c_int64
     L.cdg_pendulum_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.cdg_pendulum_workspace_offset.restype = C.c_int64
+    L.cdg_pendulum_workspace_offset.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
     L.cdg_pendulum_workspace_bytes_infomax.restype = C.c_int64
     L.cdg_pendulum_workspace_bytes_infomax.argtypes = [C.c_void_p, C.c_int64]
     L.cdg_pendulum_create.argtypes = [C.POINTER(PendulumConfig), C.POINTER(C.c_void_p)]

@@ -51,7 +51,7 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;
     static constexpr int TMEM_COLS = NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;
     static constexpr int BIAS_BYTES = 2 * BN * 4;             // per-tile bias values, two tiles in flight
     static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + BIAS_BYTES;   // (1024-aligned dynamic base)
     static_assert(BN % 32 == 0 && BN <= 256, "one MMA per tile: N <= 256, whole 16-column chunks per epilogue half");
@@ -128,11 +128,15 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* hi, __nv_bfloat16* 
 
 constexpr float K2LOG2E = 2.885390081777927f;    // 2 * log2(e): tanh(x) = 1 - 2 / (1 + 2^(K2LOG2E x))
 
-template <int BN, int EPI, bool STG>
+// PL (staged reconstruction head only): the gradient leaves as bf16 (hi, lo) planes (tmC / tmC2) instead of fp32 -- the same
+// bytes, in the form the decoder's input- and weight-gradient GEMMs (gemm_pk.cu) consume without converting anything.
+template <int BN, int EPI, bool STG, bool PL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC, const Params p) {
+               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmC2, const Params p) {
+    static_assert(!PL || STG, "planes of the gradient: staged reconstruction head only");
     using C_ = Cfg<BN, STG>;
     constexpr int NACC = C_::NACC;
     constexpr int STAGES = C_::STAGES;
@@ -146,7 +150,8 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     uint64_t* acc_full = empty + STAGES;         // [NACC]    accumulator complete (multicast)
     uint64_t* acc_empty = acc_full + NACC;       // [NACC]    drained by both CTAs' epilogue warps (leader's copy is used)
     uint64_t* in_full = acc_empty + NACC;        // [NE][EPI_NIN] staged epilogue: a warp's target chunk landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + (STG ? NE * EPI_NIN : 0));
+    uint64_t* in_empty = in_full + (STG ? NE * EPI_NIN : 0);   // [NE][EPI_NIN] ... and has been read by all 32 lanes
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + (STG ? NE * EPI_NIN : 0));
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C_::BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,7 +174,10 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             mbar_init(smem_u32(&acc_empty[b]), 2 * NE);
         }
         if (STG)
-            for (int b = 0; b < NE * EPI_NIN; ++b) mbar_init(smem_u32(&in_full[b]), 1);
+            for (int b = 0; b < NE * EPI_NIN; ++b) {
+                mbar_init(smem_u32(&in_full[b]), 1);
+                mbar_init(smem_u32(&in_empty[b]), 32);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -254,6 +262,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             constexpr int CPT = HC / 32;               // 32-column chunks per warp and tile
             uint8_t* ebuf = epi_base + (size_t)ew * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES;
             uint64_t* infull = in_full + ew * EPI_NIN;
+            uint64_t* inempty = in_empty + ew * EPI_NIN;
             const int et = threadIdx.x - 64;
             auto nvalid = [&](int n_blk) {             // chunks of this warp's column half that hold real columns
                 const int64_t nv = (p.N - ((int64_t)n_blk * BN + half * HC) + 31) / 32;
@@ -337,31 +346,60 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                                      : "r"(xin + sw_chunk<32>((uint32_t)lane, (uint32_t)ch)));
                         xs[4 * ch] = t.x; xs[4 * ch + 1] = t.y; xs[4 * ch + 2] = t.z; xs[4 * ch + 3] = t.w;
                     }
-                    __syncwarp();
-                    if (lane == 0) issue_next();                     // refill the buffer just read
+                    // Refill the buffer just read -- but only once every lane's loads have been PERFORMED: a shared-memory load
+                    // that has merely been issued may still be queued in the pipe when an early refill lands (seen on B200 as
+                    // a few stale 32-byte row tails per million elements; __syncwarp orders execution, not completion).  The
+                    // consumer-release idiom: every lane arrives (release) on the buffer's "empty" barrier behind its loads,
+                    // the issuing lane waits for that phase (acquire) before the TMA write.
+                    mbar_arrive(smem_u32(&inempty[b]));
+                    if (lane == 0) {
+                        mbar_wait(smem_u32(&inempty[b]), ((ccount - 1) / EPI_NIN) & 1u);
+                        issue_next();
+                    }
                     const int col0 = n_blk * BN + half * HC + c * 32;
                     // the bulk store that used the output buffer has read it
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (has_bias)
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
-                                         : "r"(bsh + (uint32_t)(c * 32 + 4 * g) * 4u));
-                        const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
-                        float o[4];
+                    for (int gg = 0; gg < 4; ++gg) {                 // 8 columns at a time
+                        float o[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i = 4 * g + e;
-                            const float ex = ex2_approx(fmaf(__uint_as_float(vraw[i]), K2LOG2E, b4[e]));
-                            const float r = rcp_approx(1.f + ex);
-                            const float t = fmaf(-2.f, r, 1.f);
-                            const float df = t - xs[i];
-                            rloss = fmaf(df, df, rloss);
-                            o[e] = (df * p.inv_batch) * fmaf(-t, t, 1.f);
+                        for (int h = 0; h < 2; ++h) {
+                            const int g = 2 * gg + h;
+                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (has_bias)
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                                             : "r"(bsh + (uint32_t)(c * 32 + 4 * g) * 4u));
+                            const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int i = 4 * g + e;
+                                const float ex = ex2_approx(fmaf(__uint_as_float(vraw[i]), K2LOG2E, b4[e]));
+                                const float r = rcp_approx(1.f + ex);
+                                const float t = fmaf(-2.f, r, 1.f);
+                                const float df = t - xs[i];
+                                rloss = fmaf(df, df, rloss);
+                                o[4 * h + e] = (df * p.inv_batch) * fmaf(-t, t, 1.f);
+                            }
                         }
-                        *reinterpret_cast<float4*>(xo + sw_chunk<32>((uint32_t)lane, (uint32_t)g)) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (PL) {
+                            // rows of 64 bytes (32 bf16), SWIZZLE_64B: hi tile, then lo tile
+                            uint32_t hh[4], ll[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(o[2 * k]), h1 = __float2bfloat16_rn(o[2 * k + 1]);
+                                const __nv_bfloat16 l0 = __float2bfloat16_rn(o[2 * k] - __bfloat162float(h0));
+                                const __nv_bfloat16 l1 = __float2bfloat16_rn(o[2 * k + 1] - __bfloat162float(h1));
+                                hh[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                ll[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            }
+                            const uint32_t off = sw_chunk<16>((uint32_t)lane, (uint32_t)gg);
+                            *reinterpret_cast<uint4*>(xo + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            *reinterpret_cast<uint4*>(xo + EPI_CHUNK_BYTES / 2 + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        } else {
+                            *reinterpret_cast<float4*>(xo + sw_chunk<32>((uint32_t)lane, (uint32_t)(2 * gg))) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(xo + sw_chunk<32>((uint32_t)lane, (uint32_t)(2 * gg + 1))) = make_float4(o[4], o[5], o[6], o[7]);
+                        }
                     }
                     if (xh_row) {
                         // only the step whose xhat is returned (the last of a train_* call): tanh recomputed from the accumulator
@@ -383,6 +421,10 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                          reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(xo)), "r"(col0), "r"(row0) : "memory");
+                        if (PL)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmC2)), "r"(smem_u32(xo + EPI_CHUNK_BYTES / 2)), "r"(col0),
+                                         "r"(row0) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -615,10 +657,33 @@ static int chunk_map_f32(const float* X, int64_t rows, int64_t cols, int64_t ld,
     return CDG_OK;
 }
 
-template <int BN, int EPI, bool STG = false>
+// bf16 plane [rows][cols] (row stride ld elements) as 32 x 32 boxes of 64-byte rows, SWIZZLE_64B: the gradient planes the
+// staged reconstruction head stores
+static int chunk_map_bf16(const void* X, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDG_ERR_CUDA; }
+    Key key{X, rows, cols, ld, -16};
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return CDG_OK; }
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32u, 32u}, estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16 chunks) failed (%d)", (int)r); return CDG_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(g_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *out;
+    return CDG_OK;
+}
+
+template <int BN, int EPI, bool STG = false, bool PL = false>
 static int launch(const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh, const CUtensorMap& tbl, const Params& p,
-                  cudaStream_t s, const CUtensorMap* tx = nullptr, const CUtensorMap* tc_ = nullptr) {
-    auto kern = gemm_ps_kernel<BN, EPI, STG>;
+                  cudaStream_t s, const CUtensorMap* tx = nullptr, const CUtensorMap* tc_ = nullptr, const CUtensorMap* tc2 = nullptr) {
+    auto kern = gemm_ps_kernel<BN, EPI, STG, PL>;
     static bool attr_done = false;
     if (!attr_done) {
         CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, STG>::SMEM));
@@ -635,7 +700,7 @@ static int launch(const CUtensorMap& tah, const CUtensorMap& tal, const CUtensor
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CDG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tah, tal, tbh, tbl, tx ? *tx : tah, tc_ ? *tc_ : tah, p));
+    CDG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tah, tal, tbh, tbl, tx ? *tx : tah, tc_ ? *tc_ : tah, tc2 ? *tc2 : tah, p));
     ++g_launches;
     return CDG_OK;
 }
@@ -675,10 +740,11 @@ int gemm_ps(const GemmDesc& g, cudaStream_t s) {
     if (!g.C && !out_hi) return CDG_ERR_UNSUPPORTED;
     if (out_hi && !(out_lo && ld_out16 % 8 == 0 && ld_out16 >= g.N + (ones_col ? 1 : 0) && al16p(out_hi) && al16p(out_lo)))
         return CDG_ERR_UNSUPPORTED;
+    if (g.epi == EPI_RECON && g.recon_xhat && !g.C && g.ldc % 4 != 0) return CDG_ERR_UNSUPPORTED;   // xhat rows use ldc
     // (a null bias with a bias epilogue = the bias is folded into the contraction: a ones column in A, the bias column in B)
     if (g.epi == EPI_MUL_DACT && !(g.aux && g.ld_aux % 4 == 0 && al16p(g.aux))) return CDG_ERR_UNSUPPORTED;
     if (g.epi == EPI_RECON) {
-        if (!g.recon_x || !g.C) { set_error("EPI_RECON without target / gradient buffer"); return CDG_ERR_INVALID; }
+        if (!g.recon_x || (!g.C && !out_hi)) { set_error("EPI_RECON without target / gradient buffer"); return CDG_ERR_INVALID; }
         if (!(g.ld_x % 4 == 0 && al16p(g.recon_x) && (!g.recon_xhat || al16p(g.recon_xhat)))) return CDG_ERR_UNSUPPORTED;
     }
     // tile width: 256 for wide outputs; the hidden layers (N = 300) take two 160-wide tiles
@@ -699,10 +765,17 @@ int gemm_ps(const GemmDesc& g, cudaStream_t s) {
     CDG_TRY(plane_map(g.b_hi16, g.N, g.K, g.ld_b16, BN / 2, &tbh));
     CDG_TRY(plane_map(g.b_lo16, g.N, g.K, g.ld_b16, BN / 2, &tbl));
     static const int staged = exp_switch("CDG_PS_STG", 1);
-    if (out_hi) {
-        if (g.epi == EPI_RECON) return CDG_ERR_UNSUPPORTED;          // (the staged head writes fp32 gradients only)
+    if (out_hi && g.epi == EPI_RECON) {
+        // reconstruction head with the gradient as bf16 planes (no fp32 copy): staged epilogue only
+        if (!(BN == 256 && g.N % 32 == 0 && p.side8 && ld_out16 % 8 == 0)) return CDG_ERR_UNSUPPORTED;
+        CUtensorMap tx, th, tl;
+        CDG_TRY(chunk_map_f32(g.recon_x, g.M, g.N, g.ld_x, &tx));
+        CDG_TRY(chunk_map_bf16(out_hi, g.M, g.N, ld_out16, &th));
+        CDG_TRY(chunk_map_bf16(out_lo, g.M, g.N, ld_out16, &tl));
         tl_planes_done = true;
+        return launch<256, EPI_RECON, true, true>(tah, tal, tbh, tbl, p, s, &tx, &th, &tl);
     }
+    if (out_hi) tl_planes_done = true;
     if (g.epi == EPI_RECON && BN == 256 && g.N % 32 == 0 && staged && p.c8 && p.side8) {
         // reconstruction head: target in / gradient out through shared memory by TMA
         CUtensorMap tx, tcm;

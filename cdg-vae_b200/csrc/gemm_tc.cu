@@ -802,8 +802,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float4 t = *reinterpret_cast<const float4*>(xin + sw_chunk<32>((uint32_t)lane, (uint32_t)ch));
                         xs[4 * ch] = t.x; xs[4 * ch + 1] = t.y; xs[4 * ch + 2] = t.z; xs[4 * ch + 3] = t.w;
                     }
-                    __syncwarp();
-                    if (lane == 0) issue_next();                     // refill the buffer just read
                     const int col0 = n_blk * BN + c * 32;
                     const bool full = (int64_t)col0 + 32 <= p.N;
 #pragma unroll
@@ -829,6 +827,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     put_chunk(&tmC, xs, col0, row0);
                     if (p.rxhat) put_chunk(&tmXh, v, col0, row0);
+                    if (lane == 0) issue_next();                     // refill the target buffer (its values have all been used)
                 }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

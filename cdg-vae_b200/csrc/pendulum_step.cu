@@ -21,6 +21,7 @@ struct cdg_pendulum_plan {
     static constexpr int kLayers = 3 + 3 * CDG_MAX_DEC;
     int64_t f_hi[kLayers], f_lo[kLayers], t_hi[kLayers], t_lo[kLayers];   // forward [out][pad8(in)], transposed [in][pad8(out)]
     int64_t split_elems = 0;
+    int last_pre_planes = 0;     // the last forward_backward left d loss / d pre as bf16 planes (diagnostic hook id 100)
 };
 
 namespace cdg {
@@ -35,7 +36,10 @@ struct PlaneBuf { uint16_t* hi; uint16_t* lo; };
 
 struct PendWs {
     int64_t acc, h1, h2, ml, eps, u, z, zal, g_align, a1[CDG_MAX_DEC], a2[CDG_MAX_DEC], pre, ga2, ga1, g_z, g_ml, g_h2,
-        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, a16, b16, plane_half, total;
+        g_h1, h1l, h2l, mll, g_h2l, g_h1l, gemm_ws, wsplit, asplit, plane_half, total;
+    // bf16 (hi, lo) planes [rows][ld16] of the hidden activations (kept from the forward pass for the weight gradients) and
+    // one scratch pair for the gradient that feeds the next input-gradient GEMM; 0 = not allocated
+    int64_t pl_a1[CDG_MAX_DEC], pl_a2[CDG_MAX_DEC], pl_h1, pl_h1l, pl_g;
     int64_t asplit_half;           // elements of one (hi or lo) transposed activation copy
     // InfoMax discriminator (allocated only when requested)
     int64_t dx, dh1j, dh1m, dh2j, dh2m, dj, dm, dgj, dgm, dg2, dg1j, dg1m, deps_perm, dtj, dtm, dgeps;
@@ -72,8 +76,9 @@ static PendWs pend_layout(const cdg_pendulum_config& c, int64_t B, int64_t BL, i
     // two buffers of bf16 (hi, lo) planes [rows][ld16] for the activations / gradients that feed the pre-split kernel
     // (gemm_ps.cu) as its A operand: a producer writes one, the next GEMM reads it (and may write the other)
     w.plane_half = pad64((B > BL ? B : BL) * plane_ld(c.hidden) / 2);     // floats per plane (2 bf16 per float)
-    w.a16 = take(B >= kSplitMinBatch && split_elems > 0 ? 2 * w.plane_half : 0);
-    w.b16 = take(B >= kSplitMinBatch && split_elems > 0 ? 2 * w.plane_half : 0);
+    const int64_t pl = B >= kSplitMinBatch && split_elems > 0 ? 2 * w.plane_half : 0;
+    for (int k = 0; k < CDG_MAX_DEC; ++k) { w.pl_a1[k] = k < c.n_dec ? take(pl) : 0; w.pl_a2[k] = k < c.n_dec ? take(pl) : 0; }
+    w.pl_h1 = take(pl); w.pl_h1l = take(BL > 0 ? pl : 0); w.pl_g = take(pl);
     const int64_t Bi = infomax ? B : 0;
     w.dx = take(Bi * H); w.dh1j = take(Bi * H); w.dh1m = take(Bi * H); w.dh2j = take(Bi * H); w.dh2m = take(Bi * H);
     w.dj = take(Bi); w.dm = take(Bi); w.dgj = take(Bi); w.dgm = take(Bi);
@@ -104,10 +109,16 @@ struct Ctx {
     }
     const uint16_t* pool() const { return reinterpret_cast<const uint16_t*>(W + w.wsplit); }
     int64_t ld16() const { return plane_ld(p->c.hidden); }
-    bool planes_ok() const { return split && w.a16 > 0 && p->c.hidden % 4 == 0; }
-    PlaneBuf planes(int which) const {
-        uint16_t* hi = reinterpret_cast<uint16_t*>(W + (which ? w.b16 : w.a16));
+    bool planes_ok() const { return split && w.plane_half > 0 && w.pl_g > 0 && p->c.hidden % 4 == 0; }
+    PlaneBuf planes_at(int64_t off) const {
+        uint16_t* hi = reinterpret_cast<uint16_t*>(W + off);
         return PlaneBuf{hi, hi + 2 * w.plane_half};
+    }
+    // the reconstruction gradient as planes [B][P] in the `pre` buffer (hi plane, then lo plane: the bytes of the fp32 matrix)
+    bool pre_planes = false;
+    PlaneBuf pre_pl(int64_t B) const {
+        uint16_t* hi = reinterpret_cast<uint16_t*>(W + w.pre);
+        return PlaneBuf{hi, hi + B * p->c.input_dim};
     }
 };
 
@@ -144,6 +155,10 @@ static int gemm_weights(const Ctx& c, GemmDesc& g, bool have_split) {
     return gemm_dispatch(c.mode, g, c.W + c.w.gemm_ws, c.w.gemm_ws_floats * 4, c.s);
 }
 static bool use_ps();
+static bool use_pk() {
+    static const int v = exp_switch("CDG_PK", 1);
+    return v != 0;
+}
 // the pre-split kernel on planes of A made by the producer of the activation; CDG_ERR_UNSUPPORTED = take the usual route
 static int gemm_planes_a(const Ctx& c, GemmDesc g, const PlaneBuf* in) {
     if (!in || !c.planes_ok() || !use_ps()) return CDG_ERR_UNSUPPORTED;
@@ -203,6 +218,20 @@ static int linear_fwd(const Ctx& c, const float* X, int64_t ldx, const cdg_linea
         if (r != CDG_ERR_UNSUPPORTED) return r;
     }
     return gemm_weights(c, g, sp);
+}
+// dW[rows, in] += dY^T X and db[rows] += colsum(dY) from planes that lie in memory as their producers wrote them:
+// dY's ([batch][ld_dy], first column col_dy) and X's ([batch][ld16] with the column of ones at `in`, so that column `in` of
+// the product is the bias gradient).  Contraction over the batch, both operands MN-major (gemm_pk.cu).
+static int linear_wgrad_planes(const Ctx& c, const PlaneBuf& dy, int64_t ld_dy, int64_t col_dy, const PlaneBuf& x,
+                               const cdg_linear& L, int64_t row_lo, int64_t n_rows, int64_t M, int cat) {
+    c.mark(cat);
+    GemmDesc g;
+    g.A = nullptr; g.B = nullptr; g.sa_m = g.sa_k = g.sb_n = g.sb_k = 0;
+    g.a_hi16 = dy.hi + col_dy; g.a_lo16 = dy.lo + col_dy; g.ld_a16 = ld_dy;
+    g.b_hi16 = x.hi; g.b_lo16 = x.lo; g.ld_b16 = c.ld16();
+    g.C = c.G + L.w + row_lo * L.in; g.ldc = L.in; g.M = n_rows; g.N = L.in + 1; g.K = M;
+    g.epi = EPI_NONE; g.accumulate = 1; g.extra_col = c.G + L.b + row_lo;
+    return gemm_pk(g, 1, c.s);
 }
 // dW[rows,K] += dY[M,rows]^T X[M,K];  db[rows] += colsum(dY)
 static int linear_wgrad(const Ctx& c, const float* dY, int64_t ldy, const float* X, int64_t ldx, const cdg_linear& L,
@@ -267,10 +296,10 @@ static void fill_latent(const cdg_pendulum_config& c, LatentArgs& a) {
     a.beta = c.beta; a.lambda_ = c.lambda_;
 }
 
-static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float* h2, float* ml) {
+static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float* h2, float* ml, bool labeled = false) {
     const cdg_pendulum_config& cf = c.p->c;
     const int64_t H = cf.hidden, d = cf.node;
-    const PlaneBuf p0 = c.planes(0);
+    const PlaneBuf p0 = c.planes_at(labeled ? c.w.pl_h1l : c.w.pl_h1);
     CDG_TRY(linear_fwd(c, x, cf.input_dim, cf.enc[0], 0, H, h1, H, B, true, PROF_ENC0_FWD, nullptr, &p0));
     CDG_TRY(linear_fwd(c, h1, H, cf.enc[1], 0, H, h2, H, B, true, PROF_GEMM_OTHER, &p0));
     CDG_TRY(linear_fwd(c, h2, H, cf.enc[2], 0, 2 * d, ml, 2 * d, B, false));
@@ -278,13 +307,17 @@ static int encoder_fwd(const Ctx& c, const float* x, int64_t B, float* h1, float
 }
 
 static int encoder_bwd(const Ctx& c, const float* x, int64_t B, const float* h1, const float* h2, const float* g_ml,
-                       float* g_h2, float* g_h1) {
+                       float* g_h2, float* g_h1, bool labeled = false) {
     const cdg_pendulum_config& cf = c.p->c;
     const int64_t H = cf.hidden, d = cf.node;
     CDG_TRY(linear_wgrad(c, g_ml, 2 * d, h2, H, cf.enc[2], 0, 2 * d, B));
-    const PlaneBuf p0 = c.planes(0);
+    const PlaneBuf p0 = c.planes_at(c.w.pl_g), ph1 = c.planes_at(labeled ? c.w.pl_h1l : c.w.pl_h1);
     CDG_TRY(linear_dgrad(c, g_ml, 2 * d, cf.enc[2], 0, 2 * d, g_h2, H, h2, H, B, PROF_GEMM_OTHER, nullptr, &p0));
-    CDG_TRY(linear_wgrad(c, g_h2, H, h1, H, cf.enc[1], 0, H, B));
+    // enc1 weight gradient: g_h2's planes (just written) and h1's (kept from the forward pass), as they lie in memory
+    int rw = c.planes_ok() && use_pk() && B >= kSplitMinBatch && H + 1 <= 304
+                 ? linear_wgrad_planes(c, p0, c.ld16(), 0, ph1, cf.enc[1], 0, H, B, PROF_GEMM_OTHER) : CDG_ERR_UNSUPPORTED;
+    if (rw == CDG_ERR_UNSUPPORTED) rw = linear_wgrad(c, g_h2, H, h1, H, cf.enc[1], 0, H, B);
+    CDG_TRY(rw);
     CDG_TRY(linear_dgrad(c, g_h2, H, cf.enc[1], 0, H, g_h1, H, h1, H, B, PROF_GEMM_OTHER, &p0));
     CDG_TRY(linear_wgrad(c, g_h1, H, x, cf.input_dim, cf.enc[0], 0, H, B, PROF_ENC0_WGRAD));
     return CDG_OK;
@@ -321,6 +354,21 @@ static GemmDesc dec_out_desc(const Ctx& c, int k, int64_t B, float* pre, const f
     return g;
 }
 
+// May the reconstruction gradient be produced as bf16 planes and consumed by gemm_pk (every decoder must take that route)?
+static bool recon_planes_ok(const Ctx& c, int64_t B, const float* x) {
+    const cdg_pendulum_config& cf = c.p->c;
+    if (!c.planes_ok() || !use_ps() || !use_pk() || cf.general_mask || B < kSplitMinBatch) return false;
+    const int64_t H = cf.hidden, P = cf.input_dim;
+    if (H + 1 > 304 || H % 4 != 0 || P % 8 != 0 || ((uintptr_t)x & 31) != 0) return false;
+    for (int k = 0; k < cf.n_dec; ++k) {
+        const int64_t n = cf.col_hi[k] - cf.col_lo[k];
+        if (n <= 0 || n % 32 != 0 || cf.col_lo[k] % 8 != 0) return false;
+        const int id = 3 + 3 * k + 2;
+        if (c.p->f_hi[id] < 0 || c.p->t_hi[id] < 0) return false;
+    }
+    return true;
+}
+
 // decoders: z[B,d] -> pre[B,P] (live columns only).  With x != nullptr the reconstruction head is fused.
 static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, const float* x = nullptr,
                         float* xhat = nullptr, double* acc = nullptr) {
@@ -331,7 +379,7 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
         float* a2 = c.W + c.w.a2[k];
         const float* zin; int64_t ldz;
         CDG_TRY(dec_input(c, k, z, B, &zin, &ldz));
-        const PlaneBuf p0 = c.planes(0), p1 = c.planes(1);
+        const PlaneBuf p0 = c.planes_at(c.w.pl_a1[k]), p1 = c.planes_at(c.w.pl_a2[k]);
         CDG_TRY(linear_fwd(c, zin, ldz, cf.dec[k][0], 0, H, a1, H, B, true, PROF_GEMM_OTHER, nullptr, &p0));
         CDG_TRY(linear_fwd(c, a1, H, cf.dec[k][1], 0, H, a2, H, B, true, PROF_GEMM_OTHER, &p0, x ? &p1 : nullptr));
         if (cf.col_hi[k] - cf.col_lo[k] > 0) {
@@ -345,7 +393,18 @@ static int decoders_fwd(const Ctx& c, const float* z, int64_t B, float* pre, con
                     // ones that multiplies b2 in W2's planes): TMA feeds the MMA directly, eight epilogue warps (gemm_ps.cu)
                     GemmDesc h = g;
                     if (pad8(H) > H) { h.K = H + 1; h.bias = nullptr; }
+                    if (c.pre_planes) {
+                        // the gradient d loss / d pre leaves as bf16 planes (in the `pre` buffer): what the decoder's input-
+                        // and weight-gradient GEMMs read (gemm_pk.cu)
+                        const PlaneBuf gp = c.pre_pl(B);
+                        h.C = nullptr;
+                        h.out_hi16 = gp.hi + cf.col_lo[k]; h.out_lo16 = gp.lo + cf.col_lo[k]; h.ld_out16 = cf.input_dim; h.out_ones = 0;
+                    }
                     r = gemm_planes_a(c, h, &p1);
+                    if (c.pre_planes && r == CDG_ERR_UNSUPPORTED) {
+                        set_error("internal: the planes route of the reconstruction head refused decoder %d", k);
+                        return CDG_ERR_INVALID;
+                    }
                 }
                 if (r == CDG_ERR_UNSUPPORTED) r = sp ? gemm_tc(g, 2, nullptr, 0, c.s) : CDG_ERR_UNSUPPORTED;
                 if (r == CDG_ERR_UNSUPPORTED) {
@@ -476,6 +535,22 @@ extern "C" int cdg_pendulum_profile_read(cdg_pendulum_plan* p, double* out_ms) {
     }
     pr.n = 0;
     return CDG_OK;
+}
+
+// Test / diagnostic hook: float offset of a named workspace region (0 = pre / gradient of pre, 1 + k = a1 of decoder k,
+// 5 + k = a2 of decoder k, 9 = h1, 10 = h2, 11 = ga2, 12 = planes of a2 of decoder 0); -1 for an unknown id.
+extern "C" int64_t cdg_pendulum_workspace_offset(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l, int which) {
+    if (!p || batch < 0 || batch_l < 0) return -1;
+    const PendWs w = pend_layout(p->c, batch, batch_l, p->split_elems, false);
+    if (which == 0) return w.pre;
+    if (which >= 1 && which < 1 + CDG_MAX_DEC && which - 1 < p->c.n_dec) return w.a1[which - 1];
+    if (which >= 5 && which < 5 + CDG_MAX_DEC && which - 5 < p->c.n_dec) return w.a2[which - 5];
+    if (which == 9) return w.h1;
+    if (which == 10) return w.h2;
+    if (which == 11) return w.ga2;
+    if (which == 12) return w.pl_a2[0];
+    if (which == 100) return p->last_pre_planes;
+    return -1;
 }
 
 extern "C" int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l) {
@@ -668,6 +743,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     cudaStream_t s = c.s;
     c.mark(PROF_MISC);
 
+    p->last_pre_planes = 0;
     CDG_TRY(split_weights(c, B));
     // optimizer.zero_grad() (train.py:168) + loss accumulators
     CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * cf.n_params, s));
@@ -688,7 +764,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     al.params = io->params; al.grads = io->grads; al.acc = acc;
     al.z_out = W + c.w.zal; al.g_out = W + c.w.g_align;
     if (semi) {
-        CDG_TRY(encoder_fwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.mll));
+        CDG_TRY(encoder_fwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.mll, true));
         al.batch = BL; al.ml = W + c.w.mll; al.y = io->y_l; al.ld_y = io->ld_y_l;
     } else {
         al.batch = B; al.ml = W + c.w.ml; al.y = io->y; al.ld_y = io->ld_y;
@@ -704,6 +780,8 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         c.mark(PROF_RECON);
         CDG_TRY(launch_masked_recon(sep, cf.n_dec, io->masks, io->x, io->xhat, B, Pd, acc, 1, s));
     } else if (recon_fusable(c, B, W + c.w.pre, io->x, io->xhat, acc)) {
+        c.pre_planes = recon_planes_ok(c, B, io->x);
+        p->last_pre_planes = c.pre_planes ? 1 : 0;
         CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre, io->x, io->xhat, acc));
     } else {
         CDG_TRY(decoders_fwd(c, W + c.w.z, B, W + c.w.pre));
@@ -728,16 +806,41 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         const float* a1 = W + c.w.a1[k];
         const float* a2 = W + c.w.a2[k];
         const bool dr = cf.dec_extra[k] >= 0;
-        const PlaneBuf bp0 = c.planes(0);
+        const PlaneBuf bp0 = c.planes_at(c.w.pl_g), pa1 = c.planes_at(c.w.pl_a1[k]), pa2 = c.planes_at(c.w.pl_a2[k]);
         const float* zk = dr ? W + c.w.zin[k] : W + c.w.z + p->lat_off[k];
         const int64_t ldzk = dr ? cf.factor[k] + 1 : d;
-        if (n > 0) {
+        if (n > 0 && c.pre_planes) {
+            // d loss / d pre exists only as planes [B][P] (written by the reconstruction head): both decoder-output gradients
+            // read them in place -- the weight gradient with the batch as the (outermost) contraction index, the input
+            // gradient over the decoder's live columns, cut into <= 2048-long accumulations
+            const PlaneBuf gp = c.pre_pl(B);
+            CDG_TRY(linear_wgrad_planes(c, gp, Pd, lo, pa2, cf.dec[k][2], lo, n, B, PROF_DEC2_WGRAD));
+            c.mark(PROF_DEC2_DGRAD);
+            const cdg_linear& L2 = cf.dec[k][2];
+            const int id = 3 + 3 * k + 2;
+            CDG_CHECK_CUDA(cudaMemsetAsync(ga2, 0, sizeof(float) * B * H, s));
+            GemmDesc g;
+            g.A = nullptr; g.B = nullptr; g.sa_m = g.sa_k = g.sb_n = g.sb_k = 0;
+            g.a_hi16 = gp.hi + lo; g.a_lo16 = gp.lo + lo; g.ld_a16 = Pd;
+            g.b_hi16 = c.pool() + p->t_hi[id] + lo; g.b_lo16 = c.pool() + p->t_lo[id] + lo; g.ld_b16 = pad8(L2.out);
+            g.C = ga2; g.ldc = H; g.M = B; g.N = H; g.K = n; g.accumulate = 1;
+            CDG_TRY(gemm_pk(g, 0, s));
+            tl_planes_done = false;
+            CDG_TRY(launch_bias_act(ga2, H, B, H, nullptr, EPI_MUL_DACT, CDG_ACT_ELU, a2, H, s, bp0.hi, bp0.lo, c.ld16(), 0));
+            if (!tl_planes_done) CDG_TRY(launch_split_rows(ga2, B, H, H, bp0.hi, bp0.lo, c.ld16(), nullptr, 0, s));
+        } else if (n > 0) {
             CDG_TRY(linear_wgrad(c, g_pre + lo, Pd, a2, H, cf.dec[k][2], lo, n, B, PROF_DEC2_WGRAD));
             CDG_TRY(linear_dgrad(c, g_pre + lo, Pd, cf.dec[k][2], lo, n, ga2, H, a2, H, B, PROF_DEC2_DGRAD, nullptr, &bp0));
         } else {
             CDG_CHECK_CUDA(cudaMemsetAsync(ga2, 0, sizeof(float) * B * H, s));
         }
-        CDG_TRY(linear_wgrad(c, ga2, H, a1, H, cf.dec[k][1], 0, H, B));
+        {
+            // dec1 weight gradient: ga2's planes (just written) and a1's (kept from the forward pass)
+            int rw = n > 0 && c.planes_ok() && use_pk() && B >= kSplitMinBatch && H + 1 <= 304
+                         ? linear_wgrad_planes(c, bp0, c.ld16(), 0, pa1, cf.dec[k][1], 0, H, B, PROF_GEMM_OTHER) : CDG_ERR_UNSUPPORTED;
+            if (rw == CDG_ERR_UNSUPPORTED) rw = linear_wgrad(c, ga2, H, a1, H, cf.dec[k][1], 0, H, B);
+            CDG_TRY(rw);
+        }
         CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B, PROF_GEMM_OTHER, n > 0 ? &bp0 : nullptr));
         CDG_TRY(linear_wgrad(c, ga1, H, zk, ldzk, cf.dec[k][0], 0, H, B));
         if (!dr) {
@@ -757,7 +860,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
     CDG_TRY(launch_latent_bwd(lb, s));
     CDG_TRY(encoder_bwd(c, io->x, B, W + c.w.h1, W + c.w.h2, W + c.w.g_ml, W + c.w.g_h2, W + c.w.g_h1));
     if (semi)
-        CDG_TRY(encoder_bwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.g_align, W + c.w.g_h2l, W + c.w.g_h1l));
+        CDG_TRY(encoder_bwd(c, io->x_l, BL, W + c.w.h1l, W + c.w.h2l, W + c.w.g_align, W + c.w.g_h2l, W + c.w.g_h1l, true));
 
     c.mark(PROF_MISC);
     if (infomax) {

@@ -110,6 +110,11 @@ int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_plan** out)
 void cdg_pendulum_destroy(cdg_pendulum_plan* p);
 /* Workspace the caller must provide for a step on `batch` (+ `batch_l` labeled) samples. */
 int64_t cdg_pendulum_workspace_bytes(const cdg_pendulum_plan* p, int64_t batch, int64_t batch_l);
+/* Test / diagnostic hook: offset (in floats) of a named region of the step's workspace for the given batch sizes:
+ * 0 = pre (after the step: d loss / d pre), 1 + k = a1 of decoder k, 5 + k = a2 of decoder k, 9 = h1, 10 = h2, 11 = ga2,
+ * 12 = bf16 planes of a2 of decoder 0; 100 = (not an offset) 1 when the last cdg_pendulum_forward_backward left d loss / d pre
+ * as bf16 planes [batch][P] (hi plane, then lo plane, in the bytes of `pre`) instead of fp32; -1 for an unknown id. */
+int64_t cdg_pendulum_workspace_offset(const cdg_pendulum_plan* plan, int64_t batch, int64_t batch_l, int which);
 /* ... for a step that also runs the InfoMax discriminator (io->d_params != NULL). */
 int64_t cdg_pendulum_workspace_bytes_infomax(const cdg_pendulum_plan* p, int64_t batch);
 
