@@ -4,6 +4,8 @@ arithmetic runs in libcdgvae_sm100.so (one fused kernel per step, csrc/tabular.c
 
     CDGVAE(B, mask, config, device)     tabular/modules/model.py:234-358
     TVAE(B, mask, config, device)       tabular/modules/model.py:360-460
+    VAE(B, config, device)              tabular/modules/model.py:103-222   (baseline: one decoder over all latents)
+    Discriminator(config, device)       tabular/modules/model.py:224-232   (InfoMax critic: parameter holder, see train_InfoMax)
 """
 import ctypes as C
 
@@ -82,7 +84,7 @@ class _TabularBase(ArenaModule):
         for k in range(K):
             c.factor[k], c.out_dim[k] = cfg["factor"][k], int(self.mask[k])
             for j, idx in enumerate(self.DEC_IDX):
-                c.dec[k][j] = self._lin(f"decoder.{k}.{idx}")
+                c.dec[k][j] = self._lin(self._dec_name(k, idx))
         c.scm, c.flow_num = _lib.SCM[cfg["scm"]], int(cfg.get("flow_num", 1))
         if cfg["scm"] == "nonlinear" and c.flow_num > _lib.MAX_FLOW:
             raise ValueError(f"flow_num > {_lib.MAX_FLOW} is not supported")
@@ -116,6 +118,9 @@ class _TabularBase(ArenaModule):
         _lib.check(_lib.lib().cdg_tabular_create(C.byref(c), C.byref(plan)))
         self._plan, self._plan_key = plan, key
         return plan
+
+    def _dec_name(self, k, idx):
+        return f"decoder.{k}.{idx}"
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.arena_device).cuda_stream)
@@ -236,6 +241,78 @@ class CDGVAE(_TabularBase):
         n_used = len(self.mask)
         return [n for n, _ in self.named_parameters()
                 if not (n.startswith("decoder.") and int(n.split(".")[1]) >= n_used)]
+
+
+class VAE(_TabularBase):
+    """tabular/modules/model.py:103-222: the CDG-VAE encoder and causal layer with ONE decoder over all latents.  The fused
+    step kernel takes it as a single-factor model (factor = [node], out_dim = [D']); layer widths other than the CDG-VAE's go
+    through the generic per-row kernel (csrc/tabular.cu)."""
+    KIND = "vae"
+
+    def __init__(self, B, config, device):
+        super().__init__()
+        d, D = config["node"], config["input_dim"]
+        ds = config["dataset"]
+        self.config = dict(config, factor=[d])
+        self.device = device
+        cov = ds == "covtype"
+        out = D - 1 + 7 if cov else D
+        self.mask = [out]
+        if cov:                                                          # model.py:111-119
+            self.encoder = nn.Sequential(nn.Linear(D, 4), nn.ELU(), nn.Linear(4, 4), nn.ELU(), nn.Linear(4, 4), nn.ELU(),
+                                         nn.Linear(4, d * 2)).to(device)
+        else:                                                            # model.py:121-125
+            self.encoder = nn.Sequential(nn.Linear(D, 4), nn.ELU(), nn.Linear(4, d * 2)).to(device)
+        self._causal_init(B, config, device)
+        if ds == "loan":                                                 # model.py:144-148
+            self.decoder = nn.Sequential(nn.Linear(d, 4), nn.ELU(), nn.Linear(4, out)).to(device)
+        elif ds in ("adult", "covtype"):                                 # model.py:149-169
+            self.decoder = nn.Sequential(nn.Linear(d, 8), nn.ELU(), nn.Linear(8, 8), nn.ELU(), nn.Linear(8, 16), nn.ELU(),
+                                         nn.Linear(16, out)).to(device)
+        else:
+            raise ValueError("Not supported dataset!")                   # model.py:171
+        self.ENC_IDX = (0, 2, 4, 6) if cov else (0, 2)
+        self.DEC_IDX = (0, 2) if ds == "loan" else (0, 2, 4, 6)
+        self.ACT = 0
+        self.noise_fn = None
+        self._plan = None
+        self._build_arena()
+
+    def _dec_name(self, k, idx):
+        return f"decoder.{idx}"
+
+    def _kind(self):
+        return _lib.TAB_KIND[self.config["dataset"]]
+
+    def _default_ft(self):
+        return {"loan": (1, 2, 3, 4, 0), "adult": (2, 3, 0, 1, 4)}.get(self.config["dataset"])
+
+    def live_param_names(self):
+        return [n for n, _ in self.named_parameters()]
+
+    def decode(self, input):
+        xhat = self.decoder(torch.cat(list(input), dim=1))
+        return [xhat], xhat
+
+    def forward(self, input, deterministic=False, log_determinant=False):
+        """8-tuple, no xhat_separated (model.py:222)."""
+        xhat, lat = self._run_forward(input, deterministic=deterministic)
+        mean, logvar, eps, orig, z, zal = self._unpack(lat)
+        return (mean, logvar, eps, orig, self._cols(z), self._logdet(log_determinant, orig), self._cols(zal), xhat)
+
+
+class Discriminator(nn.Module):
+    """tabular/modules/model.py:224-232: the InfoMax critic on (x, epsilon).  A plain parameter holder with the reference's
+    module tree (`net.0`, `net.2`), so checkpoints load; its training step (tabular train_InfoMax) is not built -- see there."""
+
+    def __init__(self, config, device="cpu"):
+        super().__init__()
+        self.config = config
+        self.net = nn.Sequential(nn.Linear(config["input_dim"] + config["node"], 4), nn.ELU(), nn.Linear(4, 1)).to(device)
+
+    def forward(self, x, z):
+        x = x.view(-1, self.config["input_dim"])
+        return self.net(torch.cat((x, z), dim=1))
 
 
 class TVAE(_TabularBase):

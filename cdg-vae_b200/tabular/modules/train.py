@@ -1,7 +1,9 @@
 """Drop-in for the reference's tabular/modules/train.py.
 
+    train_VAE(dataset, dataloader, model, config, optimizer, device) -> logs             train.py:10-82
     train_CDGVAE(dataset, dataloader, model, config, optimizer, device) -> logs          train.py:173-243
     train_TVAE(output_info_list, dataset, dataloader, model, config, optimizer, device) -> logs   :245-320
+    train_InfoMax(...)                                                                    train.py:84-171  (not built: raises)
 
 One fused kernel per step (forward + losses + backward), one Adam kernel; the log rows stay on the
 device until the loader is exhausted.
@@ -76,6 +78,21 @@ def train_CDGVAE(dataset, dataloader, model, config, optimizer, device):
         _graph_step(model, x_batch, y_batch, noise, rows[n], ft, None, None)
         n += 1
     return _finish(model, config, n)
+
+
+def train_VAE(dataset, dataloader, model, config, optimizer, device):
+    """tabular/modules/train.py:10-82: the loss of train_CDGVAE on the single-decoder baseline (same reconstruction terms per
+    dataset, KL, alignment on all of y, beta / lambda weights), so the same step kernel runs it."""
+    return train_CDGVAE(dataset, dataloader, model, config, optimizer, device)
+
+
+def train_InfoMax(dataset, dataloader, model, discriminator, config, optimizer, optimizer_D, device):
+    """tabular/modules/train.py:84-171.  Not built: the mutual-information term couples every row with a permuted row of
+    the same batch (permute_dims, :86-90), which the one-row-per-thread step kernel cannot express in its single pass.  The
+    pendulum InfoMax baseline (modules/train.py::train_InfoMax) is built; this one fails loudly instead of silently running
+    the reference's eager path."""
+    raise NotImplementedError("tabular train_InfoMax is not provided by cdgvae_b200 (DESIGN.md section 7); "
+                              "use the reference implementation for this baseline")
 
 
 def train_TVAE(output_info_list, dataset, dataloader, model, config, optimizer, device):

@@ -114,6 +114,21 @@ def tabular_spec(config: dict, mask: Sequence[int], flatten_topology: Optional[S
     )
 
 
+def tabular_vae_spec(config: dict, flatten_topology: Optional[Sequence[int]]) -> Spec:
+    """tabular/modules/model.py:103-172 (VAE.__init__): the CDG-VAE encoder, ONE decoder over all latents
+    (loan node-4-D, adult / covtype node-8-8-16-D')."""
+    ds = config["dataset"]
+    cov = ds == "covtype"
+    out = config["input_dim"] - 1 + 7 if cov else config["input_dim"]
+    return Spec(
+        family="tabular", node=config["node"], factor=[config["node"]], scm=config["scm"], flow_num=config.get("flow_num", 1),
+        input_dim=config["input_dim"], enc_idx=[0, 2, 4, 6] if cov else [0, 2], dec_idx=[0, 2] if ds == "loan" else [0, 2, 4, 6],
+        act="elu", n_dec_used=1, dataset=ds, mask=[out],
+        flatten_topology=None if flatten_topology is None else list(flatten_topology),
+        beta=config["beta"], lam=config["lambda"], lr=config.get("lr", 1e-2), single_decoder=True,
+    )
+
+
 def tvae_spec(config: dict, mask: Sequence[int], output_info_list) -> Spec:
     """tabular/modules/model.py:360-407 (TVAE.__init__); tabular/main_tvae.py:196-200."""
     assert sum(config["factor"]) == config["node"]
@@ -213,6 +228,8 @@ def decode(params, spec: Spec, latent: List[Tensor]) -> Tuple[List[Tensor], Tens
         z = torch.split(zc, spec.factor, dim=-1)
     if spec.single_decoder:                                     # VAE.forward, modules/model.py:178-180
         o = mlp(params, "decoder", spec.dec_idx, z[0], spec.act)
+        if spec.family != "pendulum":                           # tabular VAE: xhat = decoder(cat(latent)), tabular/modules/model.py:222
+            return [o], o
         return [o], torch.tanh(o).view(-1, spec.image_size, spec.image_size, 3)
     sep = [mlp(params, f"decoder.{k}", spec.dec_idx, z[k], spec.act) for k in range(spec.n_dec_used)]
     if spec.family == "pendulum":
@@ -438,6 +455,10 @@ def init_params(spec: Spec, seed: int = 1, hidden: int = 300) -> Dict[str, Tenso
     if fam == "pendulum":
         enc = [spec.input_dim, hidden, hidden, 2 * d]
         decs = [[k + (1 if spec.dr else 0), hidden, hidden, spec.input_dim] for k in spec.factor]
+        extra = []
+    elif fam == "tabular" and spec.single_decoder:                      # tabular VAE, model.py:110-172
+        enc = [spec.input_dim, 4, 4, 4, 2 * d] if spec.dataset == "covtype" else [spec.input_dim, 4, 2 * d]
+        decs = [[d, 4, spec.mask[0]]] if spec.dataset == "loan" else [[d, 8, 8, 16, spec.mask[0]]]
         extra = []
     elif fam == "tabular":
         if spec.dataset == "covtype":

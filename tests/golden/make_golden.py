@@ -321,6 +321,38 @@ def tabular_case(dataset, batch, nsteps):
     return case
 
 
+def tabular_vae_case(dataset, batch, nsteps):
+    """The single-decoder baseline of the tabular tree: tabular/modules/model.py::VAE + tabular/modules/train.py::train_VAE."""
+    config = dict(dataset=dataset, scm="linear", flow_num=1, inverse_loop=100, batch_size=batch, lr=0.01,
+                  beta=0.01, cuda=False, seed=1)
+    config["lambda"] = 10.0
+    if dataset in ("loan", "adult"):
+        config.update(node=3, input_dim=5)
+        ft = [1, 2, 3, 4, 0] if dataset == "loan" else [2, 3, 0, 1, 4]
+    else:
+        config.update(node=6, input_dim=8)
+        ft = None
+    Bm = orc.tabular_B(dataset)
+    torch.manual_seed(config["seed"])
+    model = tm.VAE(Bm, config, "cpu")
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=config["lr"])
+    DS = namedtuple("DS", ["flatten_topology"])
+    ds = DS(ft)
+    batches = []
+    for s in range(nsteps):
+        x, y, noise = orc.synth_tabular(dataset, batch, seed=1234 + s, noise_seed=4321 + s)
+        batches.append(dict(x=x, y=y, noise=noise))
+    spec = orc.tabular_vae_spec(config, ft)
+
+    def ref_step(b):
+        return tt.train_VAE(ds, [(b["x"], b["y"])], model, config, opt, "cpu")
+    case = run_case(f"tabular_vae_{dataset}", "tabular_vae", config, model, spec, Bm, batches, ref_step)
+    case["mask"] = spec.mask
+    case["flatten_topology"] = ft
+    return case
+
+
 def tvae_case(kind, batch, nsteps):
     oil, mask, d, Bm, D = orc.tvae_shape(kind)
     sr = [0.01, 0.1] if kind == "loan" else [0.005, 0.01]
@@ -360,6 +392,12 @@ def main():
         with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
             json.dump(c, f)
         print("wrote", c["name"])
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "tabular_vae":  # round 2: the tabular tree's baseline
+        for c in (tabular_vae_case(d, 256, 4) for d in ("loan", "adult", "covtype")):
+            with open(os.path.join(OUT, c["name"] + ".json"), "w") as f:
+                json.dump(c, f)
+            print("wrote", c["name"])
         return
     if len(sys.argv) > 1 and sys.argv[1] == "vae":         # added after the first batch of goldens
         cases = [vae_case("vae_small_linear", "linear", 8, 16, 4), vae_case("vae_small_nonlinear", "nonlinear", 8, 16, 4)]

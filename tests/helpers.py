@@ -59,6 +59,12 @@ def case_setup(c):
         for s in range(nsteps):
             x, y, noise = orc.synth_pendulum(cfg["batch_size"], cfg["image_size"], 4, 1234 + s, 4321 + s)
             batches.append(dict(x=x, y=y, noise=noise))
+    elif fam == "tabular_vae":
+        spec = orc.tabular_vae_spec(cfg, c["flatten_topology"])
+        Bm = orc.tabular_B(cfg["dataset"])
+        for s in range(nsteps):
+            x, y, noise = orc.synth_tabular(cfg["dataset"], cfg["batch_size"], 1234 + s, 4321 + s)
+            batches.append(dict(x=x, y=y, noise=noise))
     elif fam == "tabular":
         spec = orc.tabular_spec(cfg, c["mask"], c["flatten_topology"])
         Bm = orc.tabular_B(cfg["dataset"])
@@ -77,4 +83,5 @@ def case_setup(c):
 
 ALL_CASES = ["pendulum_small_linear", "pendulum_small_nonlinear", "pendulum_small_semi",
              "pendulum_full_linear", "pendulum_full_semi", "tabular_loan", "tabular_adult",
-             "tabular_covtype", "tvae_loan", "tvae_covtype", "vae_small_linear", "vae_small_nonlinear", "dr_small_linear"]
+             "tabular_covtype", "tvae_loan", "tvae_covtype", "vae_small_linear", "vae_small_nonlinear", "dr_small_linear",
+             "tabular_vae_loan", "tabular_vae_adult", "tabular_vae_covtype"]
