@@ -22,6 +22,11 @@ struct cdg_pendulum_plan {
     int64_t f_hi[kLayers], f_lo[kLayers], t_hi[kLayers], t_lo[kLayers];   // forward [out][pad8(in)], transposed [in][pad8(out)]
     int64_t split_elems = 0;
     int last_pre_planes = 0;     // the last forward_backward left d loss / d pre as bf16 planes (diagnostic hook id 100)
+    // data parallel: "the gradients of bucket b are complete" events, recorded on the caller's stream inside the backward pass
+    // (bucket k < n_dec: decoder k, in the order the backward finishes them; bucket n_dec: encoder + flows = everything)
+    bool ready_enabled = false;
+    cudaEvent_t ready[CDG_MAX_DEC + 1] = {};
+    int ready_created = 0;
 };
 
 namespace cdg {
@@ -510,8 +515,32 @@ extern "C" int cdg_pendulum_create(const cdg_pendulum_config* cfg, cdg_pendulum_
     return CDG_OK;
 }
 
+extern "C" int cdg_pendulum_ready_events_enable(cdg_pendulum_plan* p, int enable) {
+    CDG_REQUIRE(p, "null plan");
+    if (enable && p->ready_created == 0) {
+        for (int i = 0; i <= p->c.n_dec; ++i) {
+            CDG_CHECK_CUDA(cudaEventCreateWithFlags(&p->ready[i], cudaEventDisableTiming));
+            p->ready_created = i + 1;
+        }
+    }
+    p->ready_enabled = enable != 0;
+    return CDG_OK;
+}
+extern "C" int cdg_pendulum_ready_event(cdg_pendulum_plan* p, int bucket, void** event_out) {
+    CDG_REQUIRE(p && event_out, "null argument");
+    CDG_REQUIRE(p->ready_enabled && bucket >= 0 && bucket < p->ready_created, "ready events are not enabled / bucket out of range");
+    *event_out = (void*)p->ready[bucket];
+    return CDG_OK;
+}
+extern "C" int cdg_stream_wait_event(void* stream, void* event) {
+    CDG_REQUIRE(event, "null event");
+    CDG_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return CDG_OK;
+}
+
 extern "C" void cdg_pendulum_destroy(cdg_pendulum_plan* p) {
     if (!p) return;
+    for (int i = 0; i < p->ready_created; ++i) cudaEventDestroy(p->ready[i]);
     for (int i = 0; i < p->prof.created; ++i) cudaEventDestroy(p->prof.ev[i]);
     delete p;
 }
@@ -850,6 +879,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
             CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, gzin, ldzk, nullptr, 0, B));
             CDG_TRY(launch_scatter_add_cols(gzin, g_z, (int)d, cf.factor[k], p->lat_off[k], cf.dec_extra[k], B, s));
         }
+        if (p->ready_enabled) CDG_CHECK_CUDA(cudaEventRecord(p->ready[k], s));       // decoder k's gradients are final
     }
     LatentArgs lb;
     fill_latent(cf, lb);
@@ -870,6 +900,7 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
         CDG_TRY(launch_finalize_logs(acc, io->logs, (int)d, (float)B, (float)B, (float)(semi ? BL : B), cf.beta, cf.lambda_, s));
     }
     c.mark(-1);
+    if (p->ready_enabled) CDG_CHECK_CUDA(cudaEventRecord(p->ready[cf.n_dec], s));    // encoder, flows (and discriminator): all final
     return CDG_OK;
 }
 

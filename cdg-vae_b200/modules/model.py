@@ -198,6 +198,51 @@ class CDGVAE(ArenaModule):
                 segs.append((o, shapes[n]))
         return self._merge(segs)
 
+    # -- data parallel: all-reduce overlapped with the backward pass ------------------------------------
+    def exchange_gradients(self):
+        """All-reduce(sum) of the live gradient ranges, started bucket by bucket WHILE the backward pass is still running:
+        the library records an event when a decoder's gradients are final (the decoders finish in index order, the encoder
+        last), a communication stream waits for that event and issues the bucket's NCCL all-reduce, and the compute stream
+        only waits for the collectives in front of the Adam kernel.  (The host is a whole step ahead of the device, so all of
+        this is enqueued long before the first event fires.)  Returns the 1/world gradient scale."""
+        from .. import dist as _dist
+        import torch.distributed as tdist
+        w = _dist.world()
+        if w == 1:
+            return 1.0
+        plan = self._get_plan()
+        lib = _lib.lib()
+        dev = self.arena_device
+        if getattr(self, "_ready_plan", None) is not plan:
+            _lib.check(lib.cdg_pendulum_ready_events_enable(plan, 1))
+            self._ready_plan = plan
+            self._events_live = False            # the step that was just enqueued did not record them yet
+        if not getattr(self, "_events_live", False):
+            self._events_live = True
+            return _dist.allreduce_arena(self._grads, self.reduce_ranges())
+        side = self.__dict__.get("_comm_stream")
+        if side is None:
+            side = self.__dict__["_comm_stream"] = torch.cuda.Stream(device=dev)
+        K = len(self.decoder) if isinstance(self.decoder, torch.nn.ModuleList) else 1
+        # live ranges per bucket: decoder k's parameters are one contiguous block of the arena
+        first = [self._offsets[n] for n in (f"decoder.{k}.0.weight" for k in range(K))] if isinstance(self.decoder, torch.nn.ModuleList) \
+            else [self._offsets["decoder.0.weight"]]
+        buckets = [[] for _ in range(K + 1)]
+        for o, n in self.reduce_ranges():
+            k = max([i for i in range(K) if o >= first[i]], default=K)
+            buckets[k].append((o, n))
+        handles = []
+        for b in range(K + 1):
+            ev = C.c_void_p()
+            _lib.check(lib.cdg_pendulum_ready_event(plan, b, C.byref(ev)))
+            _lib.check(lib.cdg_stream_wait_event(C.c_void_p(side.cuda_stream), ev))
+            with torch.cuda.stream(side):
+                for o, n in buckets[b]:
+                    handles.append(tdist.all_reduce(self._grads[o:o + n], op=tdist.ReduceOp.SUM, async_op=True))
+        for h in handles:
+            h.wait()                              # the compute stream waits for the collectives (in front of Adam)
+        return 1.0 / w
+
     def profile(self, enable=True):
         """Per-category device timing of the step (cudaEvents inside the library)."""
         _lib.check(_lib.lib().cdg_pendulum_profile_enable(self._get_plan(), int(enable)))

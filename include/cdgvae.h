@@ -150,6 +150,14 @@ typedef struct {
 /* zero_grad + forward + losses + backward of one batch: train.py:168-202 (:235-278 when x_l != NULL).
  * Gradients land in io->grads; no optimizer update. */
 int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pendulum_io* io, void* stream);
+/* Data parallel: when enabled, cdg_pendulum_forward_backward records an event on its stream as soon as the gradients of a
+ * bucket are final -- bucket k < n_dec: decoder k (the backward pass finishes the decoders in index order), bucket n_dec:
+ * everything (encoder and flows come last).  The caller makes its communication stream wait for the event
+ * (cdg_stream_wait_event) and starts that bucket's all-reduce while the rest of the backward pass is still running.
+ * The events belong to the plan (created on first enable, destroyed with it). */
+int cdg_pendulum_ready_events_enable(cdg_pendulum_plan* p, int enable);
+int cdg_pendulum_ready_event(cdg_pendulum_plan* p, int bucket, void** event_out);
+int cdg_stream_wait_event(void* stream, void* event);
 
 /* Forward only (model.py:290-304), for model.forward()/encode()/decode() outside the train loop.
  * Any output pointer may be NULL.  deterministic != 0 uses eps = mean (model.py:273-274). */
