@@ -260,18 +260,25 @@ class ArenaModule(nn.Module):
             graph = torch.cuda.CUDAGraph()
             count0, tensors0 = self._step_count, [float(t) for t in self._step_tensors[:1]]
             n0 = _lib.lib().cdg_launch_count()
+            def _undo():
+                # capturing does not execute: undo the host-side bookkeeping the body did (launch count, step counters)
+                nodes = int(_lib.lib().cdg_launch_count() - n0)
+                _lib.lib().cdg_launch_count_add(-nodes)
+                undo = self._step_count - count0
+                self._step_count = count0
+                if undo:
+                    torch._foreach_add_(self._step_tensors, -float(undo))
+                return nodes
             try:
                 with torch.cuda.graph(graph):
                     outs = body(static)
+            except BaseException:
+                _undo()
+                cache.pop(key, None)
+                raise
             finally:
                 self._use_dev_step = False
-            nodes = int(_lib.lib().cdg_launch_count() - n0)    # kernels of this library inside the graph
-            _lib.lib().cdg_launch_count_add(-nodes)            # capturing does not execute them
-            # capturing does not execute: undo the host-side step bookkeeping the body did
-            undo = self._step_count - count0
-            self._step_count = count0
-            if undo:
-                torch._foreach_add_(self._step_tensors, -float(undo))
+            nodes = _undo()                                    # kernels of this library inside the graph
             ent = cache[key] = (graph, static, outs, nodes)
         graph, static, outs, nodes = ent
         for k, v in inputs.items():

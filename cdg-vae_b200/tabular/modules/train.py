@@ -34,7 +34,11 @@ def _graph_step(model, x_batch, y_batch, noise, row, ft, oil, clamp):
     import torch
     from ...engine import _f32c
     rows = x_batch.shape[0]
-    if rows > model.GRAPH_MAX_ROWS or _dist.world() > 1 or not getattr(model, "use_graphs", True):
+    # data parallel: the three-launch step plus a 12 KB all-reduce is pure host latency when run eagerly (measured at 2 GPUs,
+    # 2^20 rows: 0.29 ms per step against 0.17 on one GPU), so the NCCL call is captured into the step's graph as well
+    # (`dp_graphs`, on by default; a capture failure falls back to the eager path for good)
+    dp = _dist.world() > 1
+    if rows > model.GRAPH_MAX_ROWS or (dp and not getattr(model, "dp_graphs", True)) or not getattr(model, "use_graphs", True):
         model.forward_backward(x_batch, y_batch, noise, row, flatten_topology=ft, output_info_list=oil)
         model.adam_step(grad_scale=model.exchange_gradients(), clamp=clamp)
         return
@@ -49,10 +53,22 @@ def _graph_step(model, x_batch, y_batch, noise, row, ft, oil, clamp):
     def body(t):
         out_row = torch.empty_like(row)
         model.forward_backward(t["x"], t["y"], t["noise"], out_row, flatten_topology=ft, output_info_list=oil)
-        model.adam_step(grad_scale=1.0, clamp=clamp)
+        model.adam_step(grad_scale=model.exchange_gradients() if dp else 1.0, clamp=clamp)
         return {"row": out_row}
 
-    outs = model.graphed_step(key, ins, body)
+    if dp:
+        try:
+            outs = model.graphed_step(key + ("dp", _dist.world()), ins, body)
+        except RuntimeError as e:                  # NCCL inside a capture is not available here: eager from now on
+            import warnings
+            warnings.warn(f"data-parallel CUDA-graph capture failed ({e}); falling back to eager steps")
+            model.dp_graphs = False
+            model.drop_graphs()
+            model.forward_backward(x_batch, y_batch, noise, row, flatten_topology=ft, output_info_list=oil)
+            model.adam_step(grad_scale=model.exchange_gradients(), clamp=clamp)
+            return
+    else:
+        outs = model.graphed_step(key, ins, body)
     row.copy_(outs["row"], non_blocking=True)
 
 
