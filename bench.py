@@ -415,7 +415,8 @@ def main():
                        "image": "64x64x3", "gemm_mode": args.gemm, "parallelism": f"dp{world}",
                        "l2_policy": f"inputs larger than L2: x is {B * 49152 / 1e9:.1f} GB per step",
                        "samples_counted": "unlabeled samples (the labeled quarter-batch rides along)"},
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel family (every Linear fwd / dgrad / wgrad launch of the step)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM family: gemm_ps_kernel / gemm_pk_kernel (operands as bf16 planes) and gemm_tc_kernel "
+                                                      "(the two encoder-input GEMMs) -- every Linear fwd / dgrad / wgrad launch of the step",
                          "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                          "traffic": None if tr is None else tr["bytes"],
                          "traffic_launch": None if tr is None else tr["launch"],
