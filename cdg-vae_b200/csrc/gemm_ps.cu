@@ -41,10 +41,15 @@ constexpr int THREADS = 32 * (2 + NE);
 // every epilogue warp waiting on it (72 % long-scoreboard stalls) at 33 k cycles per tile.  Paid for with one ring stage.
 constexpr int EPI_NIN = 2, EPI_NOUT = 1, EPI_CHUNK_BYTES = 32 * 128;
 
-template <int BN, bool STG = false>
+// Staged OUTPUT (the other epilogues, STG with EPI != EPI_RECON): the fp32 result chunk (4 KB) and the two bf16 plane chunks
+// (2 KB each) of a warp leave through shared memory as bulk stores; the side operand of EPI_MUL_DACT is still read per row.
+constexpr int SO_BYTES = EPI_CHUNK_BYTES + EPI_CHUNK_BYTES;
+
+template <int BN, bool STG = false, bool RECON = true>
 struct Cfg {
-    static constexpr int STAGES = STG ? 2 : 3;
-    static constexpr int EPI_BYTES = STG ? NE * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES : 0;
+    static constexpr bool SO = STG && !RECON;
+    static constexpr int STAGES = (STG && RECON) ? 2 : 3;
+    static constexpr int EPI_BYTES = SO ? NE * SO_BYTES : STG ? NE * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES : 0;
     static constexpr int A_BYTES = BM * BK * 2;               // one plane of this CTA's A rows
     static constexpr int B_ROWS = BN / 2;                     // this CTA's half of the tile's B rows
     static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -55,7 +60,7 @@ struct Cfg {
     static constexpr int BIAS_BYTES = 2 * BN * 4;             // per-tile bias values, two tiles in flight
     static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + BIAS_BYTES;   // (1024-aligned dynamic base)
     static_assert(BN % 32 == 0 && BN <= 256, "one MMA per tile: N <= 256, whole 16-column chunks per epilogue half");
-    static_assert(!STG || BN % 64 == 0, "staged epilogue: whole 32-column chunks per epilogue half");
+    static_assert(!(STG && RECON) || BN % 64 == 0, "staged reconstruction head: whole 32-column chunks per epilogue half");
     static_assert(SMEM <= 232448, "tile does not fit shared memory");
 };
 
@@ -136,8 +141,8 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC,
                const __grid_constant__ CUtensorMap tmC2, const Params p) {
-    static_assert(!PL || STG, "planes of the gradient: staged reconstruction head only");
-    using C_ = Cfg<BN, STG>;
+    static_assert(!PL || (STG && EPI == EPI_RECON), "planes of the gradient: staged reconstruction head only");
+    using C_ = Cfg<BN, STG, EPI == EPI_RECON>;
     constexpr int NACC = C_::NACC;
     constexpr int STAGES = C_::STAGES;
     const uint32_t rank = cluster_ctarank();
@@ -257,8 +262,137 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // ================= epilogue (both CTAs): warp -> (TMEM lane quarter, column half) =================
         const int ew = warp - 2, q = warp & 3, half = ew >> 2;
         constexpr int HC = BN / 2;                     // columns per warp
-        if constexpr (STG) {
-            static_assert(EPI == EPI_RECON, "the staged epilogue is the reconstruction head's");
+        if constexpr (STG && EPI != EPI_RECON) {
+            // ---- staged output: 32-column chunks through shared memory, bulk stores (tmX: fp32 result, tmC / tmC2: planes) ----
+            constexpr int NCH32 = (BN + 31) / 32;                    // chunks per tile; the first half of them -> warp half 0
+            constexpr int C0 = (NCH32 + 1) / 2;
+            const int c_lo = half == 0 ? 0 : C0, c_hi = half == 0 ? C0 : NCH32;
+            uint8_t* obuf = epi_base + (size_t)ew * SO_BYTES;        // [fp32 chunk 4 KB | hi 2 KB | lo 2 KB]
+            const int et = threadIdx.x - 64;
+            const bool has_bias = p.bias != nullptr;
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC2)) : "memory");
+            }
+            uint32_t j = 0;
+            for (int64_t w = w_first; w < p.work_total; w += w_step, ++j) {
+                int m_pair, n_blk;
+                decode(w, m_pair, n_blk);
+                const uint32_t buf = j % NACC;
+                const int row0 = (2 * m_pair + (int)rank) * BM + q * 32;
+                const int64_t m = (int64_t)row0 + lane;
+                const bool row_ok = m < p.M;
+                float* bs = bias_s + (j & 1u) * BN;
+                if ((EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) && has_bias) {
+                    for (int c = et; c < BN; c += 32 * NE) {
+                        const int64_t n = (int64_t)n_blk * BN + c;
+                        bs[c] = n < p.N ? p.bias[n] : 0.f;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
+                }
+                const uint32_t bsa = smem_u32(bs);
+                const float* side = EPI == EPI_MUL_DACT ? p.aux + m * p.ld_aux + (int64_t)n_blk * BN : nullptr;
+                float sd[32];
+                auto fetch = [&](int c) {                            // side operand of chunk c: 16-byte pieces, groups past N skipped
+                    if (EPI != EPI_MUL_DACT || c >= c_hi || !row_ok) return;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if ((int64_t)n_blk * BN + 32 * c + 4 * g + 4 <= p.N) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(side + 32 * c + 4 * g));
+                            sd[4 * g] = t.x; sd[4 * g + 1] = t.y; sd[4 * g + 2] = t.z; sd[4 * g + 3] = t.w;
+                        }
+                };
+                fetch(c_lo);
+                mbar_wait(smem_u32(&acc_full[buf]), (j / NACC) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t vraw[32];
+                    tmem_ld16_issue(trow + (uint32_t)(c * 32), vraw);
+                    if (c * 32 + 16 < BN) tmem_ld16_issue(trow + (uint32_t)(c * 32 + 16), vraw + 16);
+                    tmem_ld16_wait(vraw);
+                    tmem_ld16_wait(vraw + 16);
+                    if (c == c_hi - 1) {                             // this warp's part of the accumulator is in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (rank != 0) mbar_arrive_rank0(smem_u32(&acc_empty[buf]));
+                            else mbar_arrive(smem_u32(&acc_empty[buf]));
+                        }
+                    }
+                    const int64_t n0 = (int64_t)n_blk * BN + 32 * c;
+                    if (n0 >= p.N + 4 && !(p.out_hi && n0 < p.ld16)) { fetch(c + 1); continue; }   // nothing of this chunk exists
+                    float o[32];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) && has_bias)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w)
+                                         : "r"(bsa + (uint32_t)(32 * c + 4 * g) * 4u));
+                        const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = 4 * g + e;
+                            float x = __uint_as_float(vraw[i]);
+                            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ACT) x += b4[e];
+                            if (EPI == EPI_BIAS_ACT) x = act_fwd(x, p.act);
+                            if (EPI == EPI_MUL_DACT) x *= act_bwd_from_out(sd[i], p.act);
+                            // columns past N: 0, except column N itself = 1 when the consumer's bias column needs it
+                            if (n0 + i >= p.N) x = (p.ones_col && n0 + i == p.N) ? 1.f : 0.f;
+                            o[i] = x;
+                        }
+                    }
+                    fetch(c + 1);                                    // (sd[] has been consumed)
+                    // the bulk stores that used these buffers have read them
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    if (p.C) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<float4*>(obuf + sw_chunk<32>((uint32_t)lane, (uint32_t)g)) =
+                                make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                    }
+                    if (p.out_hi) {
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg) {
+                            uint32_t hh[4], ll[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float v0 = o[8 * gg + 2 * k], v1 = o[8 * gg + 2 * k + 1];
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                                const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                                const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                                hh[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                ll[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            }
+                            const uint32_t off = sw_chunk<16>((uint32_t)lane, (uint32_t)gg);
+                            *reinterpret_cast<uint4*>(obuf + EPI_CHUNK_BYTES + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                            *reinterpret_cast<uint4*>(obuf + EPI_CHUNK_BYTES + EPI_CHUNK_BYTES / 2 + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int col0 = (int)n0;
+                        if (p.C)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(obuf)), "r"(col0), "r"(row0) : "memory");
+                        if (p.out_hi) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(obuf + EPI_CHUNK_BYTES)), "r"(col0), "r"(row0) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmC2)), "r"(smem_u32(obuf + EPI_CHUNK_BYTES + EPI_CHUNK_BYTES / 2)),
+                                         "r"(col0), "r"(row0) : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if constexpr (STG) {
+            static_assert(EPI == EPI_RECON, "the staged target / gradient epilogue is the reconstruction head's");
             constexpr int CPT = HC / 32;               // 32-column chunks per warp and tile
             uint8_t* ebuf = epi_base + (size_t)ew * (EPI_NIN + EPI_NOUT) * EPI_CHUNK_BYTES;
             uint64_t* infull = in_full + ew * EPI_NIN;
@@ -686,14 +820,14 @@ static int launch(const CUtensorMap& tah, const CUtensorMap& tal, const CUtensor
     auto kern = gemm_ps_kernel<BN, EPI, STG, PL>;
     static bool attr_done = false;
     if (!attr_done) {
-        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, STG>::SMEM));
+        CDG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, STG, EPI == EPI_RECON>::SMEM));
         attr_done = true;
     }
     const unsigned clusters = (unsigned)imin64(p.work_total, kNumSMs / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = Cfg<BN, STG>::SMEM;
+    cfg.dynamicSmemBytes = Cfg<BN, STG, EPI == EPI_RECON>::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -714,6 +848,18 @@ static int launch_epi(int epi, const CUtensorMap& tah, const CUtensorMap& tal, c
         case EPI_BIAS_ACT: return launch<BN, EPI_BIAS_ACT>(tah, tal, tbh, tbl, p, s);
         case EPI_MUL_DACT: return launch<BN, EPI_MUL_DACT>(tah, tal, tbh, tbl, p, s);
         case EPI_NONE: return launch<BN, EPI_NONE>(tah, tal, tbh, tbl, p, s);
+    }
+    return CDG_ERR_UNSUPPORTED;
+}
+
+template <int BN>
+static int launch_epi_so(int epi, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh, const CUtensorMap& tbl,
+                         const Params& p, cudaStream_t s, const CUtensorMap* tc_, const CUtensorMap* th, const CUtensorMap* tl) {
+    switch (epi) {
+        case EPI_BIAS: return launch<BN, EPI_BIAS, true>(tah, tal, tbh, tbl, p, s, tc_, th, tl);
+        case EPI_BIAS_ACT: return launch<BN, EPI_BIAS_ACT, true>(tah, tal, tbh, tbl, p, s, tc_, th, tl);
+        case EPI_MUL_DACT: return launch<BN, EPI_MUL_DACT, true>(tah, tal, tbh, tbl, p, s, tc_, th, tl);
+        case EPI_NONE: return launch<BN, EPI_NONE, true>(tah, tal, tbh, tbl, p, s, tc_, th, tl);
     }
     return CDG_ERR_UNSUPPORTED;
 }
@@ -782,6 +928,19 @@ int gemm_ps(const GemmDesc& g, cudaStream_t s) {
         CDG_TRY(chunk_map_f32(g.recon_x, g.M, g.N, g.ld_x, &tx));
         CDG_TRY(chunk_map_f32(g.C, g.M, g.N, g.ldc, &tcm));
         return launch<256, EPI_RECON, true>(tah, tal, tbh, tbl, p, s, &tx, &tcm);
+    }
+    static const int staged_out = exp_switch("CDG_PS_SO", 1);
+    if (staged_out && BN <= 160 && g.epi != EPI_RECON && g.N % 4 == 0 && (!g.C || g.ldc % 4 == 0)) {
+        // hidden-layer GEMMs: result and planes leave as bulk stores of 32-column chunks
+        CUtensorMap tcm = tah, th = tah, tl = tah;
+        if (g.C) CDG_TRY(chunk_map_f32(g.C, g.M, g.N, g.ldc, &tcm));
+        if (out_hi) {
+            CDG_TRY(chunk_map_bf16(out_hi, g.M, ld_out16, ld_out16, &th));
+            CDG_TRY(chunk_map_bf16(out_lo, g.M, ld_out16, ld_out16, &tl));
+        }
+        if (BN == 160) return launch_epi_so<160>(g.epi, tah, tal, tbh, tbl, p, s, &tcm, &th, &tl);
+        if (BN == 128) return launch_epi_so<128>(g.epi, tah, tal, tbh, tbl, p, s, &tcm, &th, &tl);
+        return launch_epi_so<64>(g.epi, tah, tal, tbh, tbl, p, s, &tcm, &th, &tl);
     }
     if (BN == 256) return launch_epi<256>(g.epi, tah, tal, tbh, tbl, p, s);
     if (BN == 160) return launch_epi<160>(g.epi, tah, tal, tbh, tbl, p, s);

@@ -67,7 +67,7 @@ def _planes(W, ld16):
     return hi, lo
 
 
-PLANE_SHAPES = [(4096, 256, 300), (4096, 304, 300), (2048 + 128, 3840, 300), (4096 + 77, 5952, 300), (1024, 2496, 300),
+PLANE_SHAPES = [(4096, 256, 300), (4096, 304, 300), (4096 + 33, 300, 301), (2048 + 128, 3840, 300), (4096 + 77, 5952, 300), (1024, 2496, 300),
                 (4096, 64, 512), (2048, 128, 96), (4096, 304, 1024), (1024, 16, 64)]
 
 
