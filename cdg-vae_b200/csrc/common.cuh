@@ -179,6 +179,10 @@ int launch_split_bf16(const float* W, int64_t rows, int64_t cols, int64_t ld, vo
 int launch_split_rows(const float* W, int64_t rows, int64_t cols, int64_t ld, void* hi, void* lo, int64_t ld16, const float* extra,
                       int ones, cudaStream_t s);
 
+// backward of a Linear with a tiny input (in <= 4) in one pass over dY [rows, out]: dW += dY^T x, db += colsum(dY), dX = dY W
+int launch_tiny_in_bwd(const float* dY, int64_t ld_dy, const float* x, int64_t ld_x, const float* W, float* dW, float* db, float* dX,
+                       int64_t ld_dx, int64_t rows, int out, int in, cudaStream_t s);
+
 int gemm_simt(const GemmDesc& g, cudaStream_t s);
 int gemm_skinny(const GemmDesc& g, cudaStream_t s);   // tiny-extent shapes; CDG_ERR_UNSUPPORTED otherwise
 // tcgen05 path; returns CDG_ERR_UNSUPPORTED when the shape/layout does not fit, so that the

@@ -871,13 +871,20 @@ extern "C" int cdg_pendulum_forward_backward(cdg_pendulum_plan* p, const cdg_pen
             CDG_TRY(rw);
         }
         CDG_TRY(linear_dgrad(c, ga2, H, cf.dec[k][1], 0, H, ga1, H, a1, H, B, PROF_GEMM_OTHER, n > 0 ? &bp0 : nullptr));
-        CDG_TRY(linear_wgrad(c, ga1, H, zk, ldzk, cf.dec[k][0], 0, H, B));
-        if (!dr) {
-            CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, g_z + p->lat_off[k], d, nullptr, 0, B));
-        } else {
+        {
+            // first decoder layer (in = 1 .. 3): weight, bias and input gradient in one pass over ga1
+            const cdg_linear& L0 = cf.dec[k][0];
             float* gzin = W + c.w.gzin;
-            CDG_TRY(linear_dgrad(c, ga1, H, cf.dec[k][0], 0, H, gzin, ldzk, nullptr, 0, B));
-            CDG_TRY(launch_scatter_add_cols(gzin, g_z, (int)d, cf.factor[k], p->lat_off[k], cf.dec_extra[k], B, s));
+            c.mark(PROF_GEMM_OTHER);
+            int r0 = c.mode == CDG_GEMM_SIMT ? CDG_ERR_UNSUPPORTED
+                                             : launch_tiny_in_bwd(ga1, H, zk, ldzk, c.P + L0.w, c.G + L0.w, c.G + L0.b,
+                                                                  dr ? gzin : g_z + p->lat_off[k], dr ? ldzk : d, B, (int)H, L0.in, s);
+            if (r0 == CDG_ERR_UNSUPPORTED) {
+                CDG_TRY(linear_wgrad(c, ga1, H, zk, ldzk, L0, 0, H, B));
+                r0 = linear_dgrad(c, ga1, H, L0, 0, H, dr ? gzin : g_z + p->lat_off[k], dr ? ldzk : d, nullptr, 0, B);
+            }
+            CDG_TRY(r0);
+            if (dr) CDG_TRY(launch_scatter_add_cols(gzin, g_z, (int)d, cf.factor[k], p->lat_off[k], cf.dec_extra[k], B, s));
         }
         if (p->ready_enabled) CDG_CHECK_CUDA(cudaEventRecord(p->ready[k], s));       // decoder k's gradients are final
     }

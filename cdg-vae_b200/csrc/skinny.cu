@@ -256,6 +256,116 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(SkinnyW a) {
     }
 }
 
+// ---- backward of a Linear with a TINY input (the decoders' first layer, in = 1 .. 4) in ONE pass over dY ---------------------
+//   dW[j, i] += sum_b dY[b, j] x[b, i]      db[j] += sum_b dY[b, j]      dX[b, i] = sum_j dY[b, j] W[j, i]
+// Round 1 ran three kernels here (skinny_wgrad, colsum, rowdot: 89 + 25 + 68 us per decoder at 131,072 rows), each reading
+// the same [batch, 300] matrix.  A warp owns a batch row at a time: lane q holds the 16-byte pieces q, q + 32, q + 64 of the
+// row, accumulates its slice of dW / db in registers over all rows it sees, and the row's dX is a warp sum.
+constexpr int TIB_MAX_IN = 4, TIB_PIECES = 3;          // in <= 4, out <= 384 (3 x 32 pieces of 4 columns)
+struct TinyInBwd {
+    const float* dY; int64_t ld_dy;
+    const float* x; int64_t ld_x;
+    const float* W;                      // [out][in]
+    float* dW; float* db;                // accumulated into
+    float* dX; int64_t ld_dx;
+    int64_t rows; int out, in;
+};
+template <int IN>
+__global__ void __launch_bounds__(256) tiny_in_bwd_kernel(TinyInBwd a) {
+    __shared__ float red[(IN + 1) * 384];
+    const int lane = threadIdx.x & 31;
+    const int n4 = a.out >> 2;
+    float w[TIB_PIECES][4][IN], gw[TIB_PIECES][4][IN], gb[TIB_PIECES][4];
+#pragma unroll
+    for (int p = 0; p < TIB_PIECES; ++p)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            gb[p][e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < IN; ++i) {
+                const int j = 4 * (lane + 32 * p) + e;
+                w[p][e][i] = lane + 32 * p < n4 ? a.W[(int64_t)j * IN + i] : 0.f;
+                gw[p][e][i] = 0.f;
+            }
+        }
+    for (int i = threadIdx.x; i < (IN + 1) * 384; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int R = 2;                                   // rows in flight per warp
+    for (int64_t b0 = warp0; b0 < a.rows; b0 += R * nwarps) {
+        float4 g[R][TIB_PIECES];
+        float xv[R][IN];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t b = b0 + r * nwarps;
+            const bool ok = b < a.rows;
+            const float4* row = reinterpret_cast<const float4*>(a.dY + (ok ? b : 0) * a.ld_dy);
+#pragma unroll
+            for (int p = 0; p < TIB_PIECES; ++p)
+                g[r][p] = (ok && lane + 32 * p < n4) ? __ldg(row + lane + 32 * p) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < IN; ++i) xv[r][i] = ok ? __ldg(a.x + b * a.ld_x + i) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t b = b0 + r * nwarps;
+            float dx[IN];
+#pragma unroll
+            for (int i = 0; i < IN; ++i) dx[i] = 0.f;
+#pragma unroll
+            for (int p = 0; p < TIB_PIECES; ++p) {
+                const float gv[4] = {g[r][p].x, g[r][p].y, g[r][p].z, g[r][p].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    gb[p][e] += gv[e];
+#pragma unroll
+                    for (int i = 0; i < IN; ++i) {
+                        gw[p][e][i] = fmaf(gv[e], xv[r][i], gw[p][e][i]);
+                        dx[i] = fmaf(gv[e], w[p][e][i], dx[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < IN; ++i) {
+                const float t = warp_sum(dx[i]);
+                if (lane == 0 && b < a.rows) a.dX[b * a.ld_dx + i] = t;
+            }
+        }
+    }
+    // block reduction of the register slices through shared memory, then one atomic per value and block
+#pragma unroll
+    for (int p = 0; p < TIB_PIECES; ++p)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * (lane + 32 * p) + e;
+            if (lane + 32 * p < n4) {
+                atomicAdd(&red[j], gb[p][e]);
+#pragma unroll
+                for (int i = 0; i < IN; ++i) atomicAdd(&red[(1 + i) * 384 + j], gw[p][e][i]);
+            }
+        }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.out; j += blockDim.x) {
+        atomicAdd(a.db + j, red[j]);
+        for (int i = 0; i < IN; ++i) atomicAdd(a.dW + (int64_t)j * IN + i, red[(1 + i) * 384 + j]);
+    }
+}
+// CDG_ERR_UNSUPPORTED when the shape does not fit (the caller then takes the three separate kernels)
+int launch_tiny_in_bwd(const float* dY, int64_t ld_dy, const float* x, int64_t ld_x, const float* W, float* dW, float* db, float* dX,
+                       int64_t ld_dx, int64_t rows, int out, int in, cudaStream_t s) {
+    if (in < 1 || in > TIB_MAX_IN || out % 4 != 0 || out > 4 * 32 * TIB_PIECES || ld_dy % 4 != 0 || (((uintptr_t)dY) & 15) != 0 || rows < 1)
+        return CDG_ERR_UNSUPPORTED;
+    TinyInBwd a{dY, ld_dy, x, ld_x, W, dW, db, dX, ld_dx, rows, out, in};
+    const int blocks = (int)imin64((rows + 15) / 16, kNumSMs * 4);
+    if (in == 1) tiny_in_bwd_kernel<1><<<blocks, 256, 0, s>>>(a);
+    else if (in == 2) tiny_in_bwd_kernel<2><<<blocks, 256, 0, s>>>(a);
+    else if (in == 3) tiny_in_bwd_kernel<3><<<blocks, 256, 0, s>>>(a);
+    else tiny_in_bwd_kernel<4><<<blocks, 256, 0, s>>>(a);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}
+
 // returns CDG_ERR_UNSUPPORTED when the contraction is not one of the skinny shapes
 int gemm_skinny(const GemmDesc& g, cudaStream_t s) {
     if (g.M <= 0 || g.N <= 0) return CDG_OK;
