@@ -75,6 +75,7 @@ struct Params {
     int ones_col;                                // planes: column N = 1 (the consumer's bias column), later columns 0
     int c8, side8;                               // C / xhat rows (side operand rows) are 32-byte aligned: 256-bit accesses
     int kb_total, tiles_n;
+    int last_ksteps;                             // K = 16 steps of the last K-block that hold real columns
     int64_t work_total;
 };
 
@@ -239,6 +240,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(smem_u32(&full[s]), ph);
                     tc_fence_after();
+                    const int ksteps = kb == p.kb_total - 1 ? p.last_ksteps : BK / 16;
                     if (elect_one()) {
                         const uint64_t dah = desc_sw128(smem_u32(a_hi(s))), dal = desc_sw128(smem_u32(a_lo(s)));
                         const uint64_t dbh = desc_sw128(smem_u32(b_hi(s))), dbl = desc_sw128(smem_u32(b_lo(s)));
@@ -248,8 +250,9 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             const uint64_t db = pass == 1 ? dbl : dbh;
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)                 // UMMA K = 16 bf16 = 32 bytes along the row
-                                umma_bf16_ss2(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                              (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
+                                if (k < ksteps)                               // (the last K-block may be short: K = 301 -> 3 steps)
+                                    umma_bf16_ss2(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                                  (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit2(smem_u32(&empty[s]));
                         if (kb == p.kb_total - 1) umma_commit2(smem_u32(&acc_full[buf]));
@@ -905,6 +908,7 @@ int gemm_ps(const GemmDesc& g, cudaStream_t s) {
     p.c8 = (!g.C || (g.ldc % 8 == 0 && al32p(g.C))) && (!g.recon_xhat || al32p(g.recon_xhat)) ? 1 : 0;
     p.side8 = g.epi == EPI_RECON ? (g.ld_x % 8 == 0 && al32p(g.recon_x)) : g.epi == EPI_MUL_DACT ? (g.ld_aux % 8 == 0 && al32p(g.aux)) : 0;
     p.kb_total = (int)((g.K + BK - 1) / BK); p.tiles_n = (int)tn; p.work_total = tm * tn;
+    p.last_ksteps = (int)((g.K - (int64_t)(p.kb_total - 1) * BK + 15) / 16);
     CUtensorMap tah, tal, tbh, tbl;
     CDG_TRY(plane_map(g.a_hi16, g.M, g.K, g.ld_a16, BM, &tah));
     CDG_TRY(plane_map(g.a_lo16, g.M, g.K, g.ld_a16, BM, &tal));
