@@ -357,6 +357,54 @@ def main():
         e2e_fp32["api"] = "same call, data.DevicePrefetcher over pinned fp32 host batches"
         e2e["fp32_host_batches"] = e2e_fp32
 
+        # a dataset that fits HBM (the reference's own: 7,500 pendulum images = 92 MB of bytes): uploaded ONCE as uint8, outside
+        # the timed region; every step's batch is assembled on the device (sampler permutation gathered + datasets.py:28 in
+        # one kernel, cdgvae_b200.data.DeviceDataLoader(pixels=True)); per step only the CPU noise draw crosses PCIe
+        from cdgvae_b200.data import DeviceDataLoader
+
+        class Epochs:                          # K batches out of a loader that is re-iterated epoch after epoch
+            exact_len = True
+
+            def __init__(self, loader, k, at=None):
+                self.loader, self.k, self.at = loader, k, at
+
+            def __len__(self):
+                return self.k
+
+            def __iter__(self):
+                n = 0
+                while n < self.k:
+                    for b in self.loader:
+                        if n == self.at:
+                            e0.record()
+                        yield b
+                        n += 1
+                        if n >= self.k:
+                            return
+        try:
+            dsU = torch.cat([xu8, xu8.flip(0)])                                   # 2 B images resident (3.2 GB at the default batch)
+            dsL = torch.cat([xlu8, xlu8.flip(0)])
+            ylab = torch.cat([yld, yld.flip(0)])
+            ldU = DeviceDataLoader(dsU, batch_size=B, shuffle=True, device=dev, pixels=True)
+            ldL = DeviceDataLoader(dsL, ylab, batch_size=BL, shuffle=True, device=dev, pixels=True)
+            We = max(W, 4)
+            barrier()
+            train_CDGVAE_semi_loaders(Epochs(ldL, We + args.steps), Epochs(ldU, We + args.steps, at=We), model, cfg, opt, dev)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e["device_resident_dataset"] = {
+                "value": B * world * args.steps / (float(t) / 1e3), "unit": "samples/s", "ms_per_step": float(t) / args.steps,
+                "h2d_bytes_per_step": noise_p.numel() * 4, "d2h_bytes_per_step": 4 * 8,
+                "dataset_bytes_resident": int(dsU.numel() + dsL.numel()),
+                "api": "train_CDGVAE_semi_loaders over data.DeviceDataLoader(pixels=True, shuffle=True): the uint8 dataset uploaded once, "
+                       "batches gathered + converted on the device; only the per-step CPU noise draw is copied"}
+            del dsU, dsL, ylab, ldU, ldL
+        except Exception as e:                                                   # informational: never costs the headline line
+            e2e["device_resident_dataset"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the other BASELINE configs and the informational "existing GPU path" -----------------------
     hbm, tf_burst, tf_sus, src = peaks()
     B_, BL_ = B, BL

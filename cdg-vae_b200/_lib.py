@@ -133,7 +133,7 @@ EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
            "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit", "cdg_gemm_planes", "cdg_gemm_planes_acc", "cdg_tvae_transform", "cdg_tvae_inverse_transform",
-           "cdg_gumbel_argmax", "cdg_pixels_to_float"]
+           "cdg_gumbel_argmax", "cdg_pixels_to_float", "cdg_pixels_gather_to_float"]
 
 _lib = None
 ABI_STRUCTS = [Linear, AdamArgs, PendulumConfig, PendulumIO, PendulumFwdIO, TabularConfig, TabularIO, Conv, BNorm, CelebaConfig,
@@ -220,6 +220,7 @@ def lib():
     L.cdg_gemm_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_int64, C.c_void_p]
+    L.cdg_pixels_gather_to_float.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.cdg_gemm_planes_acc.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     L.cdg_gemm_bsplit.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

@@ -428,6 +428,11 @@ int cdg_gumbel_argmax(const float* logits, int64_t ld, int32_t n_class, const fl
  * of 4) are what crosses PCIe every step (data.py::DevicePrefetcher(pixels=True)).
  * ---------------------------------------------------------------------------------------- */
 int cdg_pixels_to_float(const uint8_t* pixels, int64_t n, float* out, void* stream);
+/* Batch assembly from a device-resident uint8 dataset [n_images][row_bytes]: out[r] = the same conversion of image idx[r]
+ * (what DataLoader(shuffle=True) + collate + modules/datasets.py:28 do on the host), one pass, coalesced on both sides.
+ * idx: int64 on the device, values in [0, n_images) (not checked); row_bytes a multiple of 16. */
+int cdg_pixels_gather_to_float(const uint8_t* images, int64_t n_images, int64_t row_bytes, const int64_t* idx, int64_t rows,
+                               float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -315,3 +315,36 @@ def test_gpu_prefetcher_pixel_mode_yields_reference_batches():
     assert seen == 7
     for (x, y), (xh, yh) in zip(DevicePrefetcher(batches, "cuda"), batches):     # default: bytes stay bytes
         assert x.dtype == torch.uint8 and torch.equal(x.cpu(), xh)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_gpu_device_loader_uint8_dataset_matches_the_reference_pipeline(shuffle):
+    """A device-resident uint8 dataset (DeviceDataLoader(pixels=True): gather + modules/datasets.py:28 in one kernel) yields,
+    bit for bit and in the same order, the batches torch's DataLoader yields over the reference's converted fp32 dataset."""
+    from torch.utils.data import DataLoader, Dataset
+    from cdgvae_b200.data import DeviceDataLoader
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (53, 8, 8, 3), dtype=torch.uint8, generator=g)
+    y = torch.rand(53, 5, generator=g)
+
+    class Ref(Dataset):                                      # modules/datasets.py:14-45 in miniature
+        def __init__(self):
+            self.x_data = (np.array(u8).astype(float) - 127.5) / 127.5
+            self.y_data = np.array(y)
+
+        def __len__(self):
+            return len(self.x_data)
+
+        def __getitem__(self, idx):
+            return torch.FloatTensor(self.x_data[idx]), torch.FloatTensor(self.y_data[idx])
+
+    torch.manual_seed(11)
+    ref = [(a.clone(), b.clone()) for a, b in DataLoader(Ref(), batch_size=16, shuffle=shuffle)]
+    torch.manual_seed(11)
+    got = list(DeviceDataLoader(u8, y, batch_size=16, shuffle=shuffle, device="cuda", pixels=True))
+    assert len(got) == len(ref) == 4
+    for (xa, ya), (xb, yb) in zip(got, ref):
+        assert xa.dtype == torch.float32 and xa.is_cuda and torch.equal(xa.cpu(), xb) and torch.equal(ya.cpu(), yb)
+    with pytest.raises(TypeError):
+        DeviceDataLoader(u8.float(), batch_size=4, device="cuda", pixels=True)
