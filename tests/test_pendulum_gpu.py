@@ -579,3 +579,62 @@ def test_cuda_graph_replay_of_presplit_path_matches_eager():
             assert abs(a - b) <= 5e-5 * abs(a) + 1e-7, (k, a, b)
     assert rel(res[0][1], res[1][1]) < 1e-4
     assert rel(res[0][2], res[1][2]) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["vae", "dr", "infomax"])
+def test_planes_route_of_the_model_variants_matches_oracle(variant):
+    """From batch 2,048 up the step runs on bf16 planes (gemm_ps / gemm_pk kernels).  The goldens of the
+    VAE baseline, the DR variant and InfoMax are batch 16, i.e. they drive the small-batch kernels: here each variant takes
+    one step at 2,048 rows of the full image size against the oracle -- losses, reconstruction and every gradient at 1e-4
+    (single decoder over all 12,288 columns; decoders with the extra spurious input and the scatter of its gradient; the
+    discriminator's gradient arriving at epsilon on top of the decoders')."""
+    B = 2048
+    cfg = dict(node=4, scm="linear", flow_num=1, inverse_loop=100, factor=[1, 1, 2], image_size=64, batch_size=B, lr=1e-3,
+               beta=0.1, seed=1, gamma=0.01, lr_D=1e-4)
+    cfg["lambda"] = 5.0
+    mask = orc.pendulum_masks(64)
+    if variant == "dr":
+        from cdgvae_b200.DR.modules.model import CDGVAE as Model
+        from cdgvae_b200.DR.modules.train import train_CDGVAE as train
+        cfg["node"] = 5
+        Bm = torch.zeros(5, 5)
+        Bm[:4, :4] = orc.pendulum_B(4)
+        spec = orc.dr_spec(cfg, mask)
+        torch.manual_seed(1)
+        model = Model(Bm, mask, cfg, "cpu").to("cuda")
+    else:
+        from cdgvae_b200.modules.model import VAE as Model
+        Bm = orc.pendulum_B(4)
+        spec = orc.vae_spec(cfg)
+        torch.manual_seed(1)
+        model = Model(Bm, cfg, "cpu")
+        if variant == "infomax":
+            from cdgvae_b200.modules.model import Discriminator
+            disc = Discriminator(cfg, "cpu").to("cuda")
+        model = model.to("cuda")
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    x, y, noise = orc.synth_pendulum(B, 64, cfg["node"], 1234, 4321)
+    model.noise_fn = lambda n, d: noise
+    oparams = orc.init_params(spec, 1)
+    A = orc.i_b_inv(Bm)
+    if variant == "infomax":
+        from cdgvae_b200.modules.train import train_InfoMax
+        odparams = orc.init_discriminator(cfg)
+        opt_d = torch.optim.Adam(disc.parameters(), lr=cfg["lr_D"])
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(5))
+        model.perm_fn = lambda n: perm
+        logs, xhat = train_InfoMax([(x, y)], model, disc, cfg, opt, opt_d, "cuda")
+        ol, og, odg, oo = orc.infomax_train_step(oparams, odparams, orc.new_adam_state(oparams), orc.new_adam_state(odparams), spec, A,
+                                                 x, y, noise, perm, cfg["gamma"], cfg["lr_D"])
+        for n, p in disc.named_parameters():
+            assert rel(p.grad, odg[n]) < RTOL, ("D", n, rel(p.grad, odg[n]))
+    else:
+        if variant == "vae":
+            from cdgvae_b200.modules.train import train_VAE as train
+        logs, xhat = train([(x, y)], model, cfg, opt, "cuda")
+        ol, og, oo = orc.train_step(oparams, orc.new_adam_state(oparams), spec, A, x, y, noise)
+    for k, v in ol.items():
+        assert abs(logs[k][0] - v) <= RTOL * abs(v) + 1e-7, (variant, k, logs[k][0], v)
+    assert rel(xhat, oo["xhat"]) < RTOL
+    for n, p in model.named_parameters():
+        assert rel(p.grad, og[n]) < RTOL, (variant, n, rel(p.grad, og[n]))
