@@ -36,7 +36,9 @@ namespace cdg {
 
 #ifdef CDG_EXPERIMENTS
 #define CDG_PROBE(p) ((p).probe)
+#define CDG_SKIP_FENCE_OFF(p) ((p).probe & 4)       // experiments: CDG_TC_PROBE=4 keeps the proxy fence (A/B timing)
 #else
+#define CDG_SKIP_FENCE_OFF(p) 0
 #define CDG_PROBE(p) 0          // the timing probes (skip conversion / skip TMA: results invalid) are not in the shipped kernels
 #endif
 
@@ -705,7 +707,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (!B_MN) convert_kmajor<PASSES, GT>(b_hi(s), b_lo(s), C_::B_BYTES, ct, p.rawhi);
                 else convert_mnmajor<PASSES, BN, C_::B_CW, BK, GT>(b_hi(s), b_lo(s), ct, 3 + grp);
                 tc_fence_before();                                   // tcgen05.st (A ring) ordered before the arrive
-                fence_async_smem();                                  // generic-proxy writes -> async proxy (UMMA)
+                // generic-proxy writes -> async proxy (UMMA).  Not needed when this stage's conversion wrote no shared memory
+                // at all (bf16x3 with the A operand in tensor memory and a pre-split B): the proxy fence waits out every
+                // outstanding shared-memory access of the warp, a few hundred cycles in front of each hand-off to the MMA warp
+                if (!(BF3X && C_::A_TMEM && p.b_pre && !CDG_SKIP_FENCE_OFF(p))) fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     // CTA pairs: the MMA thread of rank 0 waits for both CTAs' tiles (landed by TMA and converted)
