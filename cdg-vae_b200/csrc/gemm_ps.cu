@@ -880,7 +880,8 @@ int gemm_ps(const GemmDesc& g, cudaStream_t s) {
     const int64_t ld_out16 = g.ld_out16;
     const int ones_col = g.out_ones;
     if (!g.a_hi16 || !g.a_lo16 || !g.b_hi16 || !g.b_lo16) return CDG_ERR_UNSUPPORTED;
-    if (g.M < 1024 || g.N < 16 || g.N % 4 != 0 || g.K < 16 || g.K > 2048 || g.accumulate || g.extra_col || g.conv_C > 0)
+    static const int64_t min_m = exp_switch("CDG_PS_MIN_M", 128);
+    if (g.M < min_m || g.N < 16 || g.N % 4 != 0 || g.K < 16 || g.K > 2048 || g.accumulate || g.extra_col || g.conv_C > 0)
         return CDG_ERR_UNSUPPORTED;
     auto al16p = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     if (g.ld_a16 % 8 != 0 || g.ld_b16 % 8 != 0 || (((uintptr_t)g.a_hi16 | (uintptr_t)g.a_lo16 | (uintptr_t)g.b_hi16 | (uintptr_t)g.b_lo16) & 15))

@@ -354,7 +354,7 @@ int cdg_gemm_bsplit(const float* A, int64_t sa_m, int64_t sa_k, const void* b_hi
  * a previous call's out_hi / out_lo): the CTA-pair kernel of csrc/gemm_ps.cu, TMA-fed with no in-kernel conversion.
  * epi: 0 = none, 1 = + bias[n], 2 = ELU(+ bias[n]), 3 = * ELU'(aux[m,n]) (aux = post-activation values, row stride ld_aux).
  * C (row stride ldc, 32-byte aligned rows) and / or out_hi / out_lo ([M][ld_out16] bf16 planes of the fp32 result) are written.
- * Returns CDG_ERR_UNSUPPORTED for shapes the kernel does not take (M < 1024, N % 16 != 0, K > 2048, misaligned operands). */
+ * Returns CDG_ERR_UNSUPPORTED for shapes the kernel does not take (M < 128, N % 4 != 0, K > 2048, misaligned operands). */
 int cdg_gemm_planes(const void* a_hi, const void* a_lo, int64_t ld_a16, const void* b_hi, const void* b_lo, int64_t ld_b16,
                     float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epi, const float* bias, const float* aux,
                     int64_t ld_aux, void* out_hi, void* out_lo, int64_t ld_out16, void* stream);

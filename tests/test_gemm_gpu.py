@@ -68,7 +68,7 @@ def _planes(W, ld16):
 
 
 PLANE_SHAPES = [(4096, 256, 300), (4096, 304, 300), (4096 + 33, 300, 301), (2048 + 128, 3840, 300), (4096 + 77, 5952, 300), (1024, 2496, 300),
-                (4096, 64, 512), (2048, 128, 96), (4096, 304, 1024), (1024, 16, 64)]
+                (4096, 64, 512), (2048, 128, 96), (4096, 304, 1024), (1024, 16, 64), (128, 300, 301), (200, 3840, 301)]
 
 
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
@@ -116,13 +116,13 @@ def test_gemm_planes(shape, epi):
 
 def test_gemm_planes_rejects_what_it_cannot_take():
     from cdgvae_b200 import _lib
-    A = torch.randn(512, 64).cuda(); B = torch.randn(32, 64).cuda()
+    A = torch.randn(64, 64).cuda(); B = torch.randn(32, 64).cuda()
     ah, al = _planes(A, 64); bh, bl = _planes(B, 64)
-    out = torch.zeros(512, 32, device="cuda")
+    out = torch.zeros(64, 32, device="cuda")
     p = lambda t: C.c_void_p(t.data_ptr())
-    rc = _lib.lib().cdg_gemm_planes(p(ah), p(al), 64, p(bh), p(bl), 64, p(out), 32, 512, 32, 64, 0, None, None, 0, None, None, 0,
+    rc = _lib.lib().cdg_gemm_planes(p(ah), p(al), 64, p(bh), p(bl), 64, p(out), 32, 64, 32, 64, 0, None, None, 0, None, None, 0,
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    assert rc == 4                                                          # CDG_ERR_UNSUPPORTED: M < 1024
+    assert rc == 4                                                          # CDG_ERR_UNSUPPORTED: M < 128
 
 
 # ---- long contractions on planes, K-major (input gradients) and MN-major (weight gradients): csrc/gemm_pk.cu ----------------

@@ -509,16 +509,17 @@ def test_dr_variant_matches_reference_and_oracle(golden):
     assert len(out) == 9 and len(out[4]) == 5
 
 
+@pytest.mark.parametrize("B,BL,mode", [(2048, 512, "auto"), (256, 128, "auto"), (128, 128, "bf3x")])
 @pytest.mark.parametrize("scm,semi", [("linear", False), ("nonlinear", True)])
-def test_bf16x3_presplit_path_matches_oracle(scm, semi):
-    """From batch 2,048 up the training step runs its big GEMMs as bf16x3 with pre-split narrow operands.
-    The goldens are smaller than that, so this case drives that path directly against the oracle at the full image size:
-    losses, reconstruction and every gradient within the same 1e-4."""
+def test_bf16x3_presplit_path_matches_oracle(scm, semi, B, BL, mode):
+    """From batch 256 up (128 when gemm_mode = "bf3x" asks for it) the training step runs on bf16 planes with pre-split
+    operands (DESIGN.md sections 4.5 and 4.7).  The goldens are smaller than that, so this case drives that path directly
+    against the oracle at the full image size, at its smallest batches and at 2,048: losses, reconstruction and every
+    gradient within the same 1e-4."""
     from cdgvae_b200.modules.model import CDGVAE
     from cdgvae_b200.modules import train as T
-    B, BL = 2048, 512
     cfg = dict(node=4, scm=scm, flow_num=1, inverse_loop=100, factor=[1, 1, 2], image_size=64, batch_size=B, batch_sizeL=BL,
-               lr=1e-3, beta=0.1, seed=1)
+               lr=1e-3, beta=0.1, seed=1, gemm_mode=mode)
     cfg["lambda"] = 5.0
     Bm, mask = orc.pendulum_B(4), orc.pendulum_masks(64)
     spec = orc.pendulum_spec(cfg, mask)
