@@ -403,7 +403,9 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     // the three fixed CDG-VAE tables have a compile-time specialised kernel (tabular_fixed.cu)
     static const bool generic_only = exp_switch("CDG_TAB_GENERIC", 0) != 0;
-    if (generic_only || !(launch_tab_fixed(a, (unsigned)blocks, smem, s) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
+    if (generic_only ||
+        !(launch_tab_const(a, s) || launch_tab_fixed(a, (unsigned)blocks, smem, s) ||
+          (exp_switch("CDG_TVAE_ROW", 0) == 0 && launch_tvae_tile(a, s)) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
         tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
     CDG_CHECK_LAUNCH();
     if (io->logs)
@@ -411,6 +413,8 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
                                      p->c.beta, p->c.lambda_, s));
     return CDG_OK;
 }
+
+extern "C" void cdg_tabular_const_params(int32_t on) { set_tab_const_params(on); }
 
 extern "C" int cdg_tabular_forward_backward(cdg_tabular_plan* p, const cdg_tabular_io* io, void* stream) {
     return tab_run(p, io, 1, 0, stream);

@@ -80,7 +80,8 @@ __device__ __forceinline__ void fc(const float* sp, const cdg_linear& L, const f
     }
 }
 // delta: dL/d(pre-activation outputs).  Accumulates dW, db; gin = dL/d(hin) times ELU'(hin) when HIN_ACT.
-template <int IN, int OUT, bool HIN_ACT, bool NEED_GIN, int POS, int NPAD>
+// ACC: the products are added to gp (a thread keeps its products over all of its rows and the warp reduction runs once).
+template <int IN, int OUT, bool HIN_ACT, bool NEED_GIN, int POS, bool ACC, int NPAD>
 __device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const cdg_linear& L, const float (&hin)[IN],
                                        const float (&delta)[OUT], float (&gin)[IN]) {
     static_assert(POS + OUT * IN + OUT <= NPAD, "gradient product array too small");
@@ -88,10 +89,10 @@ __device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const
     for (int i = 0; i < IN; ++i) gin[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < OUT; ++o) {
-        gp[POS + OUT * IN + o] = delta[o];                                 // bias
+        gp[POS + OUT * IN + o] = ACC ? gp[POS + OUT * IN + o] + delta[o] : delta[o];                      // bias
 #pragma unroll
         for (int i = 0; i < IN; ++i) {
-            gp[POS + o * IN + i] = delta[o] * hin[i];                       // weight
+            gp[POS + o * IN + i] = ACC ? fmaf(delta[o], hin[i], gp[POS + o * IN + i]) : delta[o] * hin[i];   // weight
             if (NEED_GIN) gin[i] = fmaf(delta[o], sp[L.w + o * IN + i], gin[i]);
         }
     }
@@ -117,7 +118,7 @@ __device__ __forceinline__ void dec_forward(const float* sp, const cdg_tabular_c
 #pragma unroll
     for (int j = 0; j < N::m(k); ++j) xh[N::col(k) + j] = out[j];
 }
-template <class N, int k>
+template <class N, int k, bool ACC>
 __device__ __forceinline__ void dec_backward(const float* sp, float (&gp)[Pos<N>::NA_PAD], const cdg_tabular_config& c,
                                              const float* z, float (&a1)[N::K][N::DH], float (&a2)[N::K][N::DH],
                                              const float (&gx)[N::OUT], float* gz) {
@@ -128,12 +129,12 @@ __device__ __forceinline__ void dec_backward(const float* sp, float (&gp)[Pos<N>
     // flat order inside decoder k: layer 0 (weights, bias), [layer 1], last layer
     constexpr int P0 = Pos<N>::dec_off(k), P1 = P0 + 2 * N::DH, P2 = P1 + (N::ND == 3 ? N::DH * N::DH + N::DH : 0);
     if constexpr (N::ND == 3) {
-        fc_bwd<N::DH, N::m(k), true, true, P2>(sp, gp, c.dec[k][2], a2[k], dout, g2);
-        fc_bwd<N::DH, N::DH, true, true, P1>(sp, gp, c.dec[k][1], a1[k], g2, g1);
+        fc_bwd<N::DH, N::m(k), true, true, P2, ACC>(sp, gp, c.dec[k][2], a2[k], dout, g2);
+        fc_bwd<N::DH, N::DH, true, true, P1, ACC>(sp, gp, c.dec[k][1], a1[k], g2, g1);
     } else {
-        fc_bwd<N::DH, N::m(k), true, true, P2>(sp, gp, c.dec[k][1], a1[k], dout, g1);
+        fc_bwd<N::DH, N::m(k), true, true, P2, ACC>(sp, gp, c.dec[k][1], a1[k], dout, g1);
     }
-    fc_bwd<1, N::DH, false, true, P0>(sp, gp, c.dec[k][0], zin, g1, gzin);
+    fc_bwd<1, N::DH, false, true, P0, ACC>(sp, gp, c.dec[k][0], zin, g1, gzin);
     gz[k] = gzin[0];
 }
 // arena offsets of decoder k's parameters in the same flat order
@@ -156,11 +157,11 @@ __device__ __forceinline__ void dec_forward_all(std::integer_sequence<int, Ks...
                                                 float (&xh)[N::OUT]) {
     (dec_forward<N, Ks>(sp, c, z, a1, a2, xh), ...);
 }
-template <class N, int... Ks>
+template <class N, bool ACC, int... Ks>
 __device__ __forceinline__ void dec_backward_all(std::integer_sequence<int, Ks...>, const float* sp, float (&gp)[Pos<N>::NA_PAD],
                                                  const cdg_tabular_config& c, const float* z, float (&a1)[N::K][N::DH],
                                                  float (&a2)[N::K][N::DH], const float (&gx)[N::OUT], float* gz) {
-    (dec_backward<N, Ks>(sp, gp, c, z, a1, a2, gx, gz), ...);
+    (dec_backward<N, Ks, ACC>(sp, gp, c, z, a1, a2, gx, gz), ...);
 }
 
 template <class N>
@@ -202,6 +203,15 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
     for (int i = 0; i < d; ++i) var_acc[i] = 0.f;
     FlowGrad fg;
     fg.clear();
+
+    // Small networks (loan / adult: 32 + 64 product slots): a thread keeps its products in registers over ALL of its rows
+    // and the warp reduce-scatter runs once per thread instead of once per row (it was ~45 % of the issued instructions).
+    constexpr bool ACCUM = P::NA_PAD + P::NB_PAD <= 128;
+    float gpa_acc[ACCUM ? P::NA_PAD : 1], gpb_acc[ACCUM ? P::NB_PAD : 1];
+#pragma unroll
+    for (int i = 0; i < (ACCUM ? P::NA_PAD : 1); ++i) gpa_acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < (ACCUM ? P::NB_PAD : 1); ++i) gpb_acc[i] = 0.f;
 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nrounds = (a.batch + stride - 1) / stride;
@@ -336,11 +346,13 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
         float gz[CDG_MAX_NODE];
 #pragma unroll
         for (int i = 0; i < CDG_MAX_NODE; ++i) gz[i] = 0.f;
-        {
+        if constexpr (ACCUM) {
+            dec_backward_all<N, true>(std::make_integer_sequence<int, N::K>{}, sp, gpa_acc, c, z, a1, a2, gx, gz);
+        } else {
             float gpa[P::NA_PAD];
 #pragma unroll
             for (int i = P::NA; i < P::NA_PAD; ++i) gpa[i] = 0.f;
-            dec_backward_all<N>(std::make_integer_sequence<int, N::K>{}, sp, gpa, c, z, a1, a2, gx, gz);
+            dec_backward_all<N, false>(std::make_integer_sequence<int, N::K>{}, sp, gpa, c, z, a1, a2, gx, gz);
             flush_products<P::NA_PAD>(gpa, posA, sg);
         }
 
@@ -357,19 +369,32 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
         }
 
         // ---- encoder backward (no gradient into x) ----
-        float gh[N::EH], gdump[N::D], gpb[P::NB_PAD];
-#pragma unroll
-        for (int i = P::NB; i < P::NB_PAD; ++i) gpb[i] = 0.f;
-        if constexpr (N::NE == 4) {
-            float gh2[N::EH], gh1[N::EH];
-            fc_bwd<N::EH, 2 * d, true, true, P::E0 + 2 * P::EM>(sp, gpb, c.enc[3], h2, gml, gh2);
-            fc_bwd<N::EH, N::EH, true, true, P::E0 + P::EM>(sp, gpb, c.enc[2], h1, gh2, gh1);
-            fc_bwd<N::EH, N::EH, true, true, P::E0>(sp, gpb, c.enc[1], h0, gh1, gh);
+        float gh[N::EH], gdump[N::D];
+        if constexpr (ACCUM) {
+            fc_bwd<N::EH, 2 * d, true, true, P::E0, true>(sp, gpb_acc, c.enc[1], h0, gml, gh);
+            fc_bwd<N::D, N::EH, false, false, 0, true>(sp, gpb_acc, c.enc[0], x, gh, gdump);
         } else {
-            fc_bwd<N::EH, 2 * d, true, true, P::E0>(sp, gpb, c.enc[1], h0, gml, gh);
+            float gpb[P::NB_PAD];
+#pragma unroll
+            for (int i = P::NB; i < P::NB_PAD; ++i) gpb[i] = 0.f;
+            if constexpr (N::NE == 4) {
+                float gh2[N::EH], gh1[N::EH];
+                fc_bwd<N::EH, 2 * d, true, true, P::E0 + 2 * P::EM, false>(sp, gpb, c.enc[3], h2, gml, gh2);
+                fc_bwd<N::EH, N::EH, true, true, P::E0 + P::EM, false>(sp, gpb, c.enc[2], h1, gh2, gh1);
+                fc_bwd<N::EH, N::EH, true, true, P::E0, false>(sp, gpb, c.enc[1], h0, gh1, gh);
+            } else {
+                fc_bwd<N::EH, 2 * d, true, true, P::E0, false>(sp, gpb, c.enc[1], h0, gml, gh);
+            }
+            fc_bwd<N::D, N::EH, false, false, 0, false>(sp, gpb, c.enc[0], x, gh, gdump);
+            flush_products<P::NB_PAD>(gpb, posB, sg);
         }
-        fc_bwd<N::D, N::EH, false, false, 0>(sp, gpb, c.enc[0], x, gh, gdump);
-        flush_products<P::NB_PAD>(gpb, posB, sg);
+    }
+    if constexpr (ACCUM) {
+        static_assert(!ACCUM || N::NE == 2, "the accumulating path is written for the two-layer encoders");
+        if (a.do_bwd) {
+            flush_products<P::NA_PAD>(gpa_acc, posA, sg);
+            flush_products<P::NB_PAD>(gpb_acc, posB, sg);
+        }
     }
 
     // ---- block reductions ----

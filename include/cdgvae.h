@@ -245,6 +245,9 @@ typedef struct {
 } cdg_tabular_io;
 
 int cdg_tabular_forward_backward(cdg_tabular_plan* p, const cdg_tabular_io* io, void* stream);
+/* The loan / adult step keeps its parameters in __constant__ memory (copied in front of every launch, stream-ordered).
+ * A process that steps two tabular models concurrently on DIFFERENT streams turns this off (0): shared-memory kernels. */
+void cdg_tabular_const_params(int32_t on);
 int cdg_tabular_forward(cdg_tabular_plan* p, const cdg_tabular_io* io, int32_t deterministic, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ def run(family, name):
         bytes_row = 4 * (D + 2 * d)
     xd, yd, nd = x.cuda(), y.cuda(), noise.cuda()
     model.noise_fn = lambda n, dd: nd
-    step([(xd, yd)] * 3)
+    step([(xd, yd)] * 6)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
