@@ -316,11 +316,10 @@ static int generator_forward(Cx& cx, const cdg_generator& G, GenRun* r, const fl
         float* y2 = cx.ws.take<float>(Mhi * Co);
         CDG_TRY(conv_fwd(cx, y1, B, 2 * H, 2 * H, Co, Co, &r->bn2[b], 1, 1, 3, 1, 1, r->c2[b].fw(), Co, f + gb.conv2.b, y2));
         // skip path: a 1x1 convolution commutes with nearest upsampling, so conv_0 runs at the low resolution
-        const size_t mark = cx.ws.off;
+        // (not handed back to the allocator: the next taker would be another generator's chain on another stream)
         float* sk = cx.ws.take<float>(Mlo * Co);
         CDG_TRY(conv_fwd(cx, h, B, H, H, Ci, Ci, nullptr, 0, 1, 1, 1, 0, r->c0[b].fw(), Co, f + gb.conv0.b, sk));
         RUN(launch_add_up2(y2, sk, y2, B, H, H, Co, cx.s));
-        cx.ws.off = mark;
         h = y2; H *= 2;
     }
     r->h_last = h;
@@ -367,7 +366,7 @@ static int generator_backward(Cx& cx, const cdg_generator& G, const GenRun& r, c
         d.C = g_zin; d.ldc = G.z_dim; d.M = B; d.N = G.z_dim; d.K = N0;
         CDG_TRY(gemm_dispatch(cx.mode, d, nullptr, 0, cx.s));
     }
-    cx.ws.off = mark;
+    (void)mark;          // the temporaries stay allocated: the next generator's chain runs concurrently on another stream
     return CDG_OK;
 }
 
@@ -620,7 +619,35 @@ using namespace cdg;
 struct cdg_celeba_plan {
     cdg_celeba_config c;
     std::map<int64_t, std::pair<int64_t, int64_t>> layout;     // batch -> (workspace bytes, im2col floats)
+    // The five generators are independent between the latent block and the reconstruction head (and again through their
+    // input-gradient chains), and at batch 16 most of their ~700 launches are far too small to fill 148 SMs: each generator
+    // is enqueued on a stream of its own, forked from / joined to the caller's stream with events (legal under capture).
+    cudaStream_t gs[kNGen] = {};
+    cudaEvent_t ev_fork[3] = {}, ev_join[2][kNGen] = {};
+    bool streams_ready = false;
+    bool ensure_streams() {
+        if (streams_ready) return true;
+        for (int k = 0; k < kNGen; ++k) {
+            if (cudaStreamCreateWithFlags(&gs[k], cudaStreamNonBlocking) != cudaSuccess) return false;
+            for (int j = 0; j < 2; ++j)
+                if (cudaEventCreateWithFlags(&ev_join[j][k], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        for (int j = 0; j < 3; ++j)
+            if (cudaEventCreateWithFlags(&ev_fork[j], cudaEventDisableTiming) != cudaSuccess) return false;
+        streams_ready = true;
+        return true;
+    }
+    ~cdg_celeba_plan() {
+        for (int k = 0; k < kNGen; ++k) {
+            if (gs[k]) cudaStreamDestroy(gs[k]);
+            for (int j = 0; j < 2; ++j) if (ev_join[j][k]) cudaEventDestroy(ev_join[j][k]);
+        }
+        for (int j = 0; j < 3; ++j) if (ev_fork[j]) cudaEventDestroy(ev_fork[j]);
+    }
 };
+
+static int g_generator_streams = 7;        // bit 0: forward chains, bit 1: input-gradient chains, bit 2: weight preparation beside the encoder
+extern "C" void cdg_celeba_generator_streams(int32_t on) { g_generator_streams = on; }
 
 static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
     const cdg_celeba_config& c = p->c;
@@ -630,10 +657,22 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
     cx.col = cx.ws.take<float>(cx.col_cap);
     cx.acc = cx.ws.take<double>(kAccDoubles);
     double* lacc = cx.ws.take<double>(CACC_LEN);
+    // one im2col / activation scratch per generator (they run side by side); the layout is the same with streams off
+    float* gen_col[kNGen];
+    for (int k = 0; k < kNGen; ++k) gen_col[k] = cx.ws.take<float>(cx.col_cap);
+    float* const main_col = cx.col;
+    const cudaStream_t main_s = cx.s;
+    const bool conc = !cx.dry && g_generator_streams && !io->encode_only && p->ensure_streams();
     if (!cx.dry) {
         CDG_CHECK_CUDA(cudaMemsetAsync(cx.acc, 0, sizeof(double) * kAccDoubles, cx.s));
         CDG_CHECK_CUDA(cudaMemsetAsync(lacc, 0, sizeof(double) * CACC_LEN, cx.s));
         if (io->backward) CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * c.n_params, cx.s));
+    }
+    const bool conc_prep = conc && (g_generator_streams & 4), conc_fwd = conc && (g_generator_streams & 1);
+    const bool conc_bwd = conc && (g_generator_streams & 2);
+    if (conc_prep) {
+        CDG_CHECK_CUDA(cudaEventRecord(p->ev_fork[0], main_s));
+        for (int k = 0; k < kNGen; ++k) CDG_CHECK_CUDA(cudaStreamWaitEvent(p->gs[k], p->ev_fork[0], 0));
     }
     // encoder (model.py:157-158): one evaluation; the deterministic pass sees the same input (model.py:212)
     const bool decode_only = io->latent_in != nullptr;
@@ -666,16 +705,26 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
         CDG_CHECK_LAUNCH();
     }
     if (io->encode_only) return CDG_OK;
-    // decoders (model.py:188-200)
+    // decoders (model.py:188-200); the weight preparation (spectral norm, layouts) of a generator does not depend on the
+    // latent block, so on its own stream it overlaps the encoder
     static thread_local GenRun runs[kNGen];
     ReconArgs ra{};
+    if (conc_fwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_fork[1], main_s));
     for (int k = 0; k < kNGen; ++k) {
         runs[k] = GenRun();
+        if (conc_fwd) cx.s = p->gs[k];
+        cx.col = gen_col[k];
+        if (conc_fwd && !conc_prep) CDG_CHECK_CUDA(cudaStreamWaitEvent(p->gs[k], p->ev_fork[1], 0));
         CDG_TRY(generator_prepare(cx, c.gen[k], &runs[k]));
+        if (conc_fwd) CDG_CHECK_CUDA(cudaStreamWaitEvent(p->gs[k], p->ev_fork[1], 0));
         CDG_TRY(generator_forward(cx, c.gen[k], &runs[k], la.zin[k], B));
+        if (conc_fwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_join[0][k], p->gs[k]));
         ra.pre[k] = runs[k].rgb_pre;
         ra.gpre[k] = io->backward ? cx.ws.take<float>(M * 3) : nullptr;
     }
+    cx.s = main_s; cx.col = main_col;
+    if (conc_fwd)
+        for (int k = 0; k < kNGen; ++k) CDG_CHECK_CUDA(cudaStreamWaitEvent(main_s, p->ev_join[0][k], 0));
     ra.masks = io->masks; ra.x = io->x; ra.ld_x = io->ld_x; ra.xhat = io->xhat; ra.sep = io->xhat_separated;
     ra.M = M; ra.inv_batch = 1.f / (float)B; ra.acc = lacc;
     if (!cx.dry) {
@@ -687,10 +736,20 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
         }
     }
     if (!io->backward) return CDG_OK;
+    if (conc_bwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_fork[2], main_s));
     for (int k = 0; k < kNGen; ++k) {
+        if (conc_bwd) {
+            cx.s = p->gs[k];
+            CDG_CHECK_CUDA(cudaStreamWaitEvent(p->gs[k], p->ev_fork[2], 0));
+        }
+        cx.col = gen_col[k];
         CDG_TRY(generator_backward(cx, c.gen[k], runs[k], ra.gpre[k], B, S, gzin[k]));
+        if (conc_bwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_join[1][k], p->gs[k]));
         la.gzin[k] = gzin[k];
     }
+    cx.s = main_s; cx.col = main_col;
+    if (conc_bwd)
+        for (int k = 0; k < kNGen; ++k) CDG_CHECK_CUDA(cudaStreamWaitEvent(main_s, p->ev_join[1][k], 0));
     la.g_h = cx.ws.take<float>(B * ldh);
     if (!cx.dry) {
         celeba_latent_bwd_kernel<<<lgrid, 128, 0, cx.s>>>(la);

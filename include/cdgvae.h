@@ -329,6 +329,9 @@ typedef struct {
 } cdg_celeba_io;
 
 int cdg_celeba_step(cdg_celeba_plan* p, const cdg_celeba_io* io, void* stream);
+/* The five generators of a step run on five internal streams forked from / joined to `stream` with events (default 1);
+ * 0 enqueues everything on `stream` alone.  The workspace layout does not depend on this switch. */
+void cdg_celeba_generator_streams(int32_t on);
 
 /* Single layers of that path, exposed for unit tests against torch (tests/test_celeba_gpu.py):
  * NHWC convolution  out[B,Ho,Wo,Co] = conv(x[B,H,W,Ci], w[Co,Ci,k,k]) + bias, and its input gradient. */
