@@ -429,8 +429,8 @@ def main():
         from tools import workloads as wl
         ctx = wl.Ctx(dev, world, rank, hbm, tf_sus, src)
         want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
-        table = {"tabular_adult": lambda: wl.tabular(ctx, "adult", 1 << 20, steps=max(args.steps, 20), cpu=want_cpu),
-                 "tabular_loan": lambda: wl.tabular(ctx, "loan", 1 << 20, steps=max(args.steps, 20), cpu=want_cpu),
+        table = {"tabular_adult": lambda: wl.tabular(ctx, "adult", 1 << 22, steps=max(args.steps, 20), cpu=want_cpu),
+                 "tabular_loan": lambda: wl.tabular(ctx, "loan", 1 << 22, steps=max(args.steps, 20), cpu=want_cpu),
                  "tabular_covtype": lambda: wl.tabular(ctx, "covtype", 1 << 20, steps=max(args.steps, 20), cpu=want_cpu),
                  "tvae_loan": lambda: wl.tvae(ctx, "loan", 1 << 20, steps=max(args.steps, 10), cpu=want_cpu),
                  "tvae_covtype": lambda: wl.tvae(ctx, "covtype", 1 << 20, steps=max(args.steps, 10), cpu=want_cpu),
