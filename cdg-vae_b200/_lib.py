@@ -130,7 +130,7 @@ EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count",
            "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_offset", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward", "cdg_pendulum_ready_events_enable", "cdg_pendulum_ready_event", "cdg_stream_wait_event",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
-           "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_tabular_const_params", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
+           "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_tabular_const_params", "cdg_tabular_tvae_tile", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
            "cdg_celeba_workspace_bytes", "cdg_celeba_step", "cdg_celeba_generator_streams", "cdg_conv2d_workspace_bytes", "cdg_conv2d_forward",
            "cdg_conv2d_dgrad", "cdg_split_bf16", "cdg_gemm_bsplit", "cdg_gemm_planes", "cdg_gemm_planes_acc", "cdg_tvae_transform", "cdg_tvae_inverse_transform",
            "cdg_gumbel_argmax", "cdg_pixels_to_float", "cdg_pixels_gather_to_float"]

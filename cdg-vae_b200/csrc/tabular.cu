@@ -378,6 +378,8 @@ extern "C" int64_t cdg_tabular_workspace_bytes(const cdg_tabular_plan* p, int64_
     return 256;     // the double-precision loss accumulators
 }
 
+static int g_tvae_tile = 1;
+
 static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, int deterministic, void* stream) {
     CDG_REQUIRE(p && io, "null argument");
     CDG_REQUIRE(io->params && io->x && io->workspace, "null buffer");
@@ -405,7 +407,7 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
     static const bool generic_only = exp_switch("CDG_TAB_GENERIC", 0) != 0;
     if (generic_only ||
         !(launch_tab_const(a, s) || launch_tab_fixed(a, (unsigned)blocks, smem, s) ||
-          (exp_switch("CDG_TVAE_ROW", 0) == 0 && launch_tvae_tile(a, s)) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
+          (g_tvae_tile && launch_tvae_tile(a, s)) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
         tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
     CDG_CHECK_LAUNCH();
     if (io->logs)
@@ -415,6 +417,7 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
 }
 
 extern "C" void cdg_tabular_const_params(int32_t on) { set_tab_const_params(on); }
+extern "C" void cdg_tabular_tvae_tile(int32_t on) { g_tvae_tile = on; }
 
 extern "C" int cdg_tabular_forward_backward(cdg_tabular_plan* p, const cdg_tabular_io* io, void* stream) {
     return tab_run(p, io, 1, 0, stream);
