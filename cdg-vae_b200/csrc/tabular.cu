@@ -378,7 +378,7 @@ extern "C" int64_t cdg_tabular_workspace_bytes(const cdg_tabular_plan* p, int64_
     return 256;     // the double-precision loss accumulators
 }
 
-static int g_tvae_tile = 1;
+static int g_tvae_tile = 1;        // 2 = mma.sync fragments (same speed on loan-shaped, slower on covtype-shaped tables: DESIGN 4.8)
 
 static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, int deterministic, void* stream) {
     CDG_REQUIRE(p && io, "null argument");
@@ -407,7 +407,8 @@ static int tab_run(cdg_tabular_plan* p, const cdg_tabular_io* io, int do_bwd, in
     static const bool generic_only = exp_switch("CDG_TAB_GENERIC", 0) != 0;
     if (generic_only ||
         !(launch_tab_const(a, s) || launch_tab_fixed(a, (unsigned)blocks, smem, s) ||
-          (g_tvae_tile && launch_tvae_tile(a, s)) || launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
+          (g_tvae_tile == 2 && launch_tvae_mma(a, s)) || (g_tvae_tile >= 1 && launch_tvae_tile(a, s)) ||
+          launch_tvae_fixed(a, (unsigned)blocks, smem, s)))
         tab_step_kernel<<<(unsigned)blocks, TAB_THREADS, smem, s>>>(a);
     CDG_CHECK_LAUNCH();
     if (io->logs)

@@ -248,8 +248,9 @@ int cdg_tabular_forward_backward(cdg_tabular_plan* p, const cdg_tabular_io* io, 
 /* The loan / adult step keeps its parameters in __constant__ memory (copied in front of every launch, stream-ordered).
  * A process that steps two tabular models concurrently on DIFFERENT streams turns this off (0): shared-memory kernels. */
 void cdg_tabular_const_params(int32_t on);
-/* CDG-TVAE step: 1 (default) = the warp-cooperative kernel (a warp owns 32 rows, tvae_tile.cu), 0 = one row per thread
- * (tvae_fixed.cu).  Same arithmetic per element; kept switchable for the route-equivalence test. */
+/* CDG-TVAE step: 1 (default) = a warp owns 32 rows, every Linear layer a register-tiled fp32 product over shared-memory
+ * slabs (tvae_tile.cu); 2 = the same organisation with mma.sync 3xTF32 fragments (tvae_mma.cu: measured no faster);
+ * 0 = one row per thread (tvae_fixed.cu).  Kept switchable for the route-equivalence tests. */
 void cdg_tabular_tvae_tile(int32_t on);
 int cdg_tabular_forward(cdg_tabular_plan* p, const cdg_tabular_io* io, int32_t deterministic, void* stream);
 

@@ -3,7 +3,7 @@ gives, on ragged batches, and stay within the 1e-4 contract of the oracle.
 
   * loan / adult step: parameters in __constant__ memory + register-held products (tabular_const.cu) vs the shared-memory
     kernel (tabular_fixed.cu), including rows driven into sigmoid saturation (the reference's -100 clamp / zero gradient);
-  * CDG-TVAE step: warp-cooperative tile kernel (tvae_tile.cu) vs one row per thread (tvae_fixed.cu), batches of 1 / 33 / 1000;
+  * CDG-TVAE step: warp-cooperative tile kernel (tvae_tile.cu) vs one row per thread (tvae_fixed.cu), batches of 1 / 33 / 1000, and the mma.sync 3xTF32 kernel (tvae_mma.cu) vs both;
   * CelebA step: the five generators on five streams vs everything on the caller's stream;
   * graphs that read the caller's tensors in place: same trajectory as eager steps, and data changed in place is seen.
 """
@@ -104,7 +104,7 @@ def test_tvae_tile_route_matches_row_route_and_oracle(kind, rows):
     x, y, nz = orc.synth_tvae(kind, rows, 91, 92)
     out = {}
     try:
-        for route in (1, 0):
+        for route in (2, 1, 0):
             _lib().cdg_tabular_tvae_tile(route)
             model, opt, cfg, oil, mask, Bm = _tvae_model(kind)
             model.noise_fn = lambda n, d: nz
@@ -112,12 +112,15 @@ def test_tvae_tile_route_matches_row_route_and_oracle(kind, rows):
             out[route] = (logs, _grads(model))
     finally:
         _lib().cdg_tabular_tvae_tile(1)
-    (l1, g1), (l0, g0) = out[1], out[0]
+    (l0, g0) = out[0]
     tol = 2e-5
-    for k in l0:
-        assert abs(l1[k][0] - l0[k][0]) <= tol * abs(l0[k][0]) + 1e-7, (k, l1[k][0], l0[k][0])
-    for n in g0:
-        assert rel(g1[n], g0[n]) < tol or float((g1[n] - g0[n]).abs().max()) < 1e-7, (n, rel(g1[n], g0[n]))
+    for route in (2, 1):                                   # tensor-pipe fragments (3xTF32), fp32 register tiles
+        l1, g1 = out[route]
+        for k in l0:
+            assert abs(l1[k][0] - l0[k][0]) <= tol * abs(l0[k][0]) + 1e-7, (route, k, l1[k][0], l0[k][0])
+        for n in g0:
+            assert rel(g1[n], g0[n]) < tol or float((g1[n] - g0[n]).abs().max()) < 1e-7, (route, n, rel(g1[n], g0[n]))
+    l1, g1 = out[1]
     spec = orc.tvae_spec(cfg, mask, oil)
     params = orc.init_params(spec, cfg["seed"])
     ol, og, _ = orc.train_step(params, orc.new_adam_state(params), spec, orc.i_b_inv(Bm), x, y, nz)
