@@ -127,7 +127,7 @@ class TvaeTransformConfig(C.Structure):
 
 # every symbol include/cdgvae.h declares
 EXPORTS = ["cdg_last_error", "cdg_version", "cdg_device_ok", "cdg_launch_count", "cdg_launch_count_add", "cdg_abi_sizeof", "cdg_flow_apply", "cdg_pendulum_profile_enable",
-           "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_pendulum_create",
+           "cdg_pendulum_profile_read", "cdg_adam_step", "cdg_allreduce_oneshot", "cdg_pendulum_create",
            "cdg_pendulum_destroy", "cdg_pendulum_workspace_bytes", "cdg_pendulum_workspace_offset", "cdg_pendulum_workspace_bytes_infomax", "cdg_pendulum_forward_backward", "cdg_pendulum_ready_events_enable", "cdg_pendulum_ready_event", "cdg_stream_wait_event",
            "cdg_pendulum_forward", "cdg_tabular_create", "cdg_tabular_destroy", "cdg_tabular_workspace_bytes",
            "cdg_tabular_forward_backward", "cdg_tabular_forward", "cdg_tabular_const_params", "cdg_tabular_tvae_tile", "cdg_gemm", "cdg_celeba_create", "cdg_celeba_destroy",
@@ -195,6 +195,8 @@ def lib():
     L.cdg_pendulum_forward_backward.argtypes = [C.c_void_p, C.POINTER(PendulumIO), C.c_void_p]
     L.cdg_pendulum_forward.argtypes = [C.c_void_p, C.POINTER(PendulumFwdIO), C.c_void_p]
     L.cdg_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamArgs), C.c_void_p]
+    L.cdg_allreduce_oneshot.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p]
     L.cdg_tabular_workspace_bytes.restype = C.c_int64
     L.cdg_tabular_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
     L.cdg_tabular_create.argtypes = [C.POINTER(TabularConfig), C.POINTER(C.c_void_p)]

@@ -1,0 +1,72 @@
+// One-shot all-reduce(sum) of a small gradient arena over NVLink peer memory: the tabular models'
+// whole arena is 2.4 KB, CDG-TVAE's 12 KB, CelebA's trainable part 49 KB.  An NCCL all-reduce of that size costs ~40 us inside
+// the step's CUDA graph at 8 GPUs (tabular adult at 2^22 rows per GPU: 0.182 -> 0.223 ms per step); here ONE kernel of one CTA per
+// rank publishes the local gradients in a symmetric buffer, raises a flag in every peer's buffer, waits for the peers' flags and
+// sums the W copies with peer loads in rank order (so every rank computes bit-identical sums).
+//   buffer layout per rank (floats): [slot 0: n_max][slot 1: n_max][flags: 64 x uint32]; flags[p] = last step rank p published.
+//   Two slots: a rank may already publish step s + 1 while a peer still reads its step-s copy; it cannot reach step s + 2
+//   before that peer has raised its flag for s + 1, i.e. has finished reading step s.
+//   The step counter lives in device memory and is advanced by the kernel itself: the launch is graph-replayable.
+#include "common.cuh"
+
+namespace cdg {
+
+constexpr int OS_MAX_WORLD = 16;
+
+struct OneShotArgs {
+    float* grads;
+    int64_t n, n_max;
+    float* peers[OS_MAX_WORLD];          // symmetric buffer of every rank as mapped into this process
+    int world, rank;
+    uint32_t* step;                      // device counter (starts at 0)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) oneshot_allreduce_kernel(OneShotArgs a) {
+    const uint32_t s = *a.step + 1;
+    const int64_t slot = (int64_t)(s & 1) * a.n_max;
+    float* mine = a.peers[a.rank];
+    for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) mine[slot + i] = a.grads[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        uint32_t* peer_flags = reinterpret_cast<uint32_t*>(a.peers[threadIdx.x] + 2 * a.n_max);
+        st_release_sys(peer_flags + a.rank, s);                                   // "rank's copy of step s is visible"
+        const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(mine + 2 * a.n_max);
+        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - s) < 0) { }      // peer threadIdx.x has published step s
+    }
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < a.world; ++p) acc += __ldcg(a.peers[p] + slot + i);   // rank order: identical sums everywhere
+        a.grads[i] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.step = s;
+}
+
+}  // namespace cdg
+
+using namespace cdg;
+
+extern "C" int cdg_allreduce_oneshot(float* grads, int64_t n, int64_t n_max, const uint64_t* peer_ptrs, int32_t world, int32_t rank,
+                                     uint32_t* step_counter, void* stream) {
+    CDG_REQUIRE(grads && peer_ptrs && step_counter, "null argument");
+    CDG_REQUIRE(world >= 1 && world <= OS_MAX_WORLD && rank >= 0 && rank < world, "world / rank out of range");
+    CDG_REQUIRE(n >= 0 && n <= n_max, "arena longer than the symmetric buffer's slot");
+    if (n == 0 || world == 1) return CDG_OK;
+    OneShotArgs a;
+    a.grads = grads; a.n = n; a.n_max = n_max; a.world = world; a.rank = rank; a.step = step_counter;
+    for (int p = 0; p < world; ++p) a.peers[p] = reinterpret_cast<float*>(peer_ptrs[p]);
+    oneshot_allreduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    CDG_CHECK_LAUNCH();
+    return CDG_OK;
+}

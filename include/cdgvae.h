@@ -78,6 +78,17 @@ int cdg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   const cdg_adam_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data parallel (no reference counterpart: the reference is single-device).  One-shot all-reduce(sum) of a SMALL gradient
+ * arena (tabular 2.4 KB, CDG-TVAE 12 KB, CelebA's trainable part 49 KB) over NVLink peer memory, one kernel per rank:
+ * every rank owns a symmetric buffer of 2 * n_max floats + 64 uint32 flags (zeroed once, mapped into every peer process);
+ * peer_ptrs[p] (HOST array, `world` entries) is rank p's buffer as mapped into THIS process.  `step_counter` is one device
+ * uint32 (zeroed once) the kernel advances itself, so the launch can be captured and replayed.  Every rank must enqueue the
+ * same sequence of calls.  Sums are taken in rank order: all ranks end with bit-identical gradients.
+ * ---------------------------------------------------------------------------------------- */
+int cdg_allreduce_oneshot(float* grads, int64_t n, int64_t n_max, const uint64_t* peer_ptrs, int32_t world, int32_t rank,
+                          uint32_t* step_counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pendulum CDG-VAE (modules/model.py:208-304 CDGVAE; modules/train.py:150-282).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
