@@ -31,6 +31,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 __global__ void __launch_bounds__(1024) oneshot_allreduce_kernel(OneShotArgs a) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
     const uint32_t s = *a.step + 1;
     const int64_t slot = (int64_t)(s & 1) * a.n_max;
     float* mine = a.peers[a.rank];
@@ -41,13 +43,19 @@ __global__ void __launch_bounds__(1024) oneshot_allreduce_kernel(OneShotArgs a) 
         uint32_t* peer_flags = reinterpret_cast<uint32_t*>(a.peers[threadIdx.x] + 2 * a.n_max);
         st_release_sys(peer_flags + a.rank, s);                                   // "rank's copy of step s is visible"
         const uint32_t* my_flags = reinterpret_cast<const uint32_t*>(mine + 2 * a.n_max);
-        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - s) < 0) { }      // peer threadIdx.x has published step s
+        // peer threadIdx.x has published step s; a peer that never comes (its process died) must not hang this GPU:
+        // after ~3 s of spinning the gradients are poisoned with NaN instead, which the next logged loss makes visible
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - s) < 0) {
+            if (clock64() - t0 > 6000000000LL) { timed_out = 1; break; }
+        }
     }
     __syncthreads();
+    const bool dead = timed_out != 0;
     for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
         float acc = 0.f;
         for (int p = 0; p < a.world; ++p) acc += __ldcg(a.peers[p] + slot + i);   // rank order: identical sums everywhere
-        a.grads[i] = acc;
+        a.grads[i] = dead ? __int_as_float(0x7fc00000) : acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) *a.step = s;
