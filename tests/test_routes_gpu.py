@@ -196,3 +196,58 @@ def test_celeba_generator_streams_match_single_stream():
         assert rel(ga[n], gb[n]) < 1e-2, (n, rel(ga[n], gb[n]))
     for k in sb:                                                          # running statistics, u / v vectors, parameters
         assert rel(sa[k], sb[k]) < 1e-3, k
+
+
+def _step_rows(model, x, y, nz, **aux):
+    width = 4 + model.config["node"]
+    row = torch.zeros(width, device="cuda")
+    model.forward_backward(x, y, nz, row, **aux)
+    torch.cuda.synchronize()
+    return row.clone(), model._grads.clone()
+
+
+@pytest.mark.parametrize("family,rows", [("adult", 1 << 22), ("loan", (1 << 21) + 70), ("tvae", 1 << 20)])
+def test_benchmarked_sizes_mean_of_shards(family, rows):
+    """The bench's own batch sizes (2^22 tabular rows, 2^20 CDG-TVAE rows; one ragged): every loss is a batch mean of per-row
+    terms, so logs and gradients of the whole batch equal the row-weighted average over its two parts -- and a batch made of
+    one small block repeated gives that block's logs and gradients (which the oracle checks on the block)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    if family == "tvae":
+        model, opt, cfg, oil, mask, Bm = _tvae_model("loan")
+        blk_x, blk_y, blk_n = (t.cuda() for t in orc.synth_tvae("loan", 4096, 31, 32))
+        aux = dict(output_info_list=[[Span(*s) for s in col] for col in oil])
+        spec = orc.tvae_spec(cfg, mask, oil)
+        seed = cfg["seed"]
+    else:
+        model, opt, cfg = _tab_model(family)
+        blk_x, blk_y, blk_n = (t.cuda() for t in orc.synth_tabular(family, 4096, 31, 32))
+        aux = dict(flatten_topology=FT[family])
+        spec = orc.tabular_spec(_tab_cfg(family), MASK[family], FT[family])
+        Bm = orc.tabular_B(family)
+        seed = 3
+    reps = rows // 4096
+    x = blk_x.repeat(reps, 1); y = blk_y.repeat(reps, 1); nz = blk_n.repeat(reps, 1)
+    tail = rows - reps * 4096
+    if tail:
+        x = torch.cat([x, blk_x[:tail]]); y = torch.cat([y, blk_y[:tail]]); nz = torch.cat([nz, blk_n[:tail]])
+    perm = torch.randperm(rows, device="cuda", generator=g)                 # rows of a block are not neighbours in the batch
+    x, y, nz = x[perm].contiguous(), y[perm].contiguous(), nz[perm].contiguous()
+    row, grads = _step_rows(model, x, y, nz, **aux)
+    h = rows // 2 + 37
+    ra, ga = _step_rows(model, x[:h], y[:h], nz[:h], **aux)
+    rb, gb = _step_rows(model, x[h:], y[h:], nz[h:], **aux)
+    wa, wb = h / rows, (rows - h) / rows
+    assert rel(row, wa * ra + wb * rb) < 2e-5
+    assert rel(grads, wa * ga + wb * gb) < 2e-5
+    if not tail:
+        # the oracle on the 4,096-row block: same logs, same gradients (a batch mean does not see the repetition)
+        params = orc.init_params(spec, seed)
+        ol, og, _ = orc.train_step(params, orc.new_adam_state(params), spec, orc.i_b_inv(Bm), blk_x.cpu(), blk_y.cpu(), blk_n.cpu())
+        keys = ["loss", "recon", "KL", "alignment"]
+        for j, k in enumerate(keys):
+            assert abs(float(row[j]) - ol[k]) <= RTOL * abs(ol[k]) + 1e-6, (k, float(row[j]), ol[k])
+        for n, p in model.named_parameters():
+            if og.get(n) is None or (n.startswith("flows.") and p.numel() <= 2):
+                continue
+            o, k = model._offsets[n], p.numel()
+            assert rel(grads[o:o + k].cpu(), og[n]) < RTOL or float((grads[o:o + k].cpu() - og[n].reshape(-1)).abs().max()) < 1e-6, n
