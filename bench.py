@@ -193,7 +193,9 @@ def run_reference(args):
     if not args.no_workloads and ref.available():
         w = {}
         for name, fn in (("tabular_adult", lambda: ref.tabular("adult", 1 << 16, target_s=5.0, steps=40)),
+                         ("tabular_covtype", lambda: ref.tabular("covtype", 1 << 16, target_s=4.0, steps=40)),
                          ("tvae_loan", lambda: ref.tvae("loan", 1 << 15, target_s=5.0, steps=40)),
+                         ("tvae_covtype", lambda: ref.tvae("covtype", 1 << 15, target_s=4.0, steps=40)),
                          ("celeba_b16", lambda: ref.celeba(16, warmup=1, steps=2)),
                          ("pendulum_b128", lambda: ref.pendulum_b128(128, target_s=5.0, steps=60))):
             try:
@@ -217,7 +219,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="headline workload only")
-    ap.add_argument("--workloads", default="tabular_adult,tvae_loan,celeba_b16,pendulum_b128")
+    ap.add_argument("--workloads", default="tabular_adult,tabular_covtype,tvae_loan,tvae_covtype,celeba_b16,pendulum_b128")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the informational stock-PyTorch run of the reference on the GPU")
     args = ap.parse_args()
     if args.impl == "reference":
