@@ -433,7 +433,7 @@ def main():
         want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
         table = {"tabular_adult": lambda: wl.tabular(ctx, "adult", 1 << 22, steps=max(args.steps, 20), cpu=want_cpu),
                  "tabular_loan": lambda: wl.tabular(ctx, "loan", 1 << 22, steps=max(args.steps, 20), cpu=want_cpu),
-                 "tabular_covtype": lambda: wl.tabular(ctx, "covtype", 1 << 20, steps=max(args.steps, 20), cpu=want_cpu),
+                 "tabular_covtype": lambda: wl.tabular(ctx, "covtype", 1 << 21, steps=max(args.steps, 20), cpu=want_cpu),
                  "tvae_loan": lambda: wl.tvae(ctx, "loan", 1 << 20, steps=max(args.steps, 10), cpu=want_cpu),
                  "tvae_covtype": lambda: wl.tvae(ctx, "covtype", 1 << 20, steps=max(args.steps, 10), cpu=want_cpu),
                  "celeba_b16": lambda: wl.celeba(ctx, 16, steps=max(args.steps, 10), cpu=want_cpu),

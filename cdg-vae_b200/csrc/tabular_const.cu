@@ -353,7 +353,8 @@ static bool canonical(const cdg_tabular_config& c) {
 }
 
 static int g_const_params = 1;
-void set_tab_const_params(int on) { g_const_params = on; }
+void set_tab_fixed_const(int on);
+void set_tab_const_params(int on) { g_const_params = on; set_tab_fixed_const(on); }
 
 // returns true when the step was launched here
 bool launch_tab_const(const TabArgs& a, cudaStream_t s) {

@@ -29,6 +29,40 @@ struct NetCov {
     __host__ __device__ static constexpr int col(int k) { return k < 3 ? k : k == 3 ? 4 : k == 4 ? 5 : 6; }
 };
 
+// CP ("constant parameters"): the arena is copied into __constant__ memory in front of the launch and every weight is a
+// compile-time offset into it (FFMA reads it as a constant-bank operand: no load instruction; the shared-memory version spends
+// 280 LDS per row on weights), exp / log / reciprocal run on the SFU, the alignment BCE is evaluated in its logits form (as in
+// tabular_const.cu, same saturation behaviour).  Only for the arena layout the drop-in covtype model produces (checked at
+// launch); any other layout keeps the shared-memory path.
+constexpr int TF_MAX_PARAMS = 2048;
+__constant__ float c_tabfix[TF_MAX_PARAMS];
+struct LinOff { int w, b; };
+template <bool CP> __device__ __forceinline__ float par(const float* sp, int idx) {
+    if constexpr (CP) return c_tabfix[idx];
+    else return sp[idx];
+}
+template <bool CP> __device__ __forceinline__ float ex(float x) {
+    if constexpr (CP) return __expf(x);
+    else return expf(x);
+}
+// canonical covtype arena (tabular/modules/model.py:245-298 in registration order, one or two 32-float slots per tensor)
+struct CovOff {
+    __host__ __device__ static constexpr int enc_w(int l) { return 64 * l; }
+    __host__ __device__ static constexpr int enc_b(int l) { return l == 3 ? 256 : 64 * l + 32; }
+    __host__ __device__ static constexpr int flow(int j) { return 288 + 32 * j; }
+    __host__ __device__ static constexpr int dec_w(int k, int l) { return 480 + 192 * k + 64 * l; }
+    __host__ __device__ static constexpr int dec_b(int k, int l) { return dec_w(k, l) + 32; }
+    static constexpr int NPARAMS = 1920;
+};
+template <bool CP> __device__ __forceinline__ LinOff enc_lin(const cdg_tabular_config& c, int l) {
+    if constexpr (CP) return LinOff{CovOff::enc_w(l), CovOff::enc_b(l)};
+    else return LinOff{(int)c.enc[l].w, (int)c.enc[l].b};
+}
+template <bool CP> __device__ __forceinline__ LinOff dec_lin(const cdg_tabular_config& c, int k, int l) {
+    if constexpr (CP) return LinOff{CovOff::dec_w(k, l), CovOff::dec_b(k, l)};
+    else return LinOff{(int)c.dec[k][l].w, (int)c.dec[k][l].b};
+}
+
 // flat positions of the parameter-gradient products a thread collects before the warp reduce-scatter
 template <class N> struct Pos {
     __host__ __device__ static constexpr int dec_np(int k) {
@@ -69,20 +103,20 @@ __device__ __forceinline__ void flush_products(float (&gp)[NPAD], const int* pos
     }
 }
 
-template <int IN, int OUT, bool ACT>
-__device__ __forceinline__ void fc(const float* sp, const cdg_linear& L, const float (&hin)[IN], float (&hout)[OUT]) {
+template <int IN, int OUT, bool ACT, bool CP = false>
+__device__ __forceinline__ void fc(const float* sp, const LinOff L, const float (&hin)[IN], float (&hout)[OUT]) {
 #pragma unroll
     for (int o = 0; o < OUT; ++o) {
-        float s = sp[L.b + o];
+        float s = par<CP>(sp, L.b + o);
 #pragma unroll
-        for (int i = 0; i < IN; ++i) s = fmaf(sp[L.w + o * IN + i], hin[i], s);
-        hout[o] = ACT ? (s > 0.f ? s : expf(s) - 1.f) : s;
+        for (int i = 0; i < IN; ++i) s = fmaf(par<CP>(sp, L.w + o * IN + i), hin[i], s);
+        hout[o] = ACT ? (s > 0.f ? s : ex<CP>(s) - 1.f) : s;
     }
 }
 // delta: dL/d(pre-activation outputs).  Accumulates dW, db; gin = dL/d(hin) times ELU'(hin) when HIN_ACT.
 // ACC: the products are added to gp (a thread keeps its products over all of its rows and the warp reduction runs once).
-template <int IN, int OUT, bool HIN_ACT, bool NEED_GIN, int POS, bool ACC, int NPAD>
-__device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const cdg_linear& L, const float (&hin)[IN],
+template <int IN, int OUT, bool HIN_ACT, bool NEED_GIN, int POS, bool ACC, bool CP = false, int NPAD>
+__device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const LinOff L, const float (&hin)[IN],
                                        const float (&delta)[OUT], float (&gin)[IN]) {
     static_assert(POS + OUT * IN + OUT <= NPAD, "gradient product array too small");
 #pragma unroll
@@ -93,7 +127,7 @@ __device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const
 #pragma unroll
         for (int i = 0; i < IN; ++i) {
             gp[POS + o * IN + i] = ACC ? fmaf(delta[o], hin[i], gp[POS + o * IN + i]) : delta[o] * hin[i];   // weight
-            if (NEED_GIN) gin[i] = fmaf(delta[o], sp[L.w + o * IN + i], gin[i]);
+            if (NEED_GIN) gin[i] = fmaf(delta[o], par<CP>(sp, L.w + o * IN + i), gin[i]);
         }
     }
     if (HIN_ACT && NEED_GIN) {
@@ -103,22 +137,22 @@ __device__ __forceinline__ void fc_bwd(const float* sp, float (&gp)[NPAD], const
 }
 
 // decoder k (compile-time index, so that its output width m(k) and column offset col(k) are constants)
-template <class N, int k>
+template <class N, int k, bool CP>
 __device__ __forceinline__ void dec_forward(const float* sp, const cdg_tabular_config& c, const float* z,
                                             float (&a1)[N::K][N::DH], float (&a2)[N::K][N::DH], float (&xh)[N::OUT]) {
     const float zin[1] = {z[k]};
-    fc<1, N::DH, true>(sp, c.dec[k][0], zin, a1[k]);
+    fc<1, N::DH, true, CP>(sp, dec_lin<CP>(c, k, 0), zin, a1[k]);
     float out[N::m(k)];
     if constexpr (N::ND == 3) {
-        fc<N::DH, N::DH, true>(sp, c.dec[k][1], a1[k], a2[k]);
-        fc<N::DH, N::m(k), false>(sp, c.dec[k][2], a2[k], out);
+        fc<N::DH, N::DH, true, CP>(sp, dec_lin<CP>(c, k, 1), a1[k], a2[k]);
+        fc<N::DH, N::m(k), false, CP>(sp, dec_lin<CP>(c, k, 2), a2[k], out);
     } else {
-        fc<N::DH, N::m(k), false>(sp, c.dec[k][1], a1[k], out);
+        fc<N::DH, N::m(k), false, CP>(sp, dec_lin<CP>(c, k, 1), a1[k], out);
     }
 #pragma unroll
     for (int j = 0; j < N::m(k); ++j) xh[N::col(k) + j] = out[j];
 }
-template <class N, int k, bool ACC>
+template <class N, int k, bool ACC, bool CP>
 __device__ __forceinline__ void dec_backward(const float* sp, float (&gp)[Pos<N>::NA_PAD], const cdg_tabular_config& c,
                                              const float* z, float (&a1)[N::K][N::DH], float (&a2)[N::K][N::DH],
                                              const float (&gx)[N::OUT], float* gz) {
@@ -129,12 +163,12 @@ __device__ __forceinline__ void dec_backward(const float* sp, float (&gp)[Pos<N>
     // flat order inside decoder k: layer 0 (weights, bias), [layer 1], last layer
     constexpr int P0 = Pos<N>::dec_off(k), P1 = P0 + 2 * N::DH, P2 = P1 + (N::ND == 3 ? N::DH * N::DH + N::DH : 0);
     if constexpr (N::ND == 3) {
-        fc_bwd<N::DH, N::m(k), true, true, P2, ACC>(sp, gp, c.dec[k][2], a2[k], dout, g2);
-        fc_bwd<N::DH, N::DH, true, true, P1, ACC>(sp, gp, c.dec[k][1], a1[k], g2, g1);
+        fc_bwd<N::DH, N::m(k), true, true, P2, ACC, CP>(sp, gp, dec_lin<CP>(c, k, 2), a2[k], dout, g2);
+        fc_bwd<N::DH, N::DH, true, true, P1, ACC, CP>(sp, gp, dec_lin<CP>(c, k, 1), a1[k], g2, g1);
     } else {
-        fc_bwd<N::DH, N::m(k), true, true, P2, ACC>(sp, gp, c.dec[k][1], a1[k], dout, g1);
+        fc_bwd<N::DH, N::m(k), true, true, P2, ACC, CP>(sp, gp, dec_lin<CP>(c, k, 1), a1[k], dout, g1);
     }
-    fc_bwd<1, N::DH, false, true, P0, ACC>(sp, gp, c.dec[k][0], zin, g1, gzin);
+    fc_bwd<1, N::DH, false, true, P0, ACC, CP>(sp, gp, dec_lin<CP>(c, k, 0), zin, g1, gzin);
     gz[k] = gzin[0];
 }
 // arena offsets of decoder k's parameters in the same flat order
@@ -151,20 +185,20 @@ template <class N, int... Ks>
 __device__ __forceinline__ void dec_positions_all(std::integer_sequence<int, Ks...>, const cdg_tabular_config& c, int* pos2off) {
     (dec_positions<N, Ks>(c, pos2off), ...);
 }
-template <class N, int... Ks>
+template <class N, bool CP, int... Ks>
 __device__ __forceinline__ void dec_forward_all(std::integer_sequence<int, Ks...>, const float* sp, const cdg_tabular_config& c,
                                                 const float* z, float (&a1)[N::K][N::DH], float (&a2)[N::K][N::DH],
                                                 float (&xh)[N::OUT]) {
-    (dec_forward<N, Ks>(sp, c, z, a1, a2, xh), ...);
+    (dec_forward<N, Ks, CP>(sp, c, z, a1, a2, xh), ...);
 }
-template <class N, bool ACC, int... Ks>
+template <class N, bool ACC, bool CP, int... Ks>
 __device__ __forceinline__ void dec_backward_all(std::integer_sequence<int, Ks...>, const float* sp, float (&gp)[Pos<N>::NA_PAD],
                                                  const cdg_tabular_config& c, const float* z, float (&a1)[N::K][N::DH],
                                                  float (&a2)[N::K][N::DH], const float (&gx)[N::OUT], float* gz) {
-    (dec_backward<N, Ks, ACC>(sp, gp, c, z, a1, a2, gx, gz), ...);
+    (dec_backward<N, Ks, ACC, CP>(sp, gp, c, z, a1, a2, gx, gz), ...);
 }
 
-template <class N>
+template <class N, bool CP = false>
 __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
     extern __shared__ float smem[];
     const cdg_tabular_config& c = a.c;
@@ -225,13 +259,13 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
         float x[N::D], h0[N::EH], h1[N::EH], h2[N::EH], ml[2 * d];
 #pragma unroll
         for (int i = 0; i < N::D; ++i) x[i] = a.x[br * N::D + i];
-        fc<N::D, N::EH, true>(sp, c.enc[0], x, h0);
+        fc<N::D, N::EH, true, CP>(sp, enc_lin<CP>(c, 0), x, h0);
         if constexpr (N::NE == 4) {
-            fc<N::EH, N::EH, true>(sp, c.enc[1], h0, h1);
-            fc<N::EH, N::EH, true>(sp, c.enc[2], h1, h2);
-            fc<N::EH, 2 * d, false>(sp, c.enc[3], h2, ml);
+            fc<N::EH, N::EH, true, CP>(sp, enc_lin<CP>(c, 1), h0, h1);
+            fc<N::EH, N::EH, true, CP>(sp, enc_lin<CP>(c, 2), h1, h2);
+            fc<N::EH, 2 * d, false, CP>(sp, enc_lin<CP>(c, 3), h2, ml);
         } else {
-            fc<N::EH, 2 * d, false>(sp, c.enc[1], h0, ml);
+            fc<N::EH, 2 * d, false, CP>(sp, enc_lin<CP>(c, 1), h0, ml);
         }
 
         // ---- latent block ----
@@ -244,16 +278,53 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
             if (i < d) {
                 mean[i] = ml[i < d ? i : 0]; lv[i] = ml[i < d ? d + i : 0];
                 nz[i] = a.deterministic ? 0.f : a.noise[br * d + i];
-                const float ev = expf(lv[i]);
-                eps[i] = a.deterministic ? mean[i] : mean[i] + expf(lv[i] / 2.f) * nz[i];
+                const float ev = ex<CP>(lv[i]);
+                eps[i] = a.deterministic ? mean[i] : mean[i] + ex<CP>(lv[i] / 2.f) * nz[i];
                 kl += mean[i] * mean[i] - lv[i] + ev;
                 var_acc[i < d ? i : 0] += vm * ev;
             }
         }
         kl_acc += (double)(vm * 0.5f * (kl - (float)d));
+        const float ascale = c.lambda_ * invB;
+        if constexpr (CP) {
+            // linear SCM, constants from the constant bank; BCE in logits form with the reference's fp32 saturation behaviour
+#pragma unroll
+            for (int j = 0; j < CDG_MAX_NODE; ++j) {
+                u[j] = u2[j] = z[j] = z2[j] = gu2[j] = 0.f;
+                if (j < d) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < d; ++i) {
+                        s1 = fmaf(eps[i], c.I_B_inv[i * d + (j < d ? j : 0)], s1);
+                        s2 = fmaf(mean[i], c.I_B_inv[i * d + (j < d ? j : 0)], s2);
+                    }
+                    u[j] = s1; u2[j] = s2;
+                    const float fw = c_tabfix[CovOff::flow(j < d ? j : 0)], fb = c_tabfix[CovOff::flow(j < d ? j : 0) + 1];
+                    z[j] = fmaf(fw, s1, fb);
+                    z2[j] = fmaf(fw, s2, fb);
+                    if (a.y) {
+                        const float e = __expf(-fabsf(z2[j]));
+                        const float r = __fdividef(1.f, 1.f + e);
+                        const float yh = z2[j] >= 0.f ? r : e * r;
+                        const float om = 1.f - yh;
+                        const float sp1 = __logf(1.f + e);
+                        const float l_yh = yh <= 0.f ? -100.f : fmaxf(-(fmaxf(-z2[j], 0.f) + sp1), -100.f);
+                        const float l_om = om <= 0.f ? -100.f : fmaxf(-(fmaxf(z2[j], 0.f) + sp1), -100.f);
+                        const float yy = a.y[br * d + j];
+                        al += (yy - 1.f) * l_om - yy * l_yh;
+                        const float t = om * yh;
+                        const float gzz = vm * ascale * (yh - yy) * (t >= 1e-12f ? 1.f : t * 1e12f);
+                        if (a.do_bwd) {
+                            fg.a[j][0] += gzz * s2;
+                            fg.a[j][1] += gzz;
+                            gu2[j] = gzz * fw;
+                        }
+                    }
+                }
+            }
+        } else {
         matvec_A(ft, d, eps, u);
         matvec_A(ft, d, mean, u2);
-        const float ascale = c.lambda_ * invB;
 #pragma unroll
         for (int j = 0; j < CDG_MAX_NODE; ++j) {
             z[j] = z2[j] = gu2[j] = 0.f;
@@ -269,8 +340,19 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
                 }
             }
         }
+        }
         al_acc += (double)(vm * al);
-        matvec_AT(ft, d, gu2, gal);
+        if constexpr (CP) {
+#pragma unroll
+            for (int i = 0; i < CDG_MAX_NODE; ++i) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int j = 0; j < d; ++j) sacc = fmaf(gu2[j], c.I_B_inv[(i < d ? i : 0) * d + j], sacc);
+                gal[i] = i < d ? sacc : 0.f;
+            }
+        } else {
+            matvec_AT(ft, d, gu2, gal);
+        }
         if (a.latents && valid) {
             float* o = a.latents + b * 6 * d;
 #pragma unroll
@@ -282,7 +364,7 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
 
         // ---- decoders (factor 1 each): hidden activations kept for the backward ----
         float a1[N::K][N::DH], a2[N::K][N::DH], xh[N::OUT], gx[N::OUT];
-        dec_forward_all<N>(std::make_integer_sequence<int, N::K>{}, sp, c, z, a1, a2, xh);
+        dec_forward_all<N, CP>(std::make_integer_sequence<int, N::K>{}, sp, c, z, a1, a2, xh);
         if (a.xhat && valid) {
 #pragma unroll
             for (int j = 0; j < N::OUT; ++j) a.xhat[b * N::OUT + j] = xh[j];
@@ -329,12 +411,12 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
             for (int j = 1; j < 7; ++j) mx = fmaxf(mx, xh[7 + j]);
             float se = 0.f;
 #pragma unroll
-            for (int j = 0; j < 7; ++j) se += expf(xh[7 + j] - mx);
-            const float lse = mx + logf(se);
+            for (int j = 0; j < 7; ++j) se += ex<CP>(xh[7 + j] - mx);
+            const float lse = mx + (CP ? __logf(se) : logf(se));
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 if (j == cls) rec += lse - xh[7 + j];
-                gx[7 + j] = (expf(xh[7 + j] - lse) - (j == cls ? 1.f : 0.f)) * invB;
+                gx[7 + j] = (ex<CP>(xh[7 + j] - lse) - (j == cls ? 1.f : 0.f)) * invB;
             }
         }
         rec_acc += (double)(vm * rec);
@@ -347,45 +429,66 @@ __global__ void __launch_bounds__(TAB_THREADS) tab_fixed_kernel(TabArgs a) {
 #pragma unroll
         for (int i = 0; i < CDG_MAX_NODE; ++i) gz[i] = 0.f;
         if constexpr (ACCUM) {
-            dec_backward_all<N, true>(std::make_integer_sequence<int, N::K>{}, sp, gpa_acc, c, z, a1, a2, gx, gz);
+            dec_backward_all<N, true, CP>(std::make_integer_sequence<int, N::K>{}, sp, gpa_acc, c, z, a1, a2, gx, gz);
         } else {
             float gpa[P::NA_PAD];
 #pragma unroll
             for (int i = P::NA; i < P::NA_PAD; ++i) gpa[i] = 0.f;
-            dec_backward_all<N, false>(std::make_integer_sequence<int, N::K>{}, sp, gpa, c, z, a1, a2, gx, gz);
+            dec_backward_all<N, false, CP>(std::make_integer_sequence<int, N::K>{}, sp, gpa, c, z, a1, a2, gx, gz);
             flush_products<P::NA_PAD>(gpa, posA, sg);
         }
 
         // ---- latent backward ----
         float gu[CDG_MAX_NODE], ge[CDG_MAX_NODE], gml[2 * d];
 #pragma unroll
-        for (int j = 0; j < CDG_MAX_NODE; ++j) gu[j] = j < d ? flow_bwd(ft, c.scm, c.flow_num, j, u[j], gz[j], fg) : 0.f;
-        matvec_AT(ft, d, gu, ge);
+        for (int j = 0; j < CDG_MAX_NODE; ++j) {
+            if constexpr (CP) {
+                gu[j] = 0.f;
+                if (j < d) {
+                    fg.a[j][0] += gz[j] * u[j];
+                    fg.a[j][1] += gz[j];
+                    gu[j] = gz[j] * c_tabfix[CovOff::flow(j < d ? j : 0)];
+                }
+            } else {
+                gu[j] = j < d ? flow_bwd(ft, c.scm, c.flow_num, j, u[j], gz[j], fg) : 0.f;
+            }
+        }
+        if constexpr (CP) {
+#pragma unroll
+            for (int i = 0; i < CDG_MAX_NODE; ++i) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int j = 0; j < d; ++j) sacc = fmaf(gu[j], c.I_B_inv[(i < d ? i : 0) * d + j], sacc);
+                ge[i] = i < d ? sacc : 0.f;
+            }
+        } else {
+            matvec_AT(ft, d, gu, ge);
+        }
         const float kscale = c.beta * invB;
 #pragma unroll
         for (int i = 0; i < d; ++i) {
             gml[i] = ge[i] + vm * kscale * mean[i] + gal[i];
-            gml[d + i] = 0.5f * ge[i] * nz[i] * expf(lv[i] / 2.f) + vm * 0.5f * kscale * (expf(lv[i]) - 1.f);
+            gml[d + i] = 0.5f * ge[i] * nz[i] * ex<CP>(lv[i] / 2.f) + vm * 0.5f * kscale * (ex<CP>(lv[i]) - 1.f);
         }
 
         // ---- encoder backward (no gradient into x) ----
         float gh[N::EH], gdump[N::D];
         if constexpr (ACCUM) {
-            fc_bwd<N::EH, 2 * d, true, true, P::E0, true>(sp, gpb_acc, c.enc[1], h0, gml, gh);
-            fc_bwd<N::D, N::EH, false, false, 0, true>(sp, gpb_acc, c.enc[0], x, gh, gdump);
+            fc_bwd<N::EH, 2 * d, true, true, P::E0, true, CP>(sp, gpb_acc, enc_lin<CP>(c, 1), h0, gml, gh);
+            fc_bwd<N::D, N::EH, false, false, 0, true, CP>(sp, gpb_acc, enc_lin<CP>(c, 0), x, gh, gdump);
         } else {
             float gpb[P::NB_PAD];
 #pragma unroll
             for (int i = P::NB; i < P::NB_PAD; ++i) gpb[i] = 0.f;
             if constexpr (N::NE == 4) {
                 float gh2[N::EH], gh1[N::EH];
-                fc_bwd<N::EH, 2 * d, true, true, P::E0 + 2 * P::EM, false>(sp, gpb, c.enc[3], h2, gml, gh2);
-                fc_bwd<N::EH, N::EH, true, true, P::E0 + P::EM, false>(sp, gpb, c.enc[2], h1, gh2, gh1);
-                fc_bwd<N::EH, N::EH, true, true, P::E0, false>(sp, gpb, c.enc[1], h0, gh1, gh);
+                fc_bwd<N::EH, 2 * d, true, true, P::E0 + 2 * P::EM, false, CP>(sp, gpb, enc_lin<CP>(c, 3), h2, gml, gh2);
+                fc_bwd<N::EH, N::EH, true, true, P::E0 + P::EM, false, CP>(sp, gpb, enc_lin<CP>(c, 2), h1, gh2, gh1);
+                fc_bwd<N::EH, N::EH, true, true, P::E0, false, CP>(sp, gpb, enc_lin<CP>(c, 1), h0, gh1, gh);
             } else {
-                fc_bwd<N::EH, 2 * d, true, true, P::E0, false>(sp, gpb, c.enc[1], h0, gml, gh);
+                fc_bwd<N::EH, 2 * d, true, true, P::E0, false, CP>(sp, gpb, enc_lin<CP>(c, 1), h0, gml, gh);
             }
-            fc_bwd<N::D, N::EH, false, false, 0, false>(sp, gpb, c.enc[0], x, gh, gdump);
+            fc_bwd<N::D, N::EH, false, false, 0, false, CP>(sp, gpb, enc_lin<CP>(c, 0), x, gh, gdump);
             flush_products<P::NB_PAD>(gpb, posB, sg);
         }
     }
@@ -440,8 +543,28 @@ static bool shape_is(const cdg_tabular_config& c) {
     return true;
 }
 
+static bool cov_canonical(const cdg_tabular_config& c) {
+    if (c.scm != CDG_SCM_LINEAR || c.n_params != CovOff::NPARAMS || c.n_params > TF_MAX_PARAMS) return false;
+    for (int l = 0; l < NetCov::NE; ++l)
+        if (c.enc[l].w != CovOff::enc_w(l) || c.enc[l].b != CovOff::enc_b(l)) return false;
+    for (int j = 0; j < NetCov::DN; ++j)
+        if (c.flow_off[j] != CovOff::flow(j)) return false;
+    for (int k = 0; k < NetCov::K; ++k)
+        for (int l = 0; l < NetCov::ND; ++l)
+            if (c.dec[k][l].w != CovOff::dec_w(k, l) || c.dec[k][l].b != CovOff::dec_b(k, l)) return false;
+    return true;
+}
+
+static int g_fixed_const = 1;
+void set_tab_fixed_const(int on) { g_fixed_const = on; }
+
 // returns true when one of the fixed networks matched and its kernel was launched
 bool launch_tab_fixed(const TabArgs& a, unsigned blocks, size_t smem, cudaStream_t s) {
+    if (g_fixed_const && shape_is<NetCov>(a.c) && cov_canonical(a.c) &&
+        cudaMemcpyToSymbolAsync(c_tabfix, a.params, sizeof(float) * a.c.n_params, 0, cudaMemcpyDeviceToDevice, s) == cudaSuccess) {
+        tab_fixed_kernel<NetCov, true><<<blocks, TAB_THREADS, smem, s>>>(a);
+        return true;
+    }
     if (shape_is<NetLoan>(a.c)) tab_fixed_kernel<NetLoan><<<blocks, TAB_THREADS, smem, s>>>(a);
     else if (shape_is<NetAdult>(a.c)) tab_fixed_kernel<NetAdult><<<blocks, TAB_THREADS, smem, s>>>(a);
     else if (shape_is<NetCov>(a.c)) tab_fixed_kernel<NetCov><<<blocks, TAB_THREADS, smem, s>>>(a);

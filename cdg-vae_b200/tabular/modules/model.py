@@ -20,13 +20,13 @@ from ...modules.model import InvertiblePriorLinear, PlanarFlows  # noqa: F401  (
 class _TabularBase(ArenaModule):
     # The whole step is three short launches (step kernel, Adam, log row).  For loan / adult the step kernel runs ~0.12 ms
     # at 2^20 rows and the host-side launch sequence is as long again, so the step is replayed as a CUDA graph up to 2^22
-    # rows (copying the batch into the graph's static buffers costs ~15 us at 2^20 rows): 4.4 -> 6.3 G rows/s.  covtype and
-    # CDG-TVAE are GPU-bound from ~2^17 / 2^14 rows, where the extra copy only costs.
+    # rows (copying the batch into the graph's static buffers costs ~15 us at 2^20 rows): 4.4 -> 6.3 G rows/s.  covtype (0.24 ms per
+    # 2^20 rows since the constant-parameter kernel) is replayed up to 2^21 rows; CDG-TVAE is GPU-bound from ~2^14 rows.
     @property
     def GRAPH_MAX_ROWS(self):
         if getattr(self, "sigma", None) is not None:
             return 1 << 14
-        return (1 << 22) if self.config.get("dataset") in ("loan", "adult") else (1 << 17)
+        return (1 << 22) if self.config.get("dataset") in ("loan", "adult") else (1 << 21)
 
     KIND = None
     ENC_IDX = DEC_IDX = ()

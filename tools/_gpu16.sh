@@ -1,0 +1,5 @@
+set -x
+timeout 600 python -m pytest tests/test_routes_gpu.py tests/test_tabular_gpu.py tests/test_fullsize_properties_gpu.py tests/test_free_running_gpu.py -q 2>&1 | tail -12 > gpurun_out/tab_pytest.log
+timeout 300 python tools/tabular_bench.py > gpurun_out/tab_bench_1m.log 2>&1
+timeout 300 python tools/tabular_bench.py 4194304 > gpurun_out/tab_bench_4m.log 2>&1
+tail -12 gpurun_out/tab_pytest.log
