@@ -118,11 +118,13 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ delta, int 
         for (int ib = 0; ib < IN; ib += PI) {
             const int i0 = ib + ig * TI;
             if (o0 < OUT && i0 < IN) {
-                float acc[TO][TI];
+                float acc[TO][TI], bsum[TO];
 #pragma unroll
-                for (int a = 0; a < TO; ++a)
+                for (int a = 0; a < TO; ++a) {
+                    bsum[a] = 0.f;
 #pragma unroll
                     for (int j = 0; j < TI; ++j) acc[a][j] = 0.f;
+                }
                 const float* dp = delta + o0 * 32;
                 const float* hp = hin + i0 * 32;
 #pragma unroll
@@ -130,7 +132,10 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ delta, int 
                     const int q = ((it + lane) & 7) * 4;
                     float4 dv[TO];
 #pragma unroll
-                    for (int a = 0; a < TO; ++a) dv[a] = ld4(dp + a * 32 + q);
+                    for (int a = 0; a < TO; ++a) {
+                        dv[a] = ld4(dp + a * 32 + q);
+                        bsum[a] += (dv[a].x + dv[a].y) + (dv[a].z + dv[a].w);     // the bias gradient rides along (used by i0 == 0)
+                    }
 #pragma unroll
                     for (int j = 0; j < TI; ++j) {
                         const float4 h = ld4(hp + j * 32 + q);
@@ -139,21 +144,14 @@ __device__ __forceinline__ void warp_wgrad(const float* __restrict__ delta, int 
                     }
                 }
 #pragma unroll
-                for (int a = 0; a < TO; ++a)
+                for (int a = 0; a < TO; ++a) {
 #pragma unroll
                     for (int j = 0; j < TI; ++j)
                         if (o0 + a < OUT && i0 + j < IN) atomicAdd(sgw + (o0 + a) * ldg + i0 + j, acc[a][j]);
+                    if (i0 == 0 && o0 + a < OUT) atomicAdd(sgb + o0 + a, bsum[a]);
+                }
             }
         }
-    }
-    for (int o = lane; o < OUT; o += 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const float4 v = ld4(delta + o * 32 + ((it + lane) & 7) * 4);
-            s += (v.x + v.y) + (v.z + v.w);
-        }
-        atomicAdd(sgb + o, s);
     }
 }
 
@@ -357,13 +355,13 @@ __global__ void __launch_bounds__(256, 1) tvae_tile_kernel(TabArgs a, int wt_tot
                 warp_wgrad<0, TT_D3>(XH, m, A3, TT_D3, sg + L3.w, TT_D3, sg + L3.b);
                 warp_gemm<1, false>(XH, m, sp + L3.w, TT_D3, nullptr, A3, TT_D3);
                 __syncwarp();
-                warp_wgrad<TT_D3, TT_D2>(A3, TT_D3, A2, TT_D2, sg + L2.w, TT_D2, sg + L2.b);
+                warp_wgrad<TT_D3, TT_D2, 2, 2, 8>(A3, TT_D3, A2, TT_D2, sg + L2.w, TT_D2, sg + L2.b);
                 warp_gemm<1, false, TT_D3>(A3, TT_D3, sp + L2.w, TT_D2, nullptr, A2, TT_D2);
                 __syncwarp();
-                warp_wgrad<TT_D2, TT_D1>(A2, TT_D2, A1, TT_D1, sg + L1.w, TT_D1, sg + L1.b);
+                warp_wgrad<TT_D2, TT_D1, 1, 2, 8>(A2, TT_D2, A1, TT_D1, sg + L1.w, TT_D1, sg + L1.b);
                 warp_gemm<1, false, TT_D2>(A2, TT_D2, sp + L1.w, TT_D1, nullptr, A1, TT_D1);
                 __syncwarp();
-                warp_wgrad<TT_D1, 1>(A1, TT_D1, Z + k * 32, 1, sg + L0.w, 1, sg + L0.b);
+                warp_wgrad<TT_D1, 1, 1, 1, 8>(A1, TT_D1, Z + k * 32, 1, sg + L0.w, 1, sg + L0.b);
                 float gz = 0.f;
 #pragma unroll
                 for (int o = 0; o < TT_D1; ++o) gz = fmaf(A1[o * 32 + lane], sp[L0.w + o], gz);
