@@ -24,7 +24,10 @@ class OneShot:
         import torch.distributed._symmetric_memory as symm
         g = dist.group.WORLD
         try:
-            symm.enable_symm_mem_for_group(g.group_name)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm.enable_symm_mem_for_group(g.group_name)
         except Exception:
             pass
         self.buf = symm.empty(2 * self.MAX_FLOATS + 64, dtype=torch.float32, device=device)

@@ -35,7 +35,7 @@ def main():
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     noise = torch.randn(batch, 6, device=dev)
     model.noise_fn = lambda b, d: noise
-    train_CDGVAE([(x, y)] * 3, model, cfg, opt, dev)
+    train_CDGVAE([(x, y)] * 6, model, cfg, opt, dev)
     torch.cuda.synchronize()
     n0 = _lib.lib().cdg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

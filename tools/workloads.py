@@ -131,7 +131,7 @@ def tvae(c, kind="loan", rows=1 << 20, steps=10, warm=4, cpu=True):
                    cpu_r, logs["loss"][-1])
 
 
-def celeba(c, batch=16, steps=10, warm=3, cpu=True):
+def celeba(c, batch=16, steps=10, warm=6, cpu=True):
     """BASELINE configs[4]: CelebA-shaped CDG-VAE, the reference's batch 16 per GPU (celeba/main.py:70)."""
     from cdgvae_b200.celeba.module.model import CDGVAE
     from cdgvae_b200.celeba.module.train import train_CDGVAE
