@@ -646,6 +646,7 @@ struct cdg_celeba_plan {
     }
 };
 
+constexpr int kGenSmBudget = 24;           // split-K occupancy target per GEMM while the five generator chains run side by side (148: 12.5 ms, 74: 11.7, 24: 11.4 at batch 16)
 static int g_generator_streams = 7;        // bit 0: forward chains, bit 1: input-gradient chains, bit 2: weight preparation beside the encoder
 extern "C" void cdg_celeba_generator_streams(int32_t on) { g_generator_streams = on; }
 
@@ -668,6 +669,8 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
         CDG_CHECK_CUDA(cudaMemsetAsync(lacc, 0, sizeof(double) * CACC_LEN, cx.s));
         if (io->backward) CDG_CHECK_CUDA(cudaMemsetAsync(io->grads, 0, sizeof(float) * c.n_params, cx.s));
     }
+    const int budget = (g_generator_streams >> 8) > 0 ? (g_generator_streams >> 8) : kGenSmBudget;
+    struct BudgetGuard { ~BudgetGuard() { gemm_tc_set_sm_budget(0); } } budget_guard;
     const bool conc_prep = conc && (g_generator_streams & 4), conc_fwd = conc && (g_generator_streams & 1);
     const bool conc_bwd = conc && (g_generator_streams & 2);
     if (conc_prep) {
@@ -710,6 +713,7 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
     static thread_local GenRun runs[kNGen];
     ReconArgs ra{};
     if (conc_fwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_fork[1], main_s));
+    if (conc_fwd) gemm_tc_set_sm_budget(budget);
     for (int k = 0; k < kNGen; ++k) {
         runs[k] = GenRun();
         if (conc_fwd) cx.s = p->gs[k];
@@ -723,6 +727,7 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
         ra.gpre[k] = io->backward ? cx.ws.take<float>(M * 3) : nullptr;
     }
     cx.s = main_s; cx.col = main_col;
+    gemm_tc_set_sm_budget(0);
     if (conc_fwd)
         for (int k = 0; k < kNGen; ++k) CDG_CHECK_CUDA(cudaStreamWaitEvent(main_s, p->ev_join[0][k], 0));
     ra.masks = io->masks; ra.x = io->x; ra.ld_x = io->ld_x; ra.xhat = io->xhat; ra.sep = io->xhat_separated;
@@ -737,6 +742,7 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
     }
     if (!io->backward) return CDG_OK;
     if (conc_bwd) CDG_CHECK_CUDA(cudaEventRecord(p->ev_fork[2], main_s));
+    if (conc_bwd) gemm_tc_set_sm_budget(budget);
     for (int k = 0; k < kNGen; ++k) {
         if (conc_bwd) {
             cx.s = p->gs[k];
@@ -748,6 +754,7 @@ static int celeba_pass(cdg_celeba_plan* p, const cdg_celeba_io* io, Cx& cx) {
         la.gzin[k] = gzin[k];
     }
     cx.s = main_s; cx.col = main_col;
+    gemm_tc_set_sm_budget(0);
     if (conc_bwd)
         for (int k = 0; k < kNGen; ++k) CDG_CHECK_CUDA(cudaStreamWaitEvent(main_s, p->ev_join[1][k], 0));
     la.g_h = cx.ws.take<float>(B * ldh);

@@ -123,6 +123,10 @@ struct Profiler {
     }
 };
 
+// split-K occupancy target of the tcgen05 GEMM planner for the calling thread (gemm_tc.cu): a caller that runs several
+// independent chains on streams of its own asks each small GEMM to fill only its share of the chip
+void gemm_tc_set_sm_budget(int sms);
+
 // ---- generic strided GEMM interface (implemented in gemm_simt.cu / gemm_tc.cu) ----
 struct GemmDesc {
     const float* A; int64_t sa_m, sa_k;

@@ -1296,6 +1296,9 @@ static bool no160() {
     return v != 0;
 }
 // shape / layout analysis shared by gemm_tc and gemm_tc_can
+static thread_local int g_sm_budget = kNumSMs;
+void gemm_tc_set_sm_budget(int sms) { g_sm_budget = sms > 0 && sms < kNumSMs ? sms : kNumSMs; }
+
 static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     using namespace tc;
     GemmDesc g = g0;
@@ -1340,8 +1343,9 @@ static int plan_gemm(const GemmDesc& g0, int BK, Plan* pl) {
     const int KB_CAP = 2048 / BK;
     int splits = (kb_total + KB_CAP - 1) / KB_CAP;
     const int64_t tiles = tm * tn;
-    if (tiles * splits < kNumSMs && kb_total >= 8 && g.epi != EPI_RECON) {
-        int want = (int)imin64((kNumSMs + tiles - 1) / tiles, kb_total / 4);
+    const int64_t sms = g_sm_budget;       // 148, or the share of the chip a caller running several chains side by side wants per GEMM
+    if (tiles * splits < sms && kb_total >= 8 && g.epi != EPI_RECON) {
+        int want = (int)imin64((sms + tiles - 1) / tiles, kb_total / 4);
         splits = (int)imax64(splits, imin64(want, 64));
     }
     if (splits < 1) splits = 1;

@@ -30,6 +30,8 @@ def main():
                    (torch.rand(batch, 128, 128, 5, device=dev, generator=g) < 0.5).float()], -1)
     y = (torch.rand(batch, 6, device=dev, generator=g) < 0.5).float()
     B = torch.zeros(6, 6); B[0, 2] = B[0, 3] = B[0, 5] = 1; B[0, 4] = B[1, 4] = 0.5
+    if os.environ.get("CDG_CELEBA_STREAMS"):
+        _lib.lib().cdg_celeba_generator_streams(int(os.environ["CDG_CELEBA_STREAMS"]))
     torch.manual_seed(1)
     model = CDGVAE(B, torch.split(x[..., 3:], 1, dim=-1), cfg, dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
