@@ -346,7 +346,7 @@ typedef struct {
 int cdg_celeba_step(cdg_celeba_plan* p, const cdg_celeba_io* io, void* stream);
 /* The five generators of a step run on five internal streams forked from / joined to `stream` with events (default 1);
  * 0 enqueues everything on `stream` alone.  Bits 8 and up, when non-zero, override the number of SMs a small GEMM of a generator
- * chain is split to fill while the chains run side by side (default 24).  The workspace layout does not depend on this switch. */
+ * chain is split to fill while the chains run side by side (default 148; lower is faster and less accurate).  The workspace layout does not depend on this switch. */
 void cdg_celeba_generator_streams(int32_t on);
 
 /* Single layers of that path, exposed for unit tests against torch (tests/test_celeba_gpu.py):
