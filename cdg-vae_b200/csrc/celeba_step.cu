@@ -648,7 +648,7 @@ struct cdg_celeba_plan {
 
 // Split-K occupancy target per GEMM while the five generator chains run side by side.  A lower target is faster (148: 12.5 ms,
 // 74: 11.7, 24: 11.4 at batch 16) but means longer TMEM accumulations, whose truncating fp32 adds this step amplifies: the fc
-// gradient's error against the fp64 oracle grows 0.0018 -> 0.0026 -> 0.0042 (batch 2, step 1) and the golden test's second step
+// gradient's error against an fp64 evaluation grows 0.0018 -> 0.0026 -> 0.0042 (batch 2, step 1) and the golden test's second step
 // crossed its 1e-2 bound in 3 runs of 6 at 24.  Parity first: the default keeps the single-chain split (148).
 constexpr int kGenSmBudget = kNumSMs;
 static int g_generator_streams = 7;        // bit 0: forward chains, bit 1: input-gradient chains, bit 2: weight preparation beside the encoder
