@@ -14,7 +14,6 @@
 // on DIFFERENT streams of one process must use the shared-memory kernels (cdg_tabular_const_params(0)).
 #include "latent.cuh"
 #include "tabular_args.cuh"
-#include <cstdlib>
 
 namespace cdg {
 
@@ -363,19 +362,14 @@ bool launch_tab_const(const TabArgs& a, cudaStream_t s) {
     if (!loan && !adult) return false;
     if (cudaMemcpyToSymbolAsync(c_tab, a.params, sizeof(float) * a.c.n_params, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
         return false;
-    // rows per thread: enough to amortise the final reduction (~500 instructions), few enough to fill the machine
-    static const int minb = getenv("CDG_TAB_MINB") ? atoi(getenv("CDG_TAB_MINB")) : 2;
+    // rows per thread: enough to amortise the final reduction (~500 instructions), few enough to fill the machine; two blocks
+    // of 255-register threads per SM (three with 168 registers spilled and measured no faster)
     int64_t blocks = (a.batch + (int64_t)TAB_THREADS * 8 - 1) / ((int64_t)TAB_THREADS * 8);
-    const int64_t cap = (int64_t)kNumSMs * minb;
+    const int64_t cap = (int64_t)kNumSMs * 2;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (minb == 3) {
-        if (loan) tab_const_kernel<CDG_TAB_LOAN, 3><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
-        else tab_const_kernel<CDG_TAB_ADULT, 3><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
-    } else {
-        if (loan) tab_const_kernel<CDG_TAB_LOAN, 2><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
-        else tab_const_kernel<CDG_TAB_ADULT, 2><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
-    }
+    if (loan) tab_const_kernel<CDG_TAB_LOAN, 2><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
+    else tab_const_kernel<CDG_TAB_ADULT, 2><<<(unsigned)blocks, TAB_THREADS, 0, s>>>(a);
     return true;
 }
 
