@@ -68,7 +68,7 @@ __device__ __forceinline__ void warp_gemm(const float* __restrict__ in, int Krt,
             for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
         const float* ip = in + rg * 4;
         const float* wp = W + o0;
-#pragma unroll(KT > 0 ? KT : 4)
+#pragma unroll 4
         for (int i = 0; i < K; ++i) {
             const float4 a = ld4(ip + i * 32);
             const float4 w = ld4(wp + i * ldw);

@@ -14,6 +14,12 @@ if kind == "tvae":
     model = M.TVAE(Bm, mask, cfg, "cpu").to("cuda"); opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
     x, y, nz = orc.synth_tvae("loan", n)
     run = lambda data: T.train_TVAE([[Span(*s) for s in col] for col in oil], None, data, model, cfg, opt, "cuda")
+elif kind == "covtype":
+    cfg = dict(dataset="covtype", scm="linear", flow_num=1, inverse_loop=100, lr=0.01, beta=0.01, node=6, factor=[1] * 6, input_dim=8)
+    cfg["lambda"] = 10.0
+    model = M.CDGVAE(orc.tabular_B("covtype"), [1, 1, 2, 1, 1, 8], cfg, "cpu").to("cuda"); opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    x, y, nz = orc.synth_tabular("covtype", n)
+    run = lambda data: T.train_CDGVAE(DS(None), data, model, cfg, opt, "cuda")
 else:
     cfg = dict(dataset="adult", scm="linear", flow_num=1, inverse_loop=100, lr=0.01, beta=0.01, node=3, factor=[1, 1, 1], input_dim=5)
     cfg["lambda"] = 10.0
