@@ -13,6 +13,9 @@ from cdgvae_b200.tabular.modules import model as M, train as T  # noqa: E402
 from oracle import cdgvae_oracle as orc  # noqa: E402
 
 ROWS = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+if os.environ.get("CDG_TVAE_ROUTE"):                       # 1 = FFMA tiles (default), 2 = mma.sync fragments, 0 = one row per thread
+    from cdgvae_b200 import _lib as _L
+    _L.lib().cdg_tabular_tvae_tile(int(os.environ["CDG_TVAE_ROUTE"]))
 STEPS = 10
 DS = namedtuple("DS", ["flatten_topology"])
 Span = namedtuple("SpanInfo", ["dim", "activation_fn"])
