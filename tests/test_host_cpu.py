@@ -250,3 +250,36 @@ def test_last_batch_detection_counts_sized_loaders_and_reads_ahead_otherwise():
             return iter([1, 2])
     assert list(_lookahead(LyingLen())) == [(1, False), (2, True)]
     assert DevicePrefetcher([1, 2], "cuda").exact_len and not DevicePrefetcher((x for x in [1]), "cuda").exact_len
+
+
+def test_tabular_arena_layout_is_the_one_the_constant_parameter_kernels_expect():
+    """tabular_const.cu (loan / adult) and tab_fixed_kernel<NetCov, CP> address every weight by a compile-time offset into
+    the arena and fall back to the slower shared-memory kernels when a model's layout differs.  The drop-in models must
+    therefore keep producing exactly that layout (one or two 32-float slots per tensor, registration order): a silent change
+    in ArenaModule would cost a factor of 1.5 - 3 without failing any parity test."""
+    import synthetic_inputs as syn
+    from cdgvae_b200.tabular.modules import model as M
+    for name, mask in (("loan", [2, 2, 1]), ("adult", [1, 1, 3])):
+        cfg = dict(dataset=name, scm="linear", flow_num=1, inverse_loop=100, lr=0.01, beta=0.01, node=3, factor=[1] * 3, input_dim=5)
+        cfg["lambda"] = 10.0
+        m = M.CDGVAE(syn.tabular_B(name), mask, cfg, "cpu")
+        o = m._offsets
+        assert m._n_params == 608                                              # TNet::NPARAMS
+        assert [o["encoder.0.weight"], o["encoder.0.bias"], o["encoder.2.weight"], o["encoder.2.bias"]] == [0, 32, 64, 96]
+        assert [o[f"flows.{j}.p"] for j in range(3)] == [128, 160, 192]         # TNet::flow(j)
+        for k in range(3):                                                     # TNet::dw / db
+            base = 224 + 128 * k
+            assert [o[f"decoder.{k}.0.weight"], o[f"decoder.{k}.0.bias"], o[f"decoder.{k}.2.weight"], o[f"decoder.{k}.2.bias"]] == \
+                [base, base + 32, base + 64, base + 96]
+    cfg = dict(dataset="covtype", scm="linear", flow_num=1, inverse_loop=100, lr=0.01, beta=0.01, node=6, factor=[1] * 6, input_dim=8)
+    cfg["lambda"] = 10.0
+    m = M.CDGVAE(syn.tabular_B("covtype"), [1, 1, 2, 1, 1, 8], cfg, "cpu")
+    o = m._offsets
+    assert m._n_params == 1920                                                  # CovOff::NPARAMS
+    assert [o[f"encoder.{i}.weight"] for i in (0, 2, 4, 6)] == [0, 64, 128, 192]  # CovOff::enc_w
+    assert [o[f"encoder.{i}.bias"] for i in (0, 2, 4, 6)] == [32, 96, 160, 256]   # CovOff::enc_b
+    assert [o[f"flows.{j}.p"] for j in range(6)] == [288 + 32 * j for j in range(6)]
+    for k in range(6):                                                          # CovOff::dec_w / dec_b (the 7th decoder is never trained)
+        for l, idx in enumerate((0, 2, 4)):
+            assert o[f"decoder.{k}.{idx}.weight"] == 480 + 192 * k + 64 * l
+            assert o[f"decoder.{k}.{idx}.bias"] == 480 + 192 * k + 64 * l + 32
